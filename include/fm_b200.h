@@ -1,0 +1,132 @@
+/*
+ * fm_b200.h -- C ABI of the B200-native Fast Marching replacement
+ * (libfm_b200.so, built from planning_motion_planning_b200/csrc/ for sm_100a).
+ *
+ * This is the drop-in boundary for the ONE hot path of
+ * esa-prl/planning-motion_planning: the Eikonal solve of src/FastMarching and the
+ * gradient-descent path extraction over its result.  Each entry point names the
+ * reference interface it replaces (paths relative to the reference repo):
+ *
+ *   fmb_solve2d_*        src/FastMarching/FastMarching.py:92-112   computeTmap (full field)
+ *                        src/FastMarching/FastMarching.py:114-162  biComputeTmap (two solves, nq = 2)
+ *                        src/FastMarching/FastMarching.py:17-29,44-80  getEikonal / updateNode
+ *   fmb_solve3d_*        src/FastMarching/FastMarching3D.py:126-145 computeTmap
+ *                        src/FastMarching/FastMarching3D.py:19-101  updateNode (descending-dimension solver)
+ *   fmb_trace2d_*        src/FastMarching/FastMarching.py:164-236  getPathGDM
+ *                        src/FastMarching/FastMarching.py:242-338  computeGradient / interpolatePoint
+ *   fmb_trace3d_*        src/FastMarching/FastMarching3D.py:198-314 getPathGDM / interpolatePoint
+ *   fmb_truncate2d_* /   the early-exit semantics of the reference loops
+ *   fmb_truncate3d_*     (FastMarching.py:108-109,150-155; FastMarching3D.py:141-142):
+ *                        turn full fields into the partial fields the reference returns
+ *
+ * Conventions
+ *  - Plain C, no torch types.  Every data pointer is a DEVICE pointer on the
+ *    current CUDA device (e.g. torch.Tensor.data_ptr()); `stream` is a
+ *    cudaStream_t passed as void* (0 = legacy default stream).
+ *  - Arrays are indexed [y][x] (2D) / [y][x][z] (3D, z contiguous) exactly like the
+ *    reference's NumPy arrays; nodes are [x,y] / [x,y,z] (reference convention).
+ *    `pitch` arguments are row strides in ELEMENTS; `qstride` is the element
+ *    stride between consecutive queries of a batch (0 = all queries share it).
+ *  - All calls are asynchronous on `stream` unless stated; they never allocate
+ *    device memory: the caller supplies a workspace of fmb_workspace_bytes_*().
+ *  - Return value: 0 = ok, nonzero = FMB_E_* ; fmb_last_error() (thread local)
+ *    gives a message.  Device-side failures (watchdog, step cap) are reported by
+ *    fmb_finish(), which synchronises the stream.
+ *  - There is NO CPU fallback anywhere behind this interface.
+ */
+#ifndef FM_B200_H
+#define FM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FMB_OK 0
+#define FMB_E_INVALID 1       /* bad argument */
+#define FMB_E_CUDA 2          /* CUDA runtime error */
+#define FMB_E_WORKSPACE 3     /* workspace too small */
+#define FMB_E_WATCHDOG 4      /* device-side watchdog fired (would have hung) */
+#define FMB_E_STEPCAP 5       /* in-tile iteration cap exceeded */
+#define FMB_E_NOJOIN 6        /* bi-solve: fronts never meet (reference raises NameError) */
+
+/* tracer status per path (observable behaviour of the reference's getPathGDM) */
+#define FMB_TRACE_OK 0          /* `end` appended, normal return */
+#define FMB_TRACE_EARLY 1       /* 2D NaN fallback: bare `except` returns the path so far (FastMarching.py:217-218) */
+#define FMB_TRACE_VALUEERROR 2  /* NaN waypoint: reference raises ValueError */
+#define FMB_TRACE_INDEXERROR 3  /* stencil left the array: reference raises IndexError */
+#define FMB_TRACE_OVERFLOW 4    /* inf waypoint: reference raises OverflowError */
+
+/* solver counters, filled by fmb_finish() */
+typedef struct fmb_stats {
+    uint64_t tile_visits;   /* tile activations processed */
+    uint64_t steps;         /* lock-step iterations summed over visits */
+    uint64_t evals;         /* local-solver evaluations (getEikonal / 3D quadratic) */
+    uint64_t pushes;        /* work-queue pushes */
+    uint64_t cells_written; /* T values stored to HBM */
+    uint64_t reserved[3];
+} fmb_stats;
+
+int fmb_version(void);
+const char *fmb_last_error(void);
+/* number of SMs of the current device (grid sizing / reporting) */
+int fmb_sm_count(void);
+
+/* ---- 2D Eikonal solve (full field per query) ------------------------------
+ * nq independent queries of identical shape rows x cols.
+ *   d_cost   cost map(s); +inf = obstacle; out-of-domain is treated as +inf
+ *   d_T      output field(s); fully overwritten (unreached cells = +inf)
+ *   d_seeds  int32 [nq][2] = [x,y] of the source (T = 0) of each query
+ *   d_ws     workspace of at least fmb_workspace_bytes_2d(rows, cols, nq) bytes
+ */
+size_t fmb_workspace_bytes_2d(int rows, int cols, int nq);
+int fmb_solve2d_f64(const double *d_cost, int64_t cost_pitch, int64_t cost_qstride,
+                    double *d_T, int64_t T_pitch, int64_t T_qstride,
+                    int rows, int cols, int nq, const int32_t *d_seeds,
+                    void *d_ws, size_t ws_bytes, void *stream);
+int fmb_solve2d_f32(const float *d_cost, int64_t cost_pitch, int64_t cost_qstride,
+                    float *d_T, int64_t T_pitch, int64_t T_qstride,
+                    int rows, int cols, int nq, const int32_t *d_seeds,
+                    void *d_ws, size_t ws_bytes, void *stream);
+
+/* ---- 3D Eikonal solve ------------------------------------------------------
+ * volumes are [ny][nx][nz] with z contiguous; pitches: elements between
+ * consecutive x (pitch_x >= nz) and consecutive y (pitch_y >= nx*pitch_x).
+ * d_seeds int32 [nq][3] = [x,y,z].
+ */
+size_t fmb_workspace_bytes_3d(int ny, int nx, int nz, int nq);
+int fmb_solve3d_f64(const double *d_cost, int64_t cost_qstride, double *d_T, int64_t T_qstride,
+                    int ny, int nx, int nz, int nq, const int32_t *d_seeds,
+                    void *d_ws, size_t ws_bytes, void *stream);
+int fmb_solve3d_f32(const float *d_cost, int64_t cost_qstride, float *d_T, int64_t T_qstride,
+                    int ny, int nx, int nz, int nq, const int32_t *d_seeds,
+                    void *d_ws, size_t ws_bytes, void *stream);
+
+/* Synchronise `stream`, report device-side failures of the solves issued with
+ * this workspace, and (optionally) return the counters.  Synchronous. */
+int fmb_finish(void *d_ws, size_t ws_bytes, void *stream, fmb_stats *stats_or_null);
+
+/* ---- gradient-descent path extraction --------------------------------------
+ * npaths paths; path p walks field  d_T + field_of_path[p]*T_qstride
+ * (field_of_path == NULL: p itself).
+ *   d_init, d_end  double [npaths][D] waypoints in cell units, [x,y(,z)]
+ *   d_out          double [npaths][cap][D]; first row = init
+ *   d_count        int32  [npaths] rows written
+ *   d_status       int32  [npaths] FMB_TRACE_*
+ * max_steps = round(15000/tau) reproduces the reference; cap >= max_steps + 2.
+ */
+int fmb_trace2d_f64(const double *d_T, int64_t T_pitch, int64_t T_qstride, int rows, int cols,
+                    int npaths, const int32_t *d_field_of_path,
+                    const double *d_init, const double *d_end, double tau, int max_steps,
+                    double *d_out, int64_t cap, int32_t *d_count, int32_t *d_status, void *stream);
+int fmb_trace3d_f64(const double *d_T, int64_t T_qstride, int ny, int nx, int nz,
+                    int npaths, const int32_t *d_field_of_path,
+                    const double *d_init, const double *d_end, double tau, int max_steps,
+                    double *d_out, int64_t cap, int32_t *d_count, int32_t *d_status, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FM_B200_H */

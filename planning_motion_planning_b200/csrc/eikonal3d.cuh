@@ -1,0 +1,353 @@
+// eikonal3d.cuh -- 3D Eikonal solve (replaces FastMarching3D.py:19-101,126-145).
+//
+// Volumes are [ny][nx][nz] with z contiguous (the planner's layout,
+// Coupled_motion_planner.py:1627).  A tile is 4 (y) x 8 (x) x TZ (z) cells and
+// belongs to one warp: lane (ly*8 + lx) owns the z-column (ly, lx) and keeps a
+// TZ-bit mask of its armed cells, so z-rows are 128/256-byte coalesced in HBM and
+// the in-tile scheme is the 2D one with two more neighbour directions (x and y
+// neighbours are other lanes, reached by shuffle; z neighbours are mask bits).
+#pragma once
+#include "fm_common.cuh"
+
+namespace fmb {
+
+constexpr int T3Y = 4, T3X = 8;     // tile cross-section: 32 columns == 32 lanes
+
+template <typename real>
+struct Problem3D {
+    const real *cost;
+    long long cost_qstride;
+    real *T;
+    long long T_qstride;
+    int ny, nx, nz, nty, ntx, ntz, nq;
+    const int *seeds;        // [nq][3] = x,y,z
+    int *tile_state;
+    Queue q;
+    int step_cap;
+};
+
+// FastMarching3D.py:59-75 -- descending-dimension quadratic solver, in the
+// reference's operation order (Tarray = [Tx,Ty,Tz]; sumlist() is right-associated).
+template <typename real>
+__device__ __forceinline__ real solve3d_update(real t0, real t1, real t2, real C) {
+    using N = num<real>;
+    const real C2 = N::mul(C, C);
+    // ---- n = 3
+    {
+        int im = 0; real mx = t0;
+        if (t1 > mx) { mx = t1; im = 1; }
+        if (t2 > mx) { mx = t2; im = 2; }
+        real d0 = N::sub(mx, t0), d1 = N::sub(mx, t1), d2 = N::sub(mx, t2);
+        real sumT = N::add(N::add(N::mul(d0, d0), N::mul(d1, d1)), N::mul(d2, d2));
+        if (C2 > sumT) {
+            real S = N::add(t0, N::add(t1, t2));
+            real Q = N::add(N::mul(t0, t0), N::add(N::mul(t1, t1), N::mul(t2, t2)));
+            real disc = N::sub(N::add(N::mul((real)3, C2), N::mul(S, S)), N::mul((real)3, Q));
+            return N::div(N::add(S, N::sqrt(disc)), (real)3);
+        }
+        // Tarray.remove(Tmax): keep the other two in order
+        if (im == 0) { t0 = t1; t1 = t2; } else if (im == 1) { t1 = t2; }
+    }
+    // ---- n = 2
+    {
+        const bool first_is_max = !(t1 > t0);
+        const real mx = first_is_max ? t0 : t1;
+        real d0 = N::sub(mx, t0), d1 = N::sub(mx, t1);
+        real sumT = N::add(N::mul(d0, d0), N::mul(d1, d1));
+        if (C2 > sumT) {
+            real S = N::add(t0, t1);
+            real Q = N::add(N::mul(t0, t0), N::mul(t1, t1));
+            real disc = N::sub(N::add(N::mul((real)2, C2), N::mul(S, S)), N::mul((real)2, Q));
+            return N::mul(N::add(S, N::sqrt(disc)), (real)0.5);
+        }
+        if (first_is_max) t0 = t1;
+    }
+    // ---- n = 1
+    {
+        real d0 = N::sub(t0, t0);                     // NaN when t0 is +inf: the test below fails like the reference's
+        if (C2 > N::mul(d0, d0)) {
+            real disc = N::sub(N::add(C2, N::mul(t0, t0)), N::mul(t0, t0));
+            return N::add(t0, N::sqrt(disc));
+        }
+    }
+    return num<real>::inf();                          // no finite neighbour (reference: max([]) raises)
+}
+
+template <typename real, int TZ>
+struct Tile3D {
+    static constexpr int PZ = TZ + 2;                          // z pitch incl. halo
+    static constexpr int PS = (T3X + 2) * PZ;                  // y-slab pitch
+    static constexpr int T_ELEMS = (T3Y + 2) * PS;
+    static constexpr int C_ELEMS = T3Y * T3X * PZ;
+    static constexpr int WARP_ELEMS = T_ELEMS + C_ELEMS;
+    static constexpr size_t WARP_BYTES = sizeof(real) * WARP_ELEMS;
+    // element index of cell (y,x,z) with y in [-1,T3Y], x in [-1,T3X], z in [-1,TZ]
+    static __device__ __forceinline__ int at(int y, int x, int z) { return (y + 1) * PS + (x + 1) * PZ + z + 1; }
+};
+
+template <typename real>
+__global__ void init_fill3d_kernel(Problem3D<real> P, int ring_slots) {
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nth = (long long)gridDim.x * blockDim.x;
+    const real INF = num<real>::inf();
+    const long long per_q = (long long)P.ny * P.nx * P.nz;
+    for (int q = 0; q < P.nq; ++q) {
+        real *Tq = P.T + (long long)q * P.T_qstride;
+        for (long long i = tid; i < per_q; i += nth) Tq[i] = INF;
+    }
+    const long long ntiles = (long long)P.nq * P.nty * P.ntx * P.ntz;
+    for (long long i = tid; i < ntiles; i += nth) P.tile_state[i] = ST_IDLE;
+    for (long long i = tid; i < ring_slots; i += nth) P.q.ring[i] = -1;
+    if (tid == 0) { QueueCtl z = {}; *P.q.ctl = z; }
+}
+
+template <typename real, int TZ>
+__global__ void init_seed3d_kernel(Problem3D<real> P) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= P.nq) return;
+    const int sx = P.seeds[3 * q], sy = P.seeds[3 * q + 1], sz = P.seeds[3 * q + 2];
+    if (sx < 0 || sy < 0 || sz < 0 || sx >= P.nx || sy >= P.ny || sz >= P.nz) return;
+    P.T[(long long)q * P.T_qstride + ((long long)sy * P.nx + sx) * P.nz + sz] = (real)0;
+    const int tx = sx / T3X, ty = sy / T3Y, tz = sz / TZ;
+    const int base = q * P.nty * P.ntx * P.ntz;
+    // the seed's own tile and every face-neighbour tile that sees it in its halo
+    for (int k = 0; k < 7; ++k) {
+        int cx = tx, cy = ty, cz = tz;
+        bool ok = true;
+        switch (k) {
+            case 1: ok = (sx % T3X == 0) && tx > 0; cx = tx - 1; break;
+            case 2: ok = (sx % T3X == T3X - 1) && tx < P.ntx - 1; cx = tx + 1; break;
+            case 3: ok = (sy % T3Y == 0) && ty > 0; cy = ty - 1; break;
+            case 4: ok = (sy % T3Y == T3Y - 1) && ty < P.nty - 1; cy = ty + 1; break;
+            case 5: ok = (sz % TZ == 0) && tz > 0; cz = tz - 1; break;
+            case 6: ok = (sz % TZ == TZ - 1) && tz < P.ntz - 1; cz = tz + 1; break;
+            default: break;
+        }
+        if (!ok) continue;
+        const int item = base + (cy * P.ntx + cx) * P.ntz + cz;
+        if (tile_activate(P.tile_state, P.q.ctl, item)) { q_push(P.q, item); atomicAdd(&P.q.ctl->pushes, 1ULL); }
+    }
+}
+
+template <typename real, int TZ, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) solve3d_kernel(Problem3D<real> P) {
+    using TL = Tile3D<real, TZ>;
+    constexpr int PZ = TL::PZ, PS = TL::PS;
+    FMB_DYN_SMEM(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    real *sT = reinterpret_cast<real *>(smem_raw) + (size_t)warp * TL::WARP_ELEMS;
+    real *sC = sT + TL::T_ELEMS;
+    const real INF = num<real>::inf();
+    const int tiles_per_q = P.nty * P.ntx * P.ntz;
+    const int ly = lane >> 3, lx = lane & 7;          // my column
+    const long long sy_ = (long long)P.nx * P.nz, sx_ = P.nz;   // global strides
+
+    unsigned long long n_visits = 0, n_steps = 0, n_evals = 0, n_pushes = 0, n_written = 0;
+    int item = -1;
+
+    for (;;) {
+        if (item < 0) {
+            int it = -1;
+            if (lane == 0) it = q_pop_lane0(P.q);
+            item = __shfl_sync(FULL, it, 0);
+            if (item < 0) break;
+        }
+        const int q = item / tiles_per_q;
+        int t = item - q * tiles_per_q;
+        const int tz = t % P.ntz; t /= P.ntz;
+        const int tx = t % P.ntx; const int ty = t / P.ntx;
+        const int x0 = tx * T3X, y0 = ty * T3Y, z0 = tz * TZ;
+        const real *cq = P.cost + (long long)q * P.cost_qstride;
+        real *Tq = P.T + (long long)q * P.T_qstride;
+
+        if (lane == 0) { atomicExch(&P.tile_state[item], ST_RUNNING); __threadfence(); }
+        __syncwarp();
+
+        // ---- stage T: every (y,x) column of the haloed tile except the 4 corner columns,
+        //      z = z0 .. z0+TZ-1 across lanes (coalesced) -----------------------------
+        for (int c = 0; c < (T3Y + 2) * (T3X + 2); ++c) {
+            const int yy = c / (T3X + 2) - 1, xx = c % (T3X + 2) - 1;
+            const bool ycorner = (yy < 0 || yy >= T3Y), xcorner = (xx < 0 || xx >= T3X);
+            if (ycorner && xcorner) continue;
+            for (int zz = lane; zz < TZ; zz += 32) {
+                const int y = y0 + yy, x = x0 + xx, z = z0 + zz;
+                real v = INF;
+                if (y >= 0 && y < P.ny && x >= 0 && x < P.nx && z < P.nz) v = ld_T(&Tq[y * sy_ + x * sx_ + z]);
+                sT[TL::at(yy, xx, zz)] = v;
+            }
+        }
+        {   // z halos of my own column
+            const int y = y0 + ly, x = x0 + lx;
+            real lo = INF, hi = INF;
+            if (y < P.ny && x < P.nx) {
+                if (z0 > 0) lo = ld_T(&Tq[y * sy_ + x * sx_ + z0 - 1]);
+                if (z0 + TZ < P.nz) hi = ld_T(&Tq[y * sy_ + x * sx_ + z0 + TZ]);
+            }
+            sT[TL::at(ly, lx, -1)] = lo;
+            sT[TL::at(ly, lx, TZ)] = hi;
+        }
+        unsigned cmask = 0;
+        for (int c = 0; c < 32; ++c) {
+            const int yy = c >> 3, xx = c & 7;
+            unsigned b = 0;
+            for (int zz = lane; zz < TZ; zz += 32) {      // executes once (TZ <= 32)
+                const int y = y0 + yy, x = x0 + xx, z = z0 + zz;
+                real cv = INF;
+                if (y < P.ny && x < P.nx && z < P.nz) cv = __ldg(&cq[y * sy_ + x * sx_ + z]);
+                sC[c * PZ + zz] = cv;
+            }
+            {
+                const int zz = lane;
+                const real cv = (zz < TZ) ? sC[c * PZ + zz] : INF;
+                b = __ballot_sync(FULL, zz < TZ && cv < INF);
+            }
+            if (lane == c) cmask = b;
+        }
+        __syncwarp();
+
+        // ---- arm the cells next to a lower halo value -------------------------
+        real *col = sT + TL::at(ly, lx, 0);          // col[k] = T(my column, z=k)
+        const real *colC = sC + lane * PZ;
+        unsigned mask = 0;
+        if (col[-1] < col[0]) mask |= 1u;
+        if (col[TZ] < col[TZ - 1]) mask |= 1u << (TZ - 1);
+        for (int c = 0; c < 32; ++c) {               // lateral faces, lane == z
+            const int yy = c >> 3, xx = c & 7;
+            const bool fxm = xx == 0, fxp = xx == T3X - 1, fym = yy == 0, fyp = yy == T3Y - 1;
+            if (!(fxm || fxp || fym || fyp)) continue;
+            const int zz = lane < TZ ? lane : 0;
+            const real own = sT[TL::at(yy, xx, zz)];
+            bool lower = false;
+            if (fxm) lower |= sT[TL::at(yy, xx - 1, zz)] < own;
+            if (fxp) lower |= sT[TL::at(yy, xx + 1, zz)] < own;
+            if (fym) lower |= sT[TL::at(yy - 1, xx, zz)] < own;
+            if (fyp) lower |= sT[TL::at(yy + 1, xx, zz)] < own;
+            const unsigned b = __ballot_sync(FULL, lane < TZ && lower);
+            if (lane == c) mask |= b;
+        }
+        {   // a source inside this tile arms its six neighbours
+            const int sx = P.seeds[3 * q] - x0, sy = P.seeds[3 * q + 1] - y0, sz = P.seeds[3 * q + 2] - z0;
+            if (sx >= 0 && sx < T3X && sy >= 0 && sy < T3Y && sz >= 0 && sz < TZ) {
+                if (lx == sx && ly == sy) {
+                    if (sz > 0) mask |= 1u << (sz - 1);
+                    if (sz < TZ - 1) mask |= 1u << (sz + 1);
+                }
+                if (ly == sy && (lx == sx - 1 || lx == sx + 1)) mask |= 1u << sz;
+                if (lx == sx && (ly == sy - 1 || ly == sy + 1)) mask |= 1u << sz;
+            }
+        }
+        mask &= cmask;
+
+        // ---- relax to the fixed point ---------------------------------------
+        unsigned dirty = 0;
+        int last = 0, dir = 1, steps = 0;
+        bool fail = false;
+        unsigned active;
+        while ((active = __ballot_sync(FULL, mask != 0)) != 0) {
+            int k = -1;
+            real v = INF, cur = INF, zm = INF, zp = INF, xm = INF, xp = INF, ym = INF, yp = INF;
+            if (mask) {
+                const unsigned hi = mask & (~0u << last);
+                const unsigned lo = mask & ((2u << last) - 1u);
+                if (dir > 0) {
+                    if (hi) k = __ffs(hi) - 1; else { k = 31 - __clz(lo); dir = -1; }
+                } else {
+                    if (lo) k = 31 - __clz(lo); else { k = __ffs(hi) - 1; dir = 1; }
+                }
+                last = k;
+                mask &= ~(1u << k);
+                const real *p = col + k;
+                zm = p[-1]; zp = p[1]; xm = p[-PZ]; xp = p[PZ]; ym = p[-PS]; yp = p[PS]; cur = p[0];
+                // FastMarching3D.py:44-57: per-axis minimum, Tarray = [Tx, Ty, Tz]
+                v = solve3d_update<real>(xm < xp ? xm : xp, ym < yp ? ym : yp, zm < zp ? zm : zp, colC[k]);
+            }
+            __syncwarp();
+            int m_xm = -1, m_xp = -1, m_ym = -1, m_yp = -1;
+            if (k >= 0 && v < cur) {
+                col[k] = v;
+                dirty |= 1u << k;
+                if (k > 0 && zm > v) mask |= 1u << (k - 1);
+                if (k < TZ - 1 && zp > v) mask |= 1u << (k + 1);
+                if (xm > v) m_xm = k;
+                if (xp > v) m_xp = k;
+                if (ym > v) m_ym = k;
+                if (yp > v) m_yp = k;
+            }
+            const int r_xp = __shfl_down_sync(FULL, m_xm, 1);   // my x+ neighbour improved and I am its x-
+            const int r_xm = __shfl_up_sync(FULL, m_xp, 1);
+            const int r_yp = __shfl_down_sync(FULL, m_ym, 8);
+            const int r_ym = __shfl_up_sync(FULL, m_yp, 8);
+            if (lx < T3X - 1 && r_xp >= 0) mask |= 1u << r_xp;
+            if (lx > 0 && r_xm >= 0) mask |= 1u << r_xm;
+            if (ly < T3Y - 1 && r_yp >= 0) mask |= 1u << r_yp;
+            if (ly > 0 && r_ym >= 0) mask |= 1u << r_ym;
+            mask &= cmask;
+            __syncwarp();
+            n_evals += __popc(active);
+            if (++steps > P.step_cap) { fail = true; break; }
+        }
+        n_steps += steps;
+        ++n_visits;
+        if (fail) {
+            if (lane == 0) atomicCAS(&P.q.ctl->abort, 0, DEV_STEPCAP);
+            break;
+        }
+
+        // ---- write back + face tests (lane == z) --------------------------------
+        bool f_xm = false, f_xp = false, f_ym = false, f_yp = false;
+        for (int c = 0; c < 32; ++c) {
+            const unsigned dj = __shfl_sync(FULL, dirty, c);
+            if (dj == 0) continue;
+            const int yy = c >> 3, xx = c & 7;
+            if (lane < TZ && ((dj >> lane) & 1u)) {
+                const real nv = sT[TL::at(yy, xx, lane)];
+                st_T(&Tq[(y0 + yy) * sy_ + (x0 + xx) * sx_ + z0 + lane], nv);
+                if (xx == 0 && nv < sT[TL::at(yy, -1, lane)]) f_xm = true;
+                if (xx == T3X - 1 && nv < sT[TL::at(yy, T3X, lane)]) f_xp = true;
+                if (yy == 0 && nv < sT[TL::at(-1, xx, lane)]) f_ym = true;
+                if (yy == T3Y - 1 && nv < sT[TL::at(T3Y, xx, lane)]) f_yp = true;
+            }
+            n_written += __popc(dj);
+        }
+        const bool f_zm = (dirty & 1u) && col[0] < col[-1];
+        const bool f_zp = ((dirty >> (TZ - 1)) & 1u) && col[TZ - 1] < col[TZ];
+        const bool a_zm = __any_sync(FULL, f_zm) && tz > 0;
+        const bool a_zp = __any_sync(FULL, f_zp) && tz < P.ntz - 1;
+        const bool a_xm = __any_sync(FULL, f_xm) && tx > 0;
+        const bool a_xp = __any_sync(FULL, f_xp) && tx < P.ntx - 1;
+        const bool a_ym = __any_sync(FULL, f_ym) && ty > 0;
+        const bool a_yp = __any_sync(FULL, f_yp) && ty < P.nty - 1;
+        __threadfence();
+        __syncwarp();
+        int next = -1;
+        if (lane == 0) {
+            __threadfence();
+            const int nbr[6] = {item - 1, item + 1, item - P.ntz, item + P.ntz, item - P.ntx * P.ntz, item + P.ntx * P.ntz};
+            const bool act[6] = {a_zm, a_zp, a_xm, a_xp, a_ym, a_yp};
+#pragma unroll
+            for (int s = 0; s < 6; ++s) {
+                if (!act[s]) continue;
+                if (tile_activate(P.tile_state, P.q.ctl, nbr[s])) {
+                    if (next < 0) next = nbr[s];
+                    else { q_push(P.q, nbr[s]); ++n_pushes; }
+                }
+            }
+            if (tile_finish(P.tile_state, P.q.ctl, item)) {
+                if (next < 0) next = item;
+                else { q_push(P.q, item); ++n_pushes; }
+            }
+            if (ld_volatile(&P.q.ctl->abort)) next = -2;
+        }
+        item = __shfl_sync(FULL, next, 0);
+        if (item == -2) break;
+    }
+    if (lane == 0) {
+        atomicAdd(&P.q.ctl->visits, n_visits);
+        atomicAdd(&P.q.ctl->steps, n_steps);
+        atomicAdd(&P.q.ctl->evals, n_evals);
+        atomicAdd(&P.q.ctl->pushes, n_pushes);
+        atomicAdd(&P.q.ctl->cells_written, n_written);
+    }
+}
+
+}  // namespace fmb

@@ -1,0 +1,196 @@
+// fm_capi.cu -- extern "C" boundary of libfm_b200.so (declared in include/fm_b200.h).
+//
+// Host side only launches kernels; no host-side numerics, no CPU fallback.
+#include "../../include/fm_b200.h"
+
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "eikonal2d.cuh"
+#include "eikonal3d.cuh"
+#include "trace2d.cuh"
+#include "trace3d.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, const char *detail = "") {
+    snprintf(g_err, sizeof(g_err), fmt, detail);
+    return code;
+}
+int cuda_fail(cudaError_t e, const char *where) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+    return FMB_E_CUDA;
+}
+#define CK(call, where) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(e_, where); } while (0)
+
+int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (!cached[dev]) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+unsigned pow2_at_least(long long v) {
+    unsigned p = 1024;
+    while ((long long)p < v && p < (1u << 30)) p <<= 1;
+    return p;
+}
+
+// workspace layout: [QueueCtl | pad to 256] [tile_state: ntiles ints] [ring: slots ints]
+struct WsLayout {
+    size_t ctl_off, state_off, ring_off, total;
+    unsigned ring_slots;
+};
+WsLayout ws_layout(long long ntiles) {
+    WsLayout L;
+    L.ctl_off = 0;
+    L.state_off = 256;
+    size_t st = ((size_t)ntiles * sizeof(int) + 255) & ~(size_t)255;
+    L.ring_off = L.state_off + st;
+    L.ring_slots = pow2_at_least(ntiles);
+    L.total = L.ring_off + (size_t)L.ring_slots * sizeof(int);
+    return L;
+}
+
+constexpr int MIN_TW = 16;       // workspace is sized for the narrowest tile so the tile width can be tuned at run time
+constexpr int WARPS = 4;         // worker warps per CTA of the persistent solver
+
+long long tiles2d(int rows, int cols, int tw) {
+    return (long long)((cols + tw - 1) / tw) * ((rows + fmb::TILE_H - 1) / fmb::TILE_H);
+}
+
+template <typename real, int TW>
+int launch_solve2d(fmb::Problem2D<real> P, const WsLayout &L, cudaStream_t st) {
+    using TL = fmb::Tile2D<real, TW>;
+    const size_t smem = TL::WARP_BYTES * WARPS;
+    auto kern = fmb::solve2d_kernel<real, TW, WARPS>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(solve2d)");
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem), "occupancy(solve2d)");
+    if (per_sm < 1) return fail(FMB_E_CUDA, "solve2d kernel does not fit on an SM%s");
+    const long long ntiles = (long long)P.nq * P.ntx * P.nty;
+    long long blocks = (long long)per_sm * sm_count();
+    const long long need = (ntiles + WARPS - 1) / WARPS;
+    if (blocks > need) blocks = need;
+    if (blocks < 1) blocks = 1;
+    const int cap_blocks = env_int("FMB_MAX_BLOCKS", 0);
+    if (cap_blocks > 0 && blocks > cap_blocks) blocks = cap_blocks;
+
+    const long long cells = (long long)P.rows * P.cols * P.nq;
+    long long fill_blocks = (cells + 256 * 8 - 1) / (256 * 8);
+    if (fill_blocks > (long long)sm_count() * 16) fill_blocks = (long long)sm_count() * 16;
+    if (fill_blocks < 1) fill_blocks = 1;
+    fmb::init_fill2d_kernel<real><<<(unsigned)fill_blocks, 256, 0, st>>>(P, (int)L.ring_slots);
+    fmb::init_seed2d_kernel<real, TW><<<(P.nq + 127) / 128, 128, 0, st>>>(P);
+    kern<<<(unsigned)blocks, WARPS * 32, smem, st>>>(P);
+    CK(cudaGetLastError(), "launch solve2d");
+    return FMB_OK;
+}
+
+template <typename real>
+int solve2d(const real *d_cost, int64_t cost_pitch, int64_t cost_qstride, real *d_T, int64_t T_pitch,
+            int64_t T_qstride, int rows, int cols, int nq, const int32_t *d_seeds, void *d_ws, size_t ws_bytes,
+            void *stream) {
+    if (!d_cost || !d_T || !d_seeds || !d_ws) return fail(FMB_E_INVALID, "null pointer argument%s");
+    if (rows < 1 || cols < 1 || nq < 1) return fail(FMB_E_INVALID, "rows, cols and nq must be positive%s");
+    if (cost_pitch < cols || T_pitch < cols) return fail(FMB_E_INVALID, "pitch smaller than cols%s");
+    int tw = env_int("FMB_TW2D", 32);
+    if (tw != 16 && tw != 32) return fail(FMB_E_INVALID, "FMB_TW2D must be 16 or 32%s");
+    const long long ntiles = tiles2d(rows, cols, tw) * nq;
+    if (ntiles >= (1LL << 30)) return fail(FMB_E_INVALID, "too many tiles for one launch%s");
+    if (ws_bytes < fmb_workspace_bytes_2d(rows, cols, nq)) return fail(FMB_E_WORKSPACE, "workspace too small%s");
+    WsLayout L = ws_layout(ntiles);
+    char *ws = (char *)d_ws;
+    fmb::Problem2D<real> P;
+    P.cost = d_cost; P.cost_pitch = cost_pitch; P.cost_qstride = cost_qstride;
+    P.T = d_T; P.T_pitch = T_pitch; P.T_qstride = T_qstride;
+    P.rows = rows; P.cols = cols; P.nq = nq;
+    P.ntx = (cols + tw - 1) / tw; P.nty = (rows + fmb::TILE_H - 1) / fmb::TILE_H;
+    P.seeds = d_seeds;
+    P.tile_state = (int *)(ws + L.state_off);
+    P.q.ctl = (fmb::QueueCtl *)(ws + L.ctl_off);
+    P.q.ring = (int *)(ws + L.ring_off);
+    P.q.ring_mask = L.ring_slots - 1;
+    P.q.watchdog_cycles = (long long)env_int("FMB_WATCHDOG_MS", 20000) * 2000000LL;   // ~2 GHz
+    P.step_cap = env_int("FMB_STEP_CAP", 1 << 20);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (tw == 16) return launch_solve2d<real, 16>(P, L, st);
+    return launch_solve2d<real, 32>(P, L, st);
+}
+
+}  // namespace
+
+extern "C" {
+
+int fmb_version(void) { return 100; }
+const char *fmb_last_error(void) { return g_err; }
+int fmb_sm_count(void) { return sm_count(); }
+
+size_t fmb_workspace_bytes_2d(int rows, int cols, int nq) {
+    if (rows < 1 || cols < 1 || nq < 1) return 0;
+    return ws_layout(tiles2d(rows, cols, MIN_TW) * nq).total;
+}
+
+int fmb_solve2d_f64(const double *d_cost, int64_t cost_pitch, int64_t cost_qstride, double *d_T, int64_t T_pitch,
+                    int64_t T_qstride, int rows, int cols, int nq, const int32_t *d_seeds, void *d_ws,
+                    size_t ws_bytes, void *stream) {
+    return solve2d<double>(d_cost, cost_pitch, cost_qstride, d_T, T_pitch, T_qstride, rows, cols, nq, d_seeds, d_ws,
+                           ws_bytes, stream);
+}
+int fmb_solve2d_f32(const float *d_cost, int64_t cost_pitch, int64_t cost_qstride, float *d_T, int64_t T_pitch,
+                    int64_t T_qstride, int rows, int cols, int nq, const int32_t *d_seeds, void *d_ws,
+                    size_t ws_bytes, void *stream) {
+    return solve2d<float>(d_cost, cost_pitch, cost_qstride, d_T, T_pitch, T_qstride, rows, cols, nq, d_seeds, d_ws,
+                          ws_bytes, stream);
+}
+
+int fmb_finish(void *d_ws, size_t ws_bytes, void *stream, fmb_stats *stats) {
+    if (!d_ws || ws_bytes < 256) return fail(FMB_E_INVALID, "bad workspace%s");
+    CK(cudaStreamSynchronize((cudaStream_t)stream), "cudaStreamSynchronize");
+    fmb::QueueCtl h;
+    CK(cudaMemcpy(&h, d_ws, sizeof(h), cudaMemcpyDeviceToHost), "cudaMemcpy(ctl)");
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        stats->tile_visits = h.visits; stats->steps = h.steps; stats->evals = h.evals;
+        stats->pushes = h.pushes; stats->cells_written = h.cells_written;
+    }
+    if (h.abort == fmb::DEV_WATCHDOG) return fail(FMB_E_WATCHDOG, "device watchdog fired: a queue wait exceeded FMB_WATCHDOG_MS%s");
+    if (h.abort == fmb::DEV_STEPCAP) return fail(FMB_E_STEPCAP, "in-tile iteration cap (FMB_STEP_CAP) exceeded%s");
+    if (h.abort) return fail(FMB_E_CUDA, "unknown device-side failure%s");
+    if (h.pending != 0) return fail(FMB_E_CUDA, "solver left with pending tiles%s");
+    return FMB_OK;
+}
+
+int fmb_trace2d_f64(const double *d_T, int64_t T_pitch, int64_t T_qstride, int rows, int cols, int npaths,
+                    const int32_t *d_field_of_path, const double *d_init, const double *d_end, double tau,
+                    int max_steps, double *d_out, int64_t cap, int32_t *d_count, int32_t *d_status, void *stream) {
+    if (!d_T || !d_init || !d_end || !d_out || !d_count || !d_status) return fail(FMB_E_INVALID, "null pointer argument%s");
+    if (rows < 2 || cols < 2 || npaths < 1 || max_steps < 0) return fail(FMB_E_INVALID, "bad shape%s");
+    if (cap < (int64_t)max_steps + 2) return fail(FMB_E_INVALID, "cap must be >= max_steps + 2%s");
+    fmb::TraceArgs2D<double> A;
+    A.T = d_T; A.T_pitch = T_pitch; A.T_qstride = T_qstride; A.rows = rows; A.cols = cols; A.npaths = npaths;
+    A.field_of_path = d_field_of_path; A.init = d_init; A.end = d_end; A.tau = tau; A.max_steps = max_steps;
+    A.out = d_out; A.cap = cap; A.count = d_count; A.status = d_status;
+    constexpr int TW_ = 4;
+    fmb::trace2d_kernel<double, TW_><<<(npaths + TW_ - 1) / TW_, TW_ * 32, 0, (cudaStream_t)stream>>>(A);
+    CK(cudaGetLastError(), "launch trace2d");
+    return FMB_OK;
+}
+
+}  // extern "C"
+
+#include "fm_capi3d.inc"

@@ -1,0 +1,100 @@
+// emu_kernels.cpp -- runs the device code of planning_motion_planning_b200/csrc on the
+// CPU through cuda_emu.h.  TEST TOOLING ONLY (see cuda_emu.h); built by tests/ as
+// tools/host_emu/libfm_emu.so and never loaded by the product package.
+//
+//   g++ -O1 -g -std=c++17 -DFMB_HOST_EMU -ffp-contract=off -fPIC -shared \
+//       -I tools/host_emu -o tools/host_emu/libfm_emu.so tools/host_emu/emu_kernels.cpp
+#include "cuda_emu.h"
+
+#include "../../planning_motion_planning_b200/csrc/eikonal2d.cuh"
+#include "../../planning_motion_planning_b200/csrc/eikonal3d.cuh"
+#include "../../planning_motion_planning_b200/csrc/trace2d.cuh"
+#include "../../planning_motion_planning_b200/csrc/trace3d.cuh"
+
+namespace {
+unsigned pow2_at_least(long long v) { unsigned p = 1024; while ((long long)p < v) p <<= 1; return p; }
+constexpr int WARPS = 4;
+
+template <typename real, int TW>
+int run2d(const real *cost, long long cost_qstride, real *T, int rows, int cols, int nq, const int *seeds, int nblocks,
+          unsigned long long *stats) {
+    fmb::Problem2D<real> P;
+    P.cost = cost; P.cost_pitch = cols; P.cost_qstride = cost_qstride;
+    P.T = T; P.T_pitch = cols; P.T_qstride = (long long)rows * cols;
+    P.rows = rows; P.cols = cols; P.nq = nq;
+    P.ntx = (cols + TW - 1) / TW; P.nty = (rows + fmb::TILE_H - 1) / fmb::TILE_H;
+    P.seeds = seeds;
+    const long long ntiles = (long long)nq * P.ntx * P.nty;
+    std::vector<int> state(ntiles), ring(pow2_at_least(ntiles));
+    fmb::QueueCtl ctl;
+    P.tile_state = state.data(); P.q.ctl = &ctl; P.q.ring = ring.data(); P.q.ring_mask = (unsigned)ring.size() - 1;
+    P.q.watchdog_cycles = 1LL << 40; P.step_cap = 1 << 20;
+    emu::launch(2, 64, 0, [&] { fmb::init_fill2d_kernel<real>(P, (int)ring.size()); });
+    emu::launch(1, 32 * ((nq + 31) / 32), 0, [&] { fmb::init_seed2d_kernel<real, TW>(P); });
+    emu::launch(nblocks, WARPS * 32, fmb::Tile2D<real, TW>::WARP_BYTES * WARPS, [&] { fmb::solve2d_kernel<real, TW, WARPS>(P); });
+    if (stats) { stats[0] = ctl.visits; stats[1] = ctl.steps; stats[2] = ctl.evals; stats[3] = ctl.pushes; stats[4] = ctl.cells_written; }
+    return ctl.abort ? ctl.abort : (ctl.pending != 0 ? -1 : 0);
+}
+
+template <typename real, int TZ>
+int run3d(const real *cost, long long cost_qstride, real *T, int ny, int nx, int nz, int nq, const int *seeds, int nblocks,
+          unsigned long long *stats) {
+    fmb::Problem3D<real> P;
+    P.cost = cost; P.cost_qstride = cost_qstride; P.T = T; P.T_qstride = (long long)ny * nx * nz;
+    P.ny = ny; P.nx = nx; P.nz = nz; P.nq = nq;
+    P.nty = (ny + fmb::T3Y - 1) / fmb::T3Y; P.ntx = (nx + fmb::T3X - 1) / fmb::T3X; P.ntz = (nz + TZ - 1) / TZ;
+    P.seeds = seeds;
+    const long long ntiles = (long long)nq * P.nty * P.ntx * P.ntz;
+    std::vector<int> state(ntiles), ring(pow2_at_least(ntiles));
+    fmb::QueueCtl ctl;
+    P.tile_state = state.data(); P.q.ctl = &ctl; P.q.ring = ring.data(); P.q.ring_mask = (unsigned)ring.size() - 1;
+    P.q.watchdog_cycles = 1LL << 40; P.step_cap = 1 << 20;
+    emu::launch(2, 64, 0, [&] { fmb::init_fill3d_kernel<real>(P, (int)ring.size()); });
+    emu::launch(1, 32 * ((nq + 31) / 32), 0, [&] { fmb::init_seed3d_kernel<real, TZ>(P); });
+    emu::launch(nblocks, WARPS * 32, fmb::Tile3D<real, TZ>::WARP_BYTES * WARPS, [&] { fmb::solve3d_kernel<real, TZ, WARPS>(P); });
+    if (stats) { stats[0] = ctl.visits; stats[1] = ctl.steps; stats[2] = ctl.evals; stats[3] = ctl.pushes; stats[4] = ctl.cells_written; }
+    return ctl.abort ? ctl.abort : (ctl.pending != 0 ? -1 : 0);
+}
+}  // namespace
+
+extern "C" {
+
+int emu_solve2d_f64(const double *cost, long long cost_qstride, double *T, int rows, int cols, int nq, const int *seeds,
+                    int tw, int nblocks, unsigned long long *stats) {
+    if (tw == 16) return run2d<double, 16>(cost, cost_qstride, T, rows, cols, nq, seeds, nblocks, stats);
+    return run2d<double, 32>(cost, cost_qstride, T, rows, cols, nq, seeds, nblocks, stats);
+}
+int emu_solve2d_f32(const float *cost, long long cost_qstride, float *T, int rows, int cols, int nq, const int *seeds,
+                    int tw, int nblocks, unsigned long long *stats) {
+    if (tw == 16) return run2d<float, 16>(cost, cost_qstride, T, rows, cols, nq, seeds, nblocks, stats);
+    return run2d<float, 32>(cost, cost_qstride, T, rows, cols, nq, seeds, nblocks, stats);
+}
+int emu_solve3d_f64(const double *cost, long long cost_qstride, double *T, int ny, int nx, int nz, int nq,
+                    const int *seeds, int tz, int nblocks, unsigned long long *stats) {
+    if (tz == 16) return run3d<double, 16>(cost, cost_qstride, T, ny, nx, nz, nq, seeds, nblocks, stats);
+    return run3d<double, 32>(cost, cost_qstride, T, ny, nx, nz, nq, seeds, nblocks, stats);
+}
+int emu_solve3d_f32(const float *cost, long long cost_qstride, float *T, int ny, int nx, int nz, int nq,
+                    const int *seeds, int tz, int nblocks, unsigned long long *stats) {
+    if (tz == 16) return run3d<float, 16>(cost, cost_qstride, T, ny, nx, nz, nq, seeds, nblocks, stats);
+    return run3d<float, 32>(cost, cost_qstride, T, ny, nx, nz, nq, seeds, nblocks, stats);
+}
+
+void emu_trace2d_f64(const double *T, int rows, int cols, int npaths, const int *field_of_path, const double *init,
+                     const double *end, double tau, int max_steps, double *out, long long cap, int *count, int *status) {
+    fmb::TraceArgs2D<double> A;
+    A.T = T; A.T_pitch = cols; A.T_qstride = (long long)rows * cols; A.rows = rows; A.cols = cols; A.npaths = npaths;
+    A.field_of_path = field_of_path; A.init = init; A.end = end; A.tau = tau; A.max_steps = max_steps;
+    A.out = out; A.cap = cap; A.count = count; A.status = status;
+    emu::launch((npaths + 3) / 4, 128, 0, [&] { fmb::trace2d_kernel<double, 4>(A); });
+}
+void emu_trace3d_f64(const double *T, int ny, int nx, int nz, int npaths, const int *field_of_path, const double *init,
+                     const double *end, double tau, int max_steps, double *out, long long cap, int *count, int *status) {
+    fmb::TraceArgs3D<double> A;
+    A.T = T; A.T_qstride = (long long)ny * nx * nz; A.ny = ny; A.nx = nx; A.nz = nz; A.npaths = npaths;
+    A.field_of_path = field_of_path; A.init = init; A.end = end; A.tau = tau; A.max_steps = max_steps;
+    A.out = out; A.cap = cap; A.count = count; A.status = status;
+    emu::launch((npaths + 3) / 4, 128, 0, [&] { fmb::trace3d_kernel<double, 4>(A); });
+}
+
+}  // extern "C"
