@@ -1,0 +1,417 @@
+#!/usr/bin/env python
+"""bench.py -- headline measurement of the Fast Marching hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # own arm (CUDA)
+    python bench.py --impl reference --gpus N --steps K ...  # reference arm (CPU port, host cores)
+
+Workload (BASELINE.json metric: "Eikonal solve ms + cell-updates/s (4096^2 map); batched
+queries/s at 1/2/4/8 GPU"): one STEP = one full-field Eikonal solve of a 4096x4096 fp64
+planner-like costmap (SURVEY.md 8d "metric map", seed 0) from one goal + one gradient-descent
+path extraction over the result.  With N GPUs every rank solves its own goal on the same map
+(independent planning queries, no data-path collective): weak scaling.
+
+  value = cells solved per second over the whole job = N * 4096^2 * K / t, t = device time of
+          the K timed steps (CUDA events), max over ranks; inputs resident in HBM.
+  e2e   = the same through the public engine API with HOST buffers: per step the costmap is
+          copied from pinned host memory, solved, traced, and the field + path copied back.
+  roofline: dominant kernel = the persistent solve2d kernel; algorithmic bytes = 2*8 B per
+          cell (read cost once, write T once); duration = CUDA events recorded
+          by the library around that kernel.
+One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "eikonal_cell_updates_per_s_4096x4096_solve_plus_path"
+UNIT = "cells/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", type=int, default=4096, help="map side (default: the metric's 4096)")
+    ap.add_argument("--map", default="mars", choices=["mars", "random"])
+    ap.add_argument("--no-batch", action="store_true", help="skip the batched-queries section")
+    ap.add_argument("--batch-queries", type=int, default=256, help="512^2 queries per GPU in the batched section")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def make_map(n, kind, seed=0):
+    from planning_motion_planning_b200 import synth
+    cache = f"/tmp/fmb_bench_{kind}_{n}_{seed}.npy"
+    if os.path.exists(cache):
+        try:
+            return np.load(cache)
+        except Exception:
+            pass
+    c = synth.mars_costmap(n, seed) if kind == "mars" else synth.random_costmap((n, n), seed)
+    try:
+        np.save(cache, c)
+    except Exception:
+        pass
+    return c
+
+
+def goals_for(c, n_ranks):
+    """Rank r solves from its own goal; rank 0's is the survey's metric-map source (n/4, n/4)
+    with the path traced from (3n/4, 3n/4)."""
+    from planning_motion_planning_b200 import synth
+    n = c.shape[0]
+    fr = [(0.25, 0.25), (0.75, 0.25), (0.25, 0.75), (0.5, 0.5), (0.6, 0.2), (0.2, 0.6), (0.4, 0.8), (0.8, 0.4)]
+    goals, starts = [], []
+    for r in range(n_ranks):
+        fx, fy = fr[r % len(fr)]
+        goals.append(synth.free_cell_near(c, int(fx * n), int(fy * n)))
+        starts.append(synth.free_cell_near(c, int((1 - fx) * n) if fx != 0.5 else int(0.1 * n), int((1 - fy) * n) if fy != 0.5 else int(0.1 * n)))
+    return goals, starts
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons of one GPU during the timed region (NVML)."""
+
+    def __init__(self, index):
+        self.index, self.samples, self.reasons, self.stop_flag = index, [], set(), False
+        self.max_mhz, self.thread, self.ok = None, None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def start(self):
+        if self.ok:
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=1.0)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------ CPU arms
+def cpu_port_run(c, goal, start, threads, sample_n):
+    """Oracle port (C restatement of the reference FMM + tracer) on `threads` host threads,
+    each solving the top-left sample_n x sample_n crop of the map from its own goal."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle as O
+    from planning_motion_planning_b200 import synth
+    crop = np.ascontiguousarray(c[:sample_n, :sample_n]).copy()
+    crop[0, :] = crop[-1, :] = crop[:, 0] = crop[:, -1] = np.inf
+    rng = np.random.default_rng(1)
+    jobs = []
+    for t in range(threads):
+        g = synth.free_cell_near(crop, int(rng.integers(sample_n // 8, sample_n // 3)), int(rng.integers(sample_n // 8, sample_n // 3)))
+        s = synth.free_cell_near(crop, sample_n - g[0], sample_n - g[1])
+        jobs.append((g, s))
+
+    def one(job):
+        g, s = job
+        T = O.computeTmap(crop, g)
+        p, _ = O.getPathGDM(T, np.array(s), g, 0.5, return_status=True)
+        return int(np.isfinite(T).sum()), len(p)
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        res = list(ex.map(one, jobs))
+    dt = time.perf_counter() - t0
+    return threads * sample_n * sample_n / dt, dt, res
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    O.build()
+    cores = len(os.sched_getaffinity(0))
+    threads = min(cores, 32)
+    n = args.size
+    c = make_map(n, args.map)
+    sample_n = min(n, 1024)
+    for _ in range(args.warmup):
+        cpu_port_run(c, None, None, threads, min(sample_n, 512))
+    t0 = time.perf_counter()
+    vals = []
+    for _ in range(args.steps):
+        v, dt, _ = cpu_port_run(c, None, None, threads, sample_n)
+        vals.append(v)
+    total = time.perf_counter() - t0
+    value = threads * sample_n * sample_n * args.steps / total
+    sample = (f"{threads} host threads x one {sample_n}x{sample_n} crop of the {n}x{n} map per step "
+              f"(heap FMM + path, C port of FastMarching.py; FMM cost is linear in cells)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{n}x{n} fp64 planner-like costmap ({args.map}, seed 0): full-field solve + 1 path",
+                   "cpu_threads": threads},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------ own arm
+def own_arm(args):
+    import torch
+    import torch.distributed as dist
+    from planning_motion_planning_b200 import _capi, engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    _capi.lib()          # fail loudly if the CUDA library is missing
+
+    n = args.size
+    c = make_map(n, args.map)
+    goals, starts = goals_for(c, max(world, 1))
+    goal, start = goals[rank], starts[rank]
+    cells = n * n
+    K, W = args.steps, args.warmup
+    tau = 0.5
+
+    cost_h = torch.from_numpy(c).pin_memory()
+    cost_d = cost_h.to(dev)
+    T_d = torch.empty((1, n, n), dtype=torch.float64, device=dev)
+    seeds_d = torch.tensor([goal], dtype=torch.int32, device=dev)
+    init = torch.tensor([start], dtype=torch.float64, device=dev)
+    end = torch.tensor([goal], dtype=torch.float64, device=dev)
+
+    def step_resident():
+        engine.solve2d(cost_d, seeds_d, out=T_d, nq=1, sync=False)
+        return engine.trace2d(T_d, init, end, tau)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also validates: device-side failure raises here)
+    for _ in range(max(W, 3)):
+        out, cnt, st = step_resident()
+        stats = engine.finish(dev)
+    path_len = int(cnt[0])
+    path_status = int(st[0])
+
+    # ---- device-timed region: K steps, inputs resident (cost+T = 2*n*n*8 B > L2 for n >= 4096)
+    sampler = ClockSampler(local if os.environ.get("CUDA_VISIBLE_DEVICES") is None else 0)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    sampler.start()
+    ev0.record()
+    for _ in range(K):
+        step_resident()
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    t_ms = ev0.elapsed_time(ev1)
+    stats = engine.finish(dev)
+    if world > 1:
+        tt = torch.tensor([t_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_ms = float(tt[0])
+    value = world * cells * K / (t_ms * 1e-3)
+
+    # ---- per-kernel durations (library CUDA events around the persistent kernel), K more steps
+    k_ms, i_ms, tr_ms = [], [], []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(max(3, min(K, 10))):
+        engine.solve2d(cost_d, seeds_d, out=T_d, nq=1, sync=False)
+        s = engine.finish(dev)
+        k_ms.append(s["solve_kernel_ms"]); i_ms.append(s["init_kernel_ms"])
+        e0.record()
+        engine.trace2d(T_d, init, end, tau)
+        e1.record()
+        torch.cuda.synchronize()
+        tr_ms.append(e0.elapsed_time(e1))
+    solve_ms, init_ms, trace_ms = float(np.mean(k_ms)), float(np.mean(i_ms)), float(np.mean(tr_ms))
+    peak, peak_src = measured_peak()
+    alg_bytes = 2 * 8 * cells
+    achieved = alg_bytes / (solve_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "solve2d_kernel<double,32,4>", "kernel_ms": solve_ms,
+                "algorithmic_bytes": alg_bytes, "peak_source": peak_src}
+
+    # ---- end to end through the public API with host buffers
+    T_h = torch.empty((1, n, n), dtype=torch.float64).pin_memory()
+    cap = int(round(15000 / tau)) + 2
+    path_h = torch.empty((1, cap, 2), dtype=torch.float64).pin_memory()
+    cnt_h = torch.empty(1, dtype=torch.int32).pin_memory()
+
+    def step_e2e():
+        cd = cost_h.to(dev, non_blocking=True)
+        engine.solve2d(cd, seeds_d, out=T_d, nq=1, sync=False)
+        out, cnt, st = engine.trace2d(T_d, init, end, tau)
+        T_h.copy_(T_d, non_blocking=True)
+        path_h.copy_(out, non_blocking=True)
+        cnt_h.copy_(cnt, non_blocking=True)
+        torch.cuda.synchronize()
+
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt[0])
+    e2e = {"value": world * cells * K / e2e_s, "unit": UNIT, "ms_per_step": 1e3 * e2e_s / K,
+           "h2d_bytes_per_step": int(cost_h.numel() * 8), "d2h_bytes_per_step": int(T_h.numel() * 8 + path_h.numel() * 8 + 4)}
+
+    # ---- batched independent queries (config 4 style): Q goal queries on one 512^2 map per GPU
+    batch = None
+    if not args.no_batch:
+        from planning_motion_planning_b200 import synth
+        Q = args.batch_queries
+        cb = make_map(512, args.map, seed=1)
+        rng = np.random.default_rng(100 + rank)
+        ok = np.argwhere(np.isfinite(cb) & (cb <= 2.0))
+        pick = ok[rng.integers(0, len(ok), size=Q)]
+        seeds_b = torch.tensor(pick[:, ::-1].copy(), dtype=torch.int32, device=dev)
+        cb_d = torch.from_numpy(cb).to(dev)
+        Tb = torch.empty((Q, 512, 512), dtype=torch.float64, device=dev)
+        starts_b = torch.tensor(ok[rng.integers(0, len(ok), size=Q)][:, ::-1].copy(), dtype=torch.float64, device=dev)
+        ends_b = seeds_b.to(torch.float64)
+        for _ in range(2):
+            engine.solve2d(cb_d, seeds_b, out=Tb, nq=Q, sync=False)
+            engine.trace2d(Tb, starts_b, ends_b, tau)
+            sb = engine.finish(dev)
+        barrier()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        b0.record()
+        for _ in range(reps):
+            engine.solve2d(cb_d, seeds_b, out=Tb, nq=Q, sync=False)
+            engine.trace2d(Tb, starts_b, ends_b, tau)
+        b1.record()
+        barrier()
+        bms = b0.elapsed_time(b1) / reps
+        sb = engine.finish(dev)
+        if world > 1:
+            tt = torch.tensor([bms], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            bms = float(tt[0])
+        bcells = Q * 512 * 512
+        batch = {"workload": f"{Q} goal queries per GPU on one 512x512 fp64 map (solve + 1 path each)",
+                 "queries_per_s": world * Q / (bms * 1e-3), "ms_per_batch": bms,
+                 "cells_per_s": world * bcells / (bms * 1e-3),
+                 "solve_kernel_ms": sb["solve_kernel_ms"],
+                 "roofline_frac_solve_kernel": (2 * 8 * bcells / (sb["solve_kernel_ms"] * 1e-3) / 1e9) / peak,
+                 "evals_per_cell": sb["evals"] / bcells}
+
+    # ---- CPU baseline beside it (rank 0, N == 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as O
+        O.build()
+        t0 = time.perf_counter()
+        Tref = O.computeTmap(c, goal)
+        pref, pst = O.getPathGDM(Tref, np.array(start), goal, tau, return_status=True)
+        dt = time.perf_counter() - t0
+        Tg = T_h[0].numpy()
+        fin = np.isfinite(Tref)
+        same_inf = bool(np.array_equal(np.isfinite(Tg), fin))
+        rel = float(np.max(np.abs(Tg[fin] - Tref[fin]) / np.maximum(Tref[fin], 1e-300)))
+        gp = path_h[0, :int(cnt_h[0])].numpy()
+        pdev = float(np.abs(gp - pref).max()) if gp.shape == pref.shape else None
+        cpu = {"value": cells / dt, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"the full {n}x{n} solve + path, once, single thread (C restatement of the reference FMM; "
+                         f"the reference itself is single-threaded CPython at ~2e4 cells/s)",
+               "seconds": dt, "host_cores_available": len(os.sched_getaffinity(0)),
+               "parity": {"field_max_rel_err": rel, "same_inf_pattern": same_inf, "path_rows": [len(gp), len(pref)],
+                          "path_max_abs_dev_cells": pdev}}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W, 3),
+            "ms_per_step": t_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{n}x{n} fp64 planner-like costmap ({args.map}, seed 0): full-field solve + 1 path "
+                                   f"per GPU per step", "l2_policy": "inputs larger than L2 (cost + T = %d MiB)" % (2 * cells * 8 >> 20),
+                       "tau": tau, "path_rows": path_len, "path_status": path_status, "parallelism": f"{world} independent queries"},
+            "breakdown_ms": {"init_fill": init_ms, "solve_kernel": solve_ms, "trace_kernel": trace_ms},
+            "solver_stats": {k: stats[k] for k in ("tile_visits", "steps", "evals", "pushes", "cells_written")},
+            "evals_per_cell": stats["evals"] / cells,
+            "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "batch": batch,
+            "gpu_launches": 4 * K, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        own_arm(args)
+
+
+if __name__ == "__main__":
+    main()

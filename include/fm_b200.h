@@ -15,9 +15,6 @@
  *   fmb_trace2d_*        src/FastMarching/FastMarching.py:164-236  getPathGDM
  *                        src/FastMarching/FastMarching.py:242-338  computeGradient / interpolatePoint
  *   fmb_trace3d_*        src/FastMarching/FastMarching3D.py:198-314 getPathGDM / interpolatePoint
- *   fmb_truncate2d_* /   the early-exit semantics of the reference loops
- *   fmb_truncate3d_*     (FastMarching.py:108-109,150-155; FastMarching3D.py:141-142):
- *                        turn full fields into the partial fields the reference returns
  *
  * Conventions
  *  - Plain C, no torch types.  Every data pointer is a DEVICE pointer on the
@@ -66,7 +63,9 @@ typedef struct fmb_stats {
     uint64_t evals;         /* local-solver evaluations (getEikonal / 3D quadratic) */
     uint64_t pushes;        /* work-queue pushes */
     uint64_t cells_written; /* T values stored to HBM */
-    uint64_t reserved[3];
+    double solve_kernel_ms; /* device time of the last persistent solve kernel on this thread (CUDA events) */
+    double init_kernel_ms;  /* device time of the init (fill + seed) launches that preceded it */
+    uint64_t reserved[1];
 } fmb_stats;
 
 int fmb_version(void);
@@ -92,8 +91,7 @@ int fmb_solve2d_f32(const float *d_cost, int64_t cost_pitch, int64_t cost_qstrid
                     void *d_ws, size_t ws_bytes, void *stream);
 
 /* ---- 3D Eikonal solve ------------------------------------------------------
- * volumes are [ny][nx][nz] with z contiguous; pitches: elements between
- * consecutive x (pitch_x >= nz) and consecutive y (pitch_y >= nx*pitch_x).
+ * volumes are dense [ny][nx][nz] arrays with z contiguous.
  * d_seeds int32 [nq][3] = [x,y,z].
  */
 size_t fmb_workspace_bytes_3d(int ny, int nx, int nz, int nq);

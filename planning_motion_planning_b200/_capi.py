@@ -1,0 +1,82 @@
+"""ctypes binding of include/fm_b200.h -> libfm_b200.so.
+
+Fails loudly when the CUDA library is missing: there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+_LIB = None
+
+FMB_OK = 0
+FMB_E_INVALID, FMB_E_CUDA, FMB_E_WORKSPACE, FMB_E_WATCHDOG, FMB_E_STEPCAP, FMB_E_NOJOIN = 1, 2, 3, 4, 5, 6
+TRACE_OK, TRACE_EARLY, TRACE_VALUEERROR, TRACE_INDEXERROR, TRACE_OVERFLOW = 0, 1, 2, 3, 4
+
+
+class FmbStats(C.Structure):
+    _fields_ = [("tile_visits", C.c_uint64), ("steps", C.c_uint64), ("evals", C.c_uint64),
+                ("pushes", C.c_uint64), ("cells_written", C.c_uint64), ("solve_kernel_ms", C.c_double),
+                ("init_kernel_ms", C.c_double), ("reserved", C.c_uint64 * 1)]
+
+    def as_dict(self):
+        d = {k: int(getattr(self, k)) for k in ("tile_visits", "steps", "evals", "pushes", "cells_written")}
+        d["solve_kernel_ms"] = float(self.solve_kernel_ms)
+        d["init_kernel_ms"] = float(self.init_kernel_ms)
+        return d
+
+
+class FmbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libfm_b200 error {code}: {msg}")
+        self.code = code
+
+
+_vp, _i64, _i32, _sz, _dbl = C.c_void_p, C.c_int64, C.c_int, C.c_size_t, C.c_double
+
+# name -> (restype, argtypes); every symbol include/fm_b200.h declares
+SIGNATURES = {
+    "fmb_version": (C.c_int, []),
+    "fmb_last_error": (C.c_char_p, []),
+    "fmb_sm_count": (C.c_int, []),
+    "fmb_workspace_bytes_2d": (_sz, [_i32, _i32, _i32]),
+    "fmb_solve2d_f64": (C.c_int, [_vp, _i64, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
+    "fmb_solve2d_f32": (C.c_int, [_vp, _i64, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
+    "fmb_workspace_bytes_3d": (_sz, [_i32, _i32, _i32, _i32]),
+    "fmb_solve3d_f64": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
+    "fmb_solve3d_f32": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
+    "fmb_finish": (C.c_int, [_vp, _sz, _vp, C.POINTER(FmbStats)]),
+    "fmb_trace2d_f64": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _dbl, _i32, _vp, _i64, _vp, _vp, _vp]),
+    "fmb_trace3d_f64": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _dbl, _i32, _vp, _i64, _vp, _vp, _vp]),
+}
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def lib():
+    """Load (building first if stale and nvcc is present) the CUDA library."""
+    global _LIB
+    if _LIB is None:
+        path = _build.LIB_PATH
+        if _build.needs_build():
+            try:
+                _build.build()
+            except Exception as e:  # no nvcc / compile error: loud, never a fallback
+                if not os.path.exists(path):
+                    raise ImportError(f"libfm_b200.so is missing and could not be built: {e}") from e
+        L = C.CDLL(path)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)          # AttributeError if the ABI lost a symbol
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = L
+    return _LIB
+
+
+def check(rc: int):
+    if rc != FMB_OK:
+        raise FmbError(rc, lib().fmb_last_error().decode())

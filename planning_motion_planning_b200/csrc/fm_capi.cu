@@ -27,6 +27,20 @@ int cuda_fail(cudaError_t e, const char *where) {
 }
 #define CK(call, where) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(e_, where); } while (0)
 
+// per-host-thread CUDA events bracketing the most recent solve (timing evidence for bench.py)
+struct Timing { cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr; bool armed = false; };
+thread_local Timing g_tm;
+bool timing_begin(cudaStream_t st) {
+    if (!g_tm.e0) {
+        if (cudaEventCreate(&g_tm.e0) != cudaSuccess || cudaEventCreate(&g_tm.e1) != cudaSuccess ||
+            cudaEventCreate(&g_tm.e2) != cudaSuccess) { g_tm.e0 = nullptr; cudaGetLastError(); return false; }
+    }
+    g_tm.armed = false;
+    return cudaEventRecord(g_tm.e0, st) == cudaSuccess;
+}
+void timing_mid(cudaStream_t st) { if (g_tm.e0) cudaEventRecord(g_tm.e1, st); }
+void timing_end(cudaStream_t st) { if (g_tm.e0 && cudaEventRecord(g_tm.e2, st) == cudaSuccess) g_tm.armed = true; }
+
 int env_int(const char *name, int dflt) {
     const char *v = getenv(name);
     return (v && *v) ? atoi(v) : dflt;
@@ -94,9 +108,12 @@ int launch_solve2d(fmb::Problem2D<real> P, const WsLayout &L, cudaStream_t st) {
     long long fill_blocks = (cells + 256 * 8 - 1) / (256 * 8);
     if (fill_blocks > (long long)sm_count() * 16) fill_blocks = (long long)sm_count() * 16;
     if (fill_blocks < 1) fill_blocks = 1;
+    timing_begin(st);
     fmb::init_fill2d_kernel<real><<<(unsigned)fill_blocks, 256, 0, st>>>(P, (int)L.ring_slots);
     fmb::init_seed2d_kernel<real, TW><<<(P.nq + 127) / 128, 128, 0, st>>>(P);
+    timing_mid(st);
     kern<<<(unsigned)blocks, WARPS * 32, smem, st>>>(P);
+    timing_end(st);
     CK(cudaGetLastError(), "launch solve2d");
     return FMB_OK;
 }
@@ -167,6 +184,12 @@ int fmb_finish(void *d_ws, size_t ws_bytes, void *stream, fmb_stats *stats) {
         memset(stats, 0, sizeof(*stats));
         stats->tile_visits = h.visits; stats->steps = h.steps; stats->evals = h.evals;
         stats->pushes = h.pushes; stats->cells_written = h.cells_written;
+        if (g_tm.armed) {
+            float a = 0.f, b = 0.f;
+            if (cudaEventElapsedTime(&a, g_tm.e0, g_tm.e1) == cudaSuccess && cudaEventElapsedTime(&b, g_tm.e1, g_tm.e2) == cudaSuccess) {
+                stats->init_kernel_ms = a; stats->solve_kernel_ms = b;
+            } else cudaGetLastError();
+        }
     }
     if (h.abort == fmb::DEV_WATCHDOG) return fail(FMB_E_WATCHDOG, "device watchdog fired: a queue wait exceeded FMB_WATCHDOG_MS%s");
     if (h.abort == fmb::DEV_STEPCAP) return fail(FMB_E_STEPCAP, "in-tile iteration cap (FMB_STEP_CAP) exceeded%s");

@@ -1,0 +1,91 @@
+"""Test helper: builds and drives tools/host_emu (CPU execution of the CUDA kernel source
+under a SIMT emulator).  Test tooling only -- see tools/host_emu/cuda_emu.h."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from conftest import ROOT
+
+_DIR = os.path.join(ROOT, "tools", "host_emu")
+_SO = os.path.join(_DIR, "libfm_emu.so")
+_L = None
+dp, fp, ip, up = C.POINTER(C.c_double), C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_ulonglong)
+
+
+def lib():
+    global _L
+    if _L is None:
+        srcs = [os.path.join(_DIR, f) for f in ("emu_kernels.cpp", "cuda_emu.h")]
+        csrc = os.path.join(ROOT, "planning_motion_planning_b200", "csrc")
+        srcs += [os.path.join(csrc, f) for f in os.listdir(csrc)]
+        if not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
+            subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-DFMB_HOST_EMU", "-ffp-contract=off", "-fPIC",
+                                   "-shared", "-I", _DIR, "-o", _SO, os.path.join(_DIR, "emu_kernels.cpp")])
+        L = C.CDLL(_SO)
+        L.emu_solve2d_f64.argtypes = [dp, C.c_longlong, dp, C.c_int, C.c_int, C.c_int, ip, C.c_int, C.c_int, up]
+        L.emu_solve2d_f32.argtypes = [fp, C.c_longlong, fp, C.c_int, C.c_int, C.c_int, ip, C.c_int, C.c_int, up]
+        L.emu_solve3d_f64.argtypes = [dp, C.c_longlong, dp, C.c_int, C.c_int, C.c_int, C.c_int, ip, C.c_int, C.c_int, up]
+        L.emu_solve3d_f32.argtypes = [fp, C.c_longlong, fp, C.c_int, C.c_int, C.c_int, C.c_int, ip, C.c_int, C.c_int, up]
+        L.emu_trace2d_f64.argtypes = [dp, C.c_int, C.c_int, C.c_int, ip, dp, dp, C.c_double, C.c_int, dp, C.c_longlong, ip, ip]
+        L.emu_trace3d_f64.argtypes = [dp, C.c_int, C.c_int, C.c_int, C.c_int, ip, dp, dp, C.c_double, C.c_int, dp, C.c_longlong, ip, ip]
+        _L = L
+    return _L
+
+
+def solve2d(cost, seeds, tw=32, nblocks=2, shared=True):
+    dt = cost.dtype
+    cost = np.ascontiguousarray(cost)
+    seeds = np.ascontiguousarray(seeds, dtype=np.int32).reshape(-1, 2)
+    nq = len(seeds)
+    rows, cols = cost.shape[-2:]
+    T = np.empty((nq, rows, cols), dtype=dt)
+    st = np.zeros(8, dtype=np.uint64)
+    P = dp if dt == np.float64 else fp
+    fn = lib().emu_solve2d_f64 if dt == np.float64 else lib().emu_solve2d_f32
+    rc = fn(cost.ctypes.data_as(P), 0 if shared else rows * cols, T.ctypes.data_as(P), rows, cols, nq,
+            seeds.ctypes.data_as(ip), tw, nblocks, st.ctypes.data_as(up))
+    assert rc == 0, f"emulated solve2d failed rc={rc}"
+    return T, dict(visits=int(st[0]), steps=int(st[1]), evals=int(st[2]), pushes=int(st[3]), written=int(st[4]))
+
+
+def solve3d(cost, seeds, tz=32, nblocks=2, shared=True):
+    dt = cost.dtype
+    cost = np.ascontiguousarray(cost)
+    seeds = np.ascontiguousarray(seeds, dtype=np.int32).reshape(-1, 3)
+    nq = len(seeds)
+    ny, nx, nz = cost.shape[-3:]
+    T = np.empty((nq, ny, nx, nz), dtype=dt)
+    st = np.zeros(8, dtype=np.uint64)
+    P = dp if dt == np.float64 else fp
+    fn = lib().emu_solve3d_f64 if dt == np.float64 else lib().emu_solve3d_f32
+    rc = fn(cost.ctypes.data_as(P), 0 if shared else ny * nx * nz, T.ctypes.data_as(P), ny, nx, nz, nq,
+            seeds.ctypes.data_as(ip), tz, nblocks, st.ctypes.data_as(up))
+    assert rc == 0, f"emulated solve3d failed rc={rc}"
+    return T, dict(visits=int(st[0]), steps=int(st[1]), evals=int(st[2]))
+
+
+def _trace(fn, T, dim, init, end, tau, field_of_path=None):
+    T = np.ascontiguousarray(T, dtype=np.float64)
+    init = np.ascontiguousarray(init, dtype=np.float64).reshape(-1, dim)
+    end = np.ascontiguousarray(end, dtype=np.float64).reshape(-1, dim)
+    npaths = len(init)
+    ms = int(round(15000 / tau))
+    cap = ms + 2
+    out = np.zeros((npaths, cap, dim))
+    cnt = np.zeros(npaths, np.int32)
+    st = np.zeros(npaths, np.int32)
+    fop = None if field_of_path is None else np.ascontiguousarray(field_of_path, dtype=np.int32)
+    shape = T.shape[-dim:]
+    fn(T.ctypes.data_as(dp), *shape, npaths, None if fop is None else fop.ctypes.data_as(ip), init.ctypes.data_as(dp),
+       end.ctypes.data_as(dp), tau, ms, out.ctypes.data_as(dp), cap, cnt.ctypes.data_as(ip), st.ctypes.data_as(ip))
+    return [out[p, :cnt[p]].copy() for p in range(npaths)], [int(s) for s in st]
+
+
+def trace2d(T, init, end, tau=0.5, field_of_path=None):
+    return _trace(lib().emu_trace2d_f64, T, 2, init, end, tau, field_of_path)
+
+
+def trace3d(T, init, end, tau=0.5, field_of_path=None):
+    return _trace(lib().emu_trace3d_f64, T, 3, init, end, tau, field_of_path)

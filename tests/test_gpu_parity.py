@@ -1,0 +1,267 @@
+"""GPU (-m gpu): the compiled sm_100a path, called through the C ABI (ctypes) via the torch
+plumbing, against the CPU oracle and the golden vectors frozen from the reference.
+
+Tolerances are the north-star's: fp64 field 1e-9 relative (fp32 1e-4), waypoints 1e-3 cell."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, plateau_map, rand_map, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL64, TOL32, TOLP = 1e-9, 1e-4, 1e-3
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import torch
+    from planning_motion_planning_b200 import engine
+    assert torch.cuda.is_available()
+    return engine
+
+
+def _gpu2d(eng, c, seeds, **kw):
+    import torch
+    T = eng.solve2d(torch.from_numpy(np.ascontiguousarray(c)).cuda(), seeds, **kw)
+    return T.cpu().numpy()
+
+
+def _gpu3d(eng, c, seeds, **kw):
+    import torch
+    T = eng.solve3d(torch.from_numpy(np.ascontiguousarray(c)).cuda(), seeds, **kw)
+    return T.cpu().numpy()
+
+
+# ------------------------------------------------------------------ 2D solve
+@pytest.mark.parametrize("tw", ["32", "16"])
+@pytest.mark.parametrize("shape,goal", [((9, 9), [4, 4]), ((100, 100), [25, 25]), ((257, 300), [290, 3]),
+                                        ((33, 65), [32, 31]), ((512, 512), [100, 400])])
+def test_solve2d_random_vs_oracle(eng, shape, goal, tw, monkeypatch):
+    from oracle import oracle as O
+    monkeypatch.setenv("FMB_TW2D", tw)
+    c = rand_map(shape, 0)
+    T = _gpu2d(eng, c, [goal])[0]
+    assert rel_err(T, O.computeTmap(c, goal)) < TOL64
+    st = eng.last_stats()
+    assert st["tile_visits"] > 0 and st["evals"] >= np.isfinite(T).sum() - 1
+
+
+def test_kat1_and_kat3_values(eng):
+    c = np.pad(np.ones((7, 7)), 1, constant_values=np.inf)
+    T = _gpu2d(eng, c, [[4, 4]])[0]
+    assert list(T[4, 1:8]) == [3, 2, 1, 0, 1, 2, 3]
+    assert abs(T[5, 5] - 1.7071067811865475) < 1e-15 and abs(T[6, 6] - 3.25243570661267) < 1e-14
+    c = rand_map((100, 100), 0)
+    T = _gpu2d(eng, c, [[25, 25]])[0]
+    assert abs(np.sum(T[np.isfinite(T)]) - 1224641.4437929934) / 1224641.4437929934 < 1e-12
+    assert abs(T[98, 98] - 280.68674463626854) < 1e-9 * 280.7
+
+
+def test_solve2d_plateau_walls_enclosed(eng):
+    from oracle import oracle as O
+    c = plateau_map(160, 3)
+    c[30:90, 40] = np.inf
+    c[100:120, 100] = c[100:120, 119] = c[100, 100:120] = c[119, 100:120] = np.inf
+    T = _gpu2d(eng, c, [[20, 60]])[0]
+    assert rel_err(T, O.computeTmap(c, [20, 60])) < TOL64
+    assert np.all(np.isinf(T[101:119, 101:119]))
+
+
+def test_solve2d_planner_like_map(eng):
+    from oracle import oracle as O
+    from planning_motion_planning_b200 import synth
+    c = synth.mars_costmap(768, 1)
+    g = synth.free_cell_near(c, 200, 190)
+    T = _gpu2d(eng, c, [g])[0]
+    assert rel_err(T, O.computeTmap(c, g)) < TOL64
+
+
+def test_solve2d_batches(eng):
+    import torch
+    from oracle import oracle as O
+    c = rand_map((96, 130), 2)
+    goals = [[5, 5], [120, 90], [31, 32], [32, 31], [64, 64], [63, 63]]
+    T = _gpu2d(eng, c, goals)
+    for q, g in enumerate(goals):
+        assert rel_err(T[q], O.computeTmap(c, g)) < TOL64
+    cs = np.stack([rand_map((80, 80), s) for s in range(5)])
+    T = eng.solve2d(torch.from_numpy(cs).cuda(), [[40, 40]] * 5).cpu().numpy()
+    for q in range(5):
+        assert rel_err(T[q], O.computeTmap(cs[q], [40, 40])) < TOL64
+
+
+def test_solve2d_fp32(eng):
+    from oracle import oracle as O
+    c32 = rand_map((300, 300), 4).astype(np.float32)
+    T = _gpu2d(eng, c32, [[10, 250]])[0]
+    assert T.dtype == np.float32
+    assert rel_err(T.astype(np.float64), O.computeTmap(c32.astype(np.float64), [10, 250])) < TOL32
+
+
+def test_solve2d_is_exact_fixed_point_4096(eng):
+    """Size-independent property (KAT-5) at BASELINE's full size: the returned field is a
+    bitwise fixed point of the reference update (FastMarching.py:17-29), evaluated here
+    with plain torch fp64 ops; and it matches the C oracle within 1e-9."""
+    import torch
+    from oracle import oracle as O
+    from planning_motion_planning_b200 import synth
+    n = 4096
+    c = synth.mars_costmap(n, 0)
+    g = synth.free_cell_near(c, n // 4, n // 4)
+    cd = torch.from_numpy(c).cuda()
+    T = eng.solve2d(cd, [g])[0]
+    inf = float("inf")
+    P = torch.nn.functional.pad(T, (1, 1, 1, 1), value=inf)
+    a = torch.minimum(P[1:-1, :-2], P[1:-1, 2:])
+    b = torch.minimum(P[:-2, 1:-1], P[2:, 1:-1])
+    d = a - b
+    one_sided = ~(d.abs() <= cd)
+    m = torch.minimum(a, b)
+    two = 0.5 * ((a + b) + torch.sqrt(2 * (cd * cd) - d * d))
+    U = torch.where(one_sided, m + cd, two)
+    U = torch.where(torch.isinf(cd), torch.full_like(U, inf), U)
+    free = torch.isfinite(cd)
+    free[g[1], g[0]] = False
+    both_inf = torch.isinf(T) & torch.isinf(U)
+    resid = torch.where(both_inf, torch.zeros_like(T), (T - U).abs())
+    assert float(resid[free].max()) == 0.0
+    assert float(T[g[1], g[0]]) == 0.0
+    ref = O.computeTmap(c, g)
+    assert rel_err(T.cpu().numpy(), ref) < TOL64
+
+
+# ------------------------------------------------------------------ 3D solve
+@pytest.mark.parametrize("tz", ["32", "16"])
+@pytest.mark.parametrize("shape,goal", [((9, 9, 9), [4, 4, 4]), ((24, 24, 24), [5, 6, 7]), ((13, 21, 40), [10, 5, 33]),
+                                        ((44, 44, 28), [35, 27, 6]), ((64, 64, 64), [10, 50, 30])])
+def test_solve3d_random_vs_oracle(eng, shape, goal, tz, monkeypatch):
+    from oracle import oracle as O
+    monkeypatch.setenv("FMB_TZ3D", tz)
+    c = rand_map(shape, 0)
+    T = _gpu3d(eng, c, [goal])[0]
+    assert rel_err(T, O.computeTmap3D(c, goal)) < TOL64
+
+
+def test_solve3d_planner_like_volume_and_batch(eng):
+    from oracle import oracle as O
+    from planning_motion_planning_b200 import synth
+    c, goal, start = synth.arm_volume((90, 90, 28), 0)
+    T = _gpu3d(eng, c, [goal, start])
+    assert rel_err(T[0], O.computeTmap3D(c, goal)) < TOL64
+    assert rel_err(T[1], O.computeTmap3D(c, start)) < TOL64
+
+
+def test_solve3d_fp32(eng):
+    from oracle import oracle as O
+    c32 = rand_map((40, 40, 40), 6).astype(np.float32)
+    T = _gpu3d(eng, c32, [[5, 5, 5]])[0]
+    assert rel_err(T.astype(np.float64), O.computeTmap3D(c32.astype(np.float64), [5, 5, 5])) < TOL32
+
+
+# ------------------------------------------------------------------ tracers
+def test_trace2d_vs_oracle_and_golden(eng):
+    import torch
+    from oracle import oracle as O
+    g = np.load(f"{GOLDEN}/ref2d.npz")
+    c = rand_map((100, 100), 0)
+    TG, TS, j = O.biComputeTmap(c, [10, 10], [90, 90])
+    out, cnt, st = eng.trace2d(torch.from_numpy(np.stack([TG, TS])).cuda(), [j, j], [[10, 10], [90, 90]])
+    out, cnt, st = out.cpu().numpy(), cnt.cpu().numpy(), st.cpu().numpy()
+    assert list(st) == [0, 0]
+    pG, pS = out[0, :cnt[0]], out[1, :cnt[1]]
+    assert pG.shape == g["kat3_pathG"].shape and np.abs(pG - g["kat3_pathG"]).max() < TOLP
+    assert pS.shape == g["kat3_pathS"].shape and np.abs(pS - g["kat3_pathS"]).max() < TOLP
+
+
+def test_trace2d_step_cap_case(eng):
+    """plateau80: the reference tracer never reaches `end` and runs all 30000 steps."""
+    import torch
+    from oracle import oracle as O
+    g = np.load(f"{GOLDEN}/ref2d.npz")
+    c = plateau_map(80, 3)
+    T = O.computeTmap(c, [20, 60])
+    out, cnt, st = eng.trace2d(torch.from_numpy(T).cuda(), [[70, 71]], [[20, 60]])
+    n = int(cnt[0])
+    ref = g["plateau80_pathF"]
+    assert n == len(ref) and int(st[0]) == 0
+    assert np.abs(out[0, :n].cpu().numpy() - ref).max() < TOLP
+
+
+def test_trace2d_fallback_statuses(eng):
+    import torch
+    from oracle import oracle as O
+    c = rand_map((30, 30), 2)
+    c[15, 5:25] = np.inf
+    T = O.computeTmap(c, [5, 5], [25, 25])
+    inits = [[25, 25], [25, 24], [14, 16], [29.2, 29.2]]
+    out, cnt, st = eng.trace2d(torch.from_numpy(T).cuda(), inits, [[5, 5]] * len(inits))
+    for p, init in enumerate(inits):
+        po, so = O.getPathGDM(T, np.array(init), [5, 5], 0.5, return_status=True)
+        assert int(st[p]) == so and int(cnt[p]) == len(po)
+        if len(po):
+            assert np.abs(out[p, :len(po)].cpu().numpy() - po).max() < TOLP
+
+
+def test_trace3d_vs_golden(eng):
+    import torch
+    from oracle import oracle as O
+    g = np.load(f"{GOLDEN}/ref3d.npz")
+    c = rand_map((24, 24, 24), 0)
+    for tag, start in (("full", None), ("trunc", [18, 17, 16])):
+        F = O.computeTmap3D(c, [5, 6, 7], start)
+        out, cnt, st = eng.trace3d(torch.from_numpy(F).cuda(), [[18, 17, 16]], [[5, 6, 7]])
+        ref = g[f"kat4_path_{tag}"]
+        assert int(st[0]) == 0 and int(cnt[0]) == len(ref)
+        assert np.abs(out[0, :len(ref)].cpu().numpy() - ref).max() < TOLP
+
+
+# ------------------------------------------------------------------ drop-in API
+def test_dropin_bi_and_paths_kat3b():
+    import FastMarching.FastMarching as FM
+    from oracle import oracle as O
+    g = np.load(f"{GOLDEN}/ref2d.npz")
+    for name, mk in (("kat3", lambda: rand_map((100, 100), 0)), ("plateau80", lambda: plateau_map(80, 3))):
+        c = mk()
+        gg, ss = list(g[f"{name}_g2"]), list(g[f"{name}_s2"])
+        TG, TS, j = FM.biComputeTmap(c, gg, ss)
+        assert j.dtype == np.uint32 and np.array_equal(j, g[f"{name}_join"])
+        oTG, oTS, _ = O.biComputeTmap(c, gg, ss)
+        assert rel_err(TG, oTG) < TOL64 and rel_err(TS, oTS) < TOL64
+        pG = FM.getPathGDM(TG, j, gg, 0.5)
+        assert pG.shape == g[f"{name}_pathG"].shape and np.abs(pG - g[f"{name}_pathG"]).max() < TOLP
+
+
+def test_dropin_replays_planner_calls():
+    """The five calls the unmodified planner makes (Coupled_motion_planner.py:1226-1230,
+    1636-1639), with the planner's own arguments (incl. the F-ordered costmap view)."""
+    import FastMarching.FastMarching as FM
+    import FastMarching.FastMarching3D as FM3D
+    from oracle import oracle as O
+    g = np.load(f"{GOLDEN}/planner_calls.npz")
+    cost = np.asfortranarray(g["bi_cost"])           # the planner passes cMap.T (F-ordered)
+    goal, start = [int(v) for v in g["bi_goal"]], [int(v) for v in g["bi_start"]]
+    TG, TS, j = FM.biComputeTmap(cost, goal, start)
+    assert np.array_equal(j, g["bi_join"]) and j.dtype == np.uint32
+    assert TG.flags.f_contiguous and TG.shape == cost.shape
+    oTG, oTS, _ = O.biComputeTmap(g["bi_cost"], goal, start)
+    assert rel_err(np.ascontiguousarray(TG), oTG) < TOL64 and rel_err(np.ascontiguousarray(TS), oTS) < TOL64
+    pG = FM.getPathGDM(TG, j, goal, 0.5)
+    pS = FM.getPathGDM(TS, j, start, 0.5)
+    assert pG.shape == g["pathG"].shape and np.abs(pG - g["pathG"]).max() < TOLP
+    assert pS.shape == g["pathS"].shape and np.abs(pS - g["pathS"]).max() < TOLP
+    T3 = FM3D.computeTmap(g["c3"], np.uint32(g["g3"]), np.uint32(g["s3"]))
+    assert rel_err(T3, O.computeTmap3D(g["c3"], list(g["g3"]), list(g["s3"]))) < TOL64
+    p3 = FM3D.getPathGDM(T3, np.uint32(g["path3d_init"]), np.uint32(g["path3d_end"]), 0.5)
+    assert p3.shape == g["path3d"].shape and np.abs(p3 - g["path3d"]).max() < TOLP
+
+
+def test_dropin_errors():
+    import FastMarching.FastMarching as FM
+    c = rand_map((40, 40), 0)
+    c[:, 20] = np.inf                                 # two disconnected halves: fronts never meet
+    with pytest.raises(NameError):
+        FM.biComputeTmap(c, [5, 5], [30, 30])
+    with pytest.raises(IndexError):
+        FM.biComputeTmap(c, [5, 5], [40, 3])

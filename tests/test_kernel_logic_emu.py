@@ -1,0 +1,110 @@
+"""CPU: the CUDA kernel SOURCE (csrc/*.cuh) executed under the host SIMT emulator
+(tools/host_emu) and compared with the oracle.  This checks kernel logic -- tile staging,
+masks, queue/tile-state protocol, tracer quirks -- where no GPU exists; the real parity
+tests (-m gpu) run the compiled sm_100a code through the C ABI."""
+import numpy as np
+import pytest
+
+import emu
+from conftest import GOLDEN, plateau_map, rand_map, rel_err
+from oracle import oracle as O
+
+TOL64 = 1e-9          # north_star: fp64 field within 1e-9 relative
+TOL32 = 1e-4          # fp32 variant within 1e-4
+TOLP = 1e-3           # waypoints within 1e-3 cell
+
+
+@pytest.mark.parametrize("shape,goal,tw", [((9, 9), [4, 4], 32), ((64, 64), [40, 12], 32), ((64, 64), [40, 12], 16),
+                                           ((45, 97), [95, 1], 32), ((33, 65), [32, 31], 16)])
+def test_solve2d_random(shape, goal, tw):
+    c = rand_map(shape, 7)
+    T, st = emu.solve2d(c, [goal], tw=tw)
+    assert rel_err(T[0], O.computeTmap(c, goal)) < TOL64
+    assert st["visits"] > 0
+
+
+def test_solve2d_plateau_and_walls():
+    c = plateau_map(80, 3)
+    c[30:50, 40] = np.inf              # a wall
+    c[10, 10:30] = np.inf
+    T, _ = emu.solve2d(c, [[20, 60]])
+    assert rel_err(T[0], O.computeTmap(c, [20, 60])) < TOL64
+
+
+def test_solve2d_enclosed_region_stays_inf():
+    c = rand_map((40, 40), 1)
+    c[10:20, 10] = c[10:20, 19] = c[10, 10:20] = c[19, 10:20] = np.inf
+    T, _ = emu.solve2d(c, [[3, 3]])
+    assert np.all(np.isinf(T[0][11:19, 11:19]))
+    assert rel_err(T[0], O.computeTmap(c, [3, 3])) < TOL64
+
+
+def test_solve2d_batch_shared_and_per_query_maps():
+    c = rand_map((48, 70), 2)
+    goals = [[5, 5], [60, 40], [31, 32], [32, 31]]      # incl. seeds on tile edges
+    T, _ = emu.solve2d(c, goals, nblocks=3)
+    for q, g in enumerate(goals):
+        assert rel_err(T[q], O.computeTmap(c, g)) < TOL64
+    cs = np.stack([rand_map((40, 40), s) for s in (1, 2, 3)])
+    T, _ = emu.solve2d(cs, [[20, 20]] * 3, shared=False)
+    for q in range(3):
+        assert rel_err(T[q], O.computeTmap(cs[q], [20, 20])) < TOL64
+
+
+def test_solve2d_fp32_variant():
+    c = rand_map((64, 64), 4)
+    T, _ = emu.solve2d(c.astype(np.float32), [[10, 50]])
+    ref = O.computeTmap(c.astype(np.float32).astype(np.float64), [10, 50])
+    assert rel_err(T[0].astype(np.float64), ref) < TOL32
+
+
+@pytest.mark.parametrize("shape,goal,tz", [((9, 9, 9), [4, 4, 4], 32), ((20, 20, 20), [4, 4, 4], 32),
+                                           ((13, 21, 40), [10, 5, 33], 16), ((10, 12, 28), [8, 7, 6], 32)])
+def test_solve3d_random(shape, goal, tz):
+    c = rand_map(shape, 5)
+    if shape == (20, 20, 20):
+        c[8:10, 3:15, 3:15] = np.inf
+    T, _ = emu.solve3d(c, [goal], tz=tz)
+    assert rel_err(T[0], O.computeTmap3D(c, goal)) < TOL64
+
+
+def test_solve3d_fp32_variant():
+    c = rand_map((12, 16, 20), 6)
+    T, _ = emu.solve3d(c.astype(np.float32), [[5, 5, 5]])
+    ref = O.computeTmap3D(c.astype(np.float32).astype(np.float64), [5, 5, 5])
+    assert rel_err(T[0].astype(np.float64), ref) < TOL32
+
+
+def test_trace2d_matches_oracle_paths():
+    g = np.load(f"{GOLDEN}/ref2d.npz")
+    c = rand_map((100, 100), 0)
+    TG, TS, j = O.biComputeTmap(c, [10, 10], [90, 90])
+    paths, st = emu.trace2d(np.stack([TG, TS]), [j, j], [[10, 10], [90, 90]])
+    assert st == [0, 0]
+    assert np.abs(paths[0] - g["kat3_pathG"]).max() < TOLP and np.abs(paths[1] - g["kat3_pathS"]).max() < TOLP
+    assert np.array_equal(paths[0][0], j.astype(float)) and np.array_equal(paths[0][-1], [10, 10])
+
+
+def test_trace2d_nan_fallback_and_errors():
+    c = rand_map((30, 30), 2)
+    c[15, 5:25] = np.inf
+    T = O.computeTmap(c, [5, 5], [25, 25])            # truncated field: start sits on the front
+    for init in ([25, 25], [25, 24], [14, 16]):
+        po, so = O.getPathGDM(T, np.array(init), [5, 5], 0.5, return_status=True)
+        p, s = emu.trace2d(T, [init], [[5, 5]])
+        assert s[0] == so and p[0].shape == po.shape
+        if len(po):
+            assert np.abs(p[0] - po).max() < TOLP
+    # stencil leaving the map -> IndexError status
+    p, s = emu.trace2d(T, [[29.2, 29.2]], [[5, 5]])
+    assert s[0] == 3 == O.getPathGDM(T, np.array([29.2, 29.2]), [5, 5], 0.5, return_status=True)[1]
+
+
+def test_trace3d_matches_oracle_paths():
+    g = np.load(f"{GOLDEN}/ref3d.npz")
+    c = rand_map((24, 24, 24), 0)
+    for tag, start in (("full", None), ("trunc", [18, 17, 16])):
+        F = O.computeTmap3D(c, [5, 6, 7], start)
+        p, s = emu.trace3d(F, [[18, 17, 16]], [[5, 6, 7]])
+        assert s == [0]
+        assert np.abs(p[0] - g[f"kat4_path_{tag}"]).max() < TOLP
