@@ -54,16 +54,6 @@ def _to_numpy_field(Tt: torch.Tensor, swap: bool) -> np.ndarray:
     return a.T if swap else a          # .T of a C array is F-ordered, like zeros_like() of the planner's view
 
 
-def _truncate(T: torch.Tensor, cost: torch.Tensor, rank: torch.Tensor, k: int) -> torch.Tensor:
-    """Partial field after k pops: accepted cells final, narrow band kept, the rest +inf."""
-    acc = rank <= k
-    band = _c.accepted_neighbour(acc) & ~acc & torch.isfinite(cost)
-    out = torch.full_like(T, float("inf"))
-    keep = acc | band
-    out[keep] = T[keep]
-    return out
-
-
 def computeTmap(costMap, goal, start):
     """Single-front total-cost map from ``goal``, stopping when ``start`` is accepted.
 
@@ -77,7 +67,7 @@ def computeTmap(costMap, goal, start):
     rows, cols = T0.shape
     if 0 <= s[0] < cols and 0 <= s[1] < rows and bool(torch.isfinite(T0[s[1], s[0]])):
         rank = _c.pop_ranks(T0)
-        T0 = _truncate(T0, cd, rank, int(rank[s[1], s[0]]))
+        T0 = _c.truncate(T0, cd, rank, int(rank[s[1], s[0]]))
     return _to_numpy_field(T0, swap)
 
 
@@ -92,7 +82,7 @@ def biComputeTmap(costMap, goal, start):
     both = torch.isfinite(TG) & torch.isfinite(TS)
     if not bool(both.any()):
         raise NameError("name 'nodeJoin' is not defined")
-    big = torch.iinfo(torch.int64).max
+    big = torch.iinfo(torch.int32).max
     m = torch.where(both, torch.maximum(rG, rS), torch.full_like(rG, big))
     k = int(m.min())
     cand = (m == k).reshape(-1)
@@ -103,8 +93,8 @@ def biComputeTmap(costMap, goal, start):
     j = int(pick[0]) if pick.numel() else int(idx[0])
     cols = TG.shape[1]
     jy, jx = divmod(j, cols)
-    TGt = _truncate(TG, cd, rG, k)
-    TSt = _truncate(TS, cd, rS, k)
+    TGt = _c.truncate(TG, cd, rG, k)
+    TSt = _c.truncate(TS, cd, rS, k)
     node = (jy, jx) if swap else (jx, jy)
     return _to_numpy_field(TGt, swap), _to_numpy_field(TSt, swap), np.uint32(node)
 

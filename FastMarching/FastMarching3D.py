@@ -16,15 +16,6 @@ from planning_motion_planning_b200 import engine
 from . import _compat as _c
 
 
-def _truncate(T, cost, rank, k):
-    acc = rank <= k
-    band = _c.accepted_neighbour(acc) & ~acc & torch.isfinite(cost)
-    out = torch.full_like(T, float("inf"))
-    keep = acc | band
-    out[keep] = T[keep]
-    return out
-
-
 def computeTmap(costMap, goal, start):
     """Total-cost volume from ``goal``; the reference stops as soon as ``start`` is accepted
     (FastMarching3D.py:141-142), so cells beyond that front are +inf.  Pass an unreachable
@@ -42,7 +33,7 @@ def computeTmap(costMap, goal, start):
     s = [int(np.int64(v)) for v in start]
     if 0 <= s[0] < nx and 0 <= s[1] < ny and 0 <= s[2] < nz and bool(torch.isfinite(T[s[1], s[0], s[2]])):
         rank = _c.pop_ranks(T)
-        T = _truncate(T, cd, rank, int(rank[s[1], s[0], s[2]]))
+        T = _c.truncate(T, cd, rank, int(rank[s[1], s[0], s[2]]))
     return T.cpu().numpy()
 
 

@@ -59,26 +59,30 @@ def raise_trace(status: int):
 # The solver always produces the full field; pop ranks are recovered by a stable
 # sort of T (ties in row-major order) and the partial field is rebuilt from them.
 def pop_ranks(T: torch.Tensor) -> torch.Tensor:
-    """rank[c] = number of nodes popped before-or-with c (source = 0, unreached = huge)."""
+    """int32 rank[c] = number of nodes popped before-or-with c (source = 0, unreached = INT32_MAX)."""
     flat = T.reshape(-1)
     order = torch.sort(flat, stable=True).indices
-    rank = torch.empty_like(order)
-    rank[order] = torch.arange(order.numel(), device=T.device)
-    rank[~torch.isfinite(flat)] = torch.iinfo(torch.int64).max
+    rank = torch.empty(flat.numel(), dtype=torch.int32, device=T.device)
+    rank[order] = torch.arange(flat.numel(), dtype=torch.int32, device=T.device)
+    rank[~torch.isfinite(flat)] = torch.iinfo(torch.int32).max
     return rank.reshape(T.shape)
 
 
-def accepted_neighbour(acc: torch.Tensor) -> torch.Tensor:
-    """True where at least one face neighbour is accepted (any number of dims)."""
-    nb = torch.zeros_like(acc)
-    for d in range(acc.dim()):
-        n = acc.shape[d]
-        if n < 2:
-            continue
-        lo = [slice(None)] * acc.dim()
-        hi = [slice(None)] * acc.dim()
-        lo[d] = slice(0, n - 1)
-        hi[d] = slice(1, n)
-        nb[tuple(hi)] |= acc[tuple(lo)]
-        nb[tuple(lo)] |= acc[tuple(hi)]
-    return nb
+def truncate(T: torch.Tensor, cost: torch.Tensor, rank: torch.Tensor, k: int) -> torch.Tensor:
+    """Partial field after k pops (accepted final, narrow band tentative, rest +inf), rebuilt on the
+    device by libfm_b200's fmb_truncate{2d,3d}_f64 (csrc/truncate.cuh)."""
+    T = T.contiguous()
+    cost = cost.contiguous()
+    rank = rank.contiguous()
+    out = torch.empty_like(T)
+    ovf = torch.zeros(1, dtype=torch.int32, device=T.device)
+    L = _capi.lib()
+    stream = torch.cuda.current_stream().cuda_stream
+    if T.dim() == 2:
+        rc = L.fmb_truncate2d_f64(T.data_ptr(), cost.data_ptr(), rank.data_ptr(), T.shape[0], T.shape[1], int(k),
+                                  out.data_ptr(), ovf.data_ptr(), stream)
+    else:
+        rc = L.fmb_truncate3d_f64(T.data_ptr(), cost.data_ptr(), rank.data_ptr(), T.shape[0], T.shape[1], T.shape[2],
+                                  int(k), out.data_ptr(), ovf.data_ptr(), stream)
+    _capi.check(rc)
+    return out

@@ -15,6 +15,9 @@
  *   fmb_trace2d_*        src/FastMarching/FastMarching.py:164-236  getPathGDM
  *                        src/FastMarching/FastMarching.py:242-338  computeGradient / interpolatePoint
  *   fmb_trace3d_*        src/FastMarching/FastMarching3D.py:198-314 getPathGDM / interpolatePoint
+ *   fmb_truncate2d_* /   the early-exit semantics of the reference loops
+ *   fmb_truncate3d_*     (FastMarching.py:108-109,150-155; FastMarching3D.py:141-142): turn a full
+ *                        field + pop ranks into the PARTIAL field the reference returns
  *
  * Conventions
  *  - Plain C, no torch types.  Every data pointer is a DEVICE pointer on the
@@ -65,6 +68,7 @@ typedef struct fmb_stats {
     uint64_t cells_written; /* T values stored to HBM */
     double solve_kernel_ms; /* device time of the last persistent solve kernel on this thread (CUDA events) */
     double init_kernel_ms;  /* device time of the init (fill + seed) launches that preceded it */
+    uint64_t cyc_wait, cyc_load, cyc_relax, cyc_store; /* warp-cycles per phase, summed over worker warps (2D) */
     uint64_t reserved[1];
 } fmb_stats;
 
@@ -123,6 +127,20 @@ int fmb_trace3d_f64(const double *d_T, int64_t T_qstride, int ny, int nx, int nz
                     int npaths, const int32_t *d_field_of_path,
                     const double *d_init, const double *d_end, double tau, int max_steps,
                     double *d_out, int64_t cap, int32_t *d_count, int32_t *d_status, void *stream);
+
+/* ---- early-exit emulation ------------------------------------------------------
+ * The reference returns partial fields: cells accepted within the first k pops are
+ * final, narrow-band cells hold the tentative value of their last relaxation, the
+ * rest is +inf.  Given the full field d_F, the costs, and d_rank (int32 pop rank of
+ * every cell: source 0, unreached INT32_MAX; a stable ascending sort of d_F), these
+ * rebuild that partial field for truncation after k pops.  Dense arrays.
+ * d_overflow (int32, zeroed by the caller) counts narrow-band cells whose replay
+ * exceeded the internal recursion depth (their value then falls back to d_F).
+ */
+int fmb_truncate2d_f64(const double *d_F, const double *d_cost, const int32_t *d_rank, int rows, int cols,
+                       int32_t k, double *d_out, int32_t *d_overflow, void *stream);
+int fmb_truncate3d_f64(const double *d_F, const double *d_cost, const int32_t *d_rank, int ny, int nx, int nz,
+                       int32_t k, double *d_out, int32_t *d_overflow, void *stream);
 
 #ifdef __cplusplus
 }

@@ -19,10 +19,12 @@ TRACE_OK, TRACE_EARLY, TRACE_VALUEERROR, TRACE_INDEXERROR, TRACE_OVERFLOW = 0, 1
 class FmbStats(C.Structure):
     _fields_ = [("tile_visits", C.c_uint64), ("steps", C.c_uint64), ("evals", C.c_uint64),
                 ("pushes", C.c_uint64), ("cells_written", C.c_uint64), ("solve_kernel_ms", C.c_double),
-                ("init_kernel_ms", C.c_double), ("reserved", C.c_uint64 * 1)]
+                ("init_kernel_ms", C.c_double), ("cyc_wait", C.c_uint64), ("cyc_load", C.c_uint64),
+                ("cyc_relax", C.c_uint64), ("cyc_store", C.c_uint64), ("reserved", C.c_uint64 * 1)]
 
     def as_dict(self):
-        d = {k: int(getattr(self, k)) for k in ("tile_visits", "steps", "evals", "pushes", "cells_written")}
+        d = {k: int(getattr(self, k)) for k in ("tile_visits", "steps", "evals", "pushes", "cells_written",
+                                                "cyc_wait", "cyc_load", "cyc_relax", "cyc_store")}
         d["solve_kernel_ms"] = float(self.solve_kernel_ms)
         d["init_kernel_ms"] = float(self.init_kernel_ms)
         return d
@@ -50,6 +52,8 @@ SIGNATURES = {
     "fmb_finish": (C.c_int, [_vp, _sz, _vp, C.POINTER(FmbStats)]),
     "fmb_trace2d_f64": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _dbl, _i32, _vp, _i64, _vp, _vp, _vp]),
     "fmb_trace3d_f64": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _dbl, _i32, _vp, _i64, _vp, _vp, _vp]),
+    "fmb_truncate2d_f64": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "fmb_truncate3d_f64": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
 }
 
 

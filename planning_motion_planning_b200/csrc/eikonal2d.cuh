@@ -27,6 +27,7 @@ struct Problem2D {
     int *tile_state;         // [nq*ntx*nty]
     Queue q;
     int step_cap;            // in-tile iteration cap (DEV_STEPCAP beyond)
+    int handoff;             // 1: a finishing warp keeps one of the tiles it activated (skips the queue)
 };
 
 // FastMarching.py:17-29 getEikonal, written branch-for-branch on the values
@@ -114,15 +115,18 @@ __global__ void __launch_bounds__(WARPS * 32) solve2d_kernel(Problem2D<real> P) 
     const int tiles_per_q = P.ntx * P.nty;
 
     unsigned long long n_visits = 0, n_steps = 0, n_evals = 0, n_pushes = 0, n_written = 0;
+    long long c_wait = 0, c_load = 0, c_relax = 0, c_store = 0;
     int item = -1;
 
     for (;;) {
+        const long long tc0 = clock64();
         if (item < 0) {
             int it = -1;
             if (lane == 0) it = q_pop_lane0(P.q);
             item = __shfl_sync(FULL, it, 0);
             if (item < 0) break;
         }
+        const long long tc1 = clock64();
         const int q = item / tiles_per_q;
         const int t = item - q * tiles_per_q;
         const int ty = t / P.ntx, tx = t - ty * P.ntx;
@@ -191,6 +195,7 @@ __global__ void __launch_bounds__(WARPS * 32) solve2d_kernel(Problem2D<real> P) 
         mask &= cmask;
 
         // ---- relax to the fixed point ---------------------------------------
+        const long long tc2 = clock64();
         unsigned dirty = 0;
         int last = 0, dir = 1, steps = 0;
         bool fail = false;
@@ -238,6 +243,7 @@ __global__ void __launch_bounds__(WARPS * 32) solve2d_kernel(Problem2D<real> P) 
             if (lane == 0) atomicCAS(&P.q.ctl->abort, 0, DEV_STEPCAP);
             break;
         }
+        const long long tc3 = clock64();
 
         // ---- write back changed cells (row by row, coalesced) ----------------
         for (int j = 0; j < TILE_H; ++j) {
@@ -271,21 +277,27 @@ __global__ void __launch_bounds__(WARPS * 32) solve2d_kernel(Problem2D<real> P) 
             for (int s = 0; s < 4; ++s) {
                 if (!act[s]) continue;
                 if (tile_activate(P.tile_state, P.q.ctl, nbr[s])) {
-                    if (next < 0) next = nbr[s];            // keep one for myself: no queue round trip
+                    if (next < 0 && P.handoff) next = nbr[s];     // keep one for myself: no queue round trip
                     else { q_push(P.q, nbr[s]); ++n_pushes; }
                 }
             }
             if (tile_finish(P.tile_state, P.q.ctl, item)) {
-                if (next < 0) next = item;
+                if (next < 0 && P.handoff) next = item;
                 else { q_push(P.q, item); ++n_pushes; }
             }
             if (ld_volatile(&P.q.ctl->abort)) next = -2;     // somebody failed: leave (warp-uniform via shfl)
         }
         item = __shfl_sync(FULL, next, 0);
+        const long long tc4 = clock64();
+        c_wait += tc1 - tc0; c_load += tc2 - tc1; c_relax += tc3 - tc2; c_store += tc4 - tc3;
         if (item == -2) break;
     }
     // per-warp counters (lane 0 holds the per-warp ones; evals/steps are warp-uniform)
     if (lane == 0) {
+        atomicAdd(&P.q.ctl->cyc_wait, (unsigned long long)c_wait);
+        atomicAdd(&P.q.ctl->cyc_load, (unsigned long long)c_load);
+        atomicAdd(&P.q.ctl->cyc_relax, (unsigned long long)c_relax);
+        atomicAdd(&P.q.ctl->cyc_store, (unsigned long long)c_store);
         atomicAdd(&P.q.ctl->visits, n_visits);
         atomicAdd(&P.q.ctl->steps, n_steps);
         atomicAdd(&P.q.ctl->evals, n_evals);

@@ -144,6 +144,7 @@ int solve2d(const real *d_cost, int64_t cost_pitch, int64_t cost_qstride, real *
     P.q.ring_mask = L.ring_slots - 1;
     P.q.watchdog_cycles = (long long)env_int("FMB_WATCHDOG_MS", 20000) * 2000000LL;   // ~2 GHz
     P.step_cap = env_int("FMB_STEP_CAP", 1 << 20);
+    P.handoff = env_int("FMB_HANDOFF", 0);
     cudaStream_t st = (cudaStream_t)stream;
     if (tw == 16) return launch_solve2d<real, 16>(P, L, st);
     return launch_solve2d<real, 32>(P, L, st);
@@ -184,6 +185,7 @@ int fmb_finish(void *d_ws, size_t ws_bytes, void *stream, fmb_stats *stats) {
         memset(stats, 0, sizeof(*stats));
         stats->tile_visits = h.visits; stats->steps = h.steps; stats->evals = h.evals;
         stats->pushes = h.pushes; stats->cells_written = h.cells_written;
+        stats->cyc_wait = h.cyc_wait; stats->cyc_load = h.cyc_load; stats->cyc_relax = h.cyc_relax; stats->cyc_store = h.cyc_store;
         if (g_tm.armed) {
             float a = 0.f, b = 0.f;
             if (cudaEventElapsedTime(&a, g_tm.e0, g_tm.e1) == cudaSuccess && cudaEventElapsedTime(&b, g_tm.e1, g_tm.e2) == cudaSuccess) {

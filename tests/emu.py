@@ -89,3 +89,28 @@ def trace2d(T, init, end, tau=0.5, field_of_path=None):
 
 def trace3d(T, init, end, tau=0.5, field_of_path=None):
     return _trace(lib().emu_trace3d_f64, T, 3, init, end, tau, field_of_path)
+
+
+def _ranks(F):
+    """Stable ascending sort of the full field -> int32 pop rank per cell (source 0)."""
+    flat = np.ascontiguousarray(F).reshape(-1)
+    order = np.argsort(flat, kind="stable")
+    rank = np.empty(flat.size, dtype=np.int32)
+    rank[order] = np.arange(flat.size, dtype=np.int32)
+    rank[~np.isfinite(flat)] = np.iinfo(np.int32).max
+    return rank
+
+
+def truncate(F, cost, k, rank=None):
+    F = np.ascontiguousarray(F, dtype=np.float64)
+    cost = np.ascontiguousarray(cost, dtype=np.float64)
+    rank = _ranks(F) if rank is None else np.ascontiguousarray(rank, dtype=np.int32)
+    out = np.empty_like(F)
+    L = lib()
+    if F.ndim == 2:
+        L.emu_truncate2d_f64.argtypes = [dp, dp, ip, C.c_int, C.c_int, C.c_int, dp]
+        ov = L.emu_truncate2d_f64(F.ctypes.data_as(dp), cost.ctypes.data_as(dp), rank.ctypes.data_as(ip), *F.shape, int(k), out.ctypes.data_as(dp))
+    else:
+        L.emu_truncate3d_f64.argtypes = [dp, dp, ip, C.c_int, C.c_int, C.c_int, C.c_int, dp]
+        ov = L.emu_truncate3d_f64(F.ctypes.data_as(dp), cost.ctypes.data_as(dp), rank.ctypes.data_as(ip), *F.shape, int(k), out.ctypes.data_as(dp))
+    return out, ov

@@ -108,3 +108,27 @@ def test_trace3d_matches_oracle_paths():
         p, s = emu.trace3d(F, [[18, 17, 16]], [[5, 6, 7]])
         assert s == [0]
         assert np.abs(p[0] - g[f"kat4_path_{tag}"]).max() < TOLP
+
+
+def test_truncate_rebuilds_reference_partial_fields():
+    """csrc/truncate.cuh under the emulator: early-exit (2D/3D) and bidirectional partial fields
+    equal the reference's, including every narrow-band tentative value."""
+    for c, g, s in ((rand_map((64, 64), 7), [40, 12], [57, 9]), (plateau_map(80, 3), [20, 60], [70, 71])):
+        F, Tt = O.computeTmap(c, g), O.computeTmap(c, g, s)
+        rank = emu._ranks(F)
+        out, ovf = emu.truncate(F, c, rank[s[1] * c.shape[1] + s[0]], rank)
+        assert ovf == 0 and np.array_equal(out, Tt)
+    c = rand_map((100, 100), 0)
+    TG, TS, j = O.biComputeTmap(c, [10, 10], [90, 90])
+    FG, FS = O.computeTmap(c, [10, 10]), O.computeTmap(c, [90, 90])
+    rG, rS = emu._ranks(FG), emu._ranks(FS)
+    m = np.maximum(rG, rS)
+    k = int(m.min())
+    jj = int(np.argmin(m))
+    assert [jj % 100, jj // 100] == list(j)
+    assert np.array_equal(emu.truncate(FG, c, k, rG)[0], TG) and np.array_equal(emu.truncate(FS, c, k, rS)[0], TS)
+    c3 = rand_map((24, 24, 24), 0)
+    F3, T3 = O.computeTmap3D(c3, [5, 6, 7]), O.computeTmap3D(c3, [5, 6, 7], [18, 17, 16])
+    r3 = emu._ranks(F3)
+    out, ovf = emu.truncate(F3, c3, r3[(17 * 24 + 18) * 24 + 16], r3)
+    assert ovf == 0 and np.array_equal(out, T3)

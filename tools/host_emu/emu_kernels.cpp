@@ -10,6 +10,7 @@
 #include "../../planning_motion_planning_b200/csrc/eikonal3d.cuh"
 #include "../../planning_motion_planning_b200/csrc/trace2d.cuh"
 #include "../../planning_motion_planning_b200/csrc/trace3d.cuh"
+#include "../../planning_motion_planning_b200/csrc/truncate.cuh"
 
 namespace {
 unsigned pow2_at_least(long long v) { unsigned p = 1024; while ((long long)p < v) p <<= 1; return p; }
@@ -28,7 +29,7 @@ int run2d(const real *cost, long long cost_qstride, real *T, int rows, int cols,
     std::vector<int> state(ntiles), ring(pow2_at_least(ntiles));
     fmb::QueueCtl ctl;
     P.tile_state = state.data(); P.q.ctl = &ctl; P.q.ring = ring.data(); P.q.ring_mask = (unsigned)ring.size() - 1;
-    P.q.watchdog_cycles = 1LL << 40; P.step_cap = 1 << 20;
+    P.q.watchdog_cycles = 1LL << 40; P.step_cap = 1 << 20; P.handoff = getenv("FMB_HANDOFF") ? atoi(getenv("FMB_HANDOFF")) : 0;
     emu::launch(2, 64, 0, [&] { fmb::init_fill2d_kernel<real>(P, (int)ring.size()); });
     emu::launch(1, 32 * ((nq + 31) / 32), 0, [&] { fmb::init_seed2d_kernel<real, TW>(P); });
     emu::launch(nblocks, WARPS * 32, fmb::Tile2D<real, TW>::WARP_BYTES * WARPS, [&] { fmb::solve2d_kernel<real, TW, WARPS>(P); });
@@ -95,6 +96,19 @@ void emu_trace3d_f64(const double *T, int ny, int nx, int nz, int npaths, const 
     A.field_of_path = field_of_path; A.init = init; A.end = end; A.tau = tau; A.max_steps = max_steps;
     A.out = out; A.cap = cap; A.count = count; A.status = status;
     emu::launch((npaths + 3) / 4, 128, 0, [&] { fmb::trace3d_kernel<double, 4>(A); });
+}
+
+int emu_truncate2d_f64(const double *F, const double *cost, const int *rank, int rows, int cols, int k, double *out) {
+    fmb::Grid<2> g; g.rows = rows; g.cols = cols;
+    int overflow = 0;
+    emu::launch(4, 64, 0, [&] { fmb::truncate_kernel<double, 2>(g, F, cost, rank, k, out, &overflow); });
+    return overflow;
+}
+int emu_truncate3d_f64(const double *F, const double *cost, const int *rank, int ny, int nx, int nz, int k, double *out) {
+    fmb::Grid<3> g; g.ny = ny; g.nx = nx; g.nz = nz;
+    int overflow = 0;
+    emu::launch(4, 64, 0, [&] { fmb::truncate_kernel<double, 3>(g, F, cost, rank, k, out, &overflow); });
+    return overflow;
 }
 
 }  // extern "C"
