@@ -105,17 +105,17 @@ def getPathGDM(totalCostMap, initWaypoint, endWaypoint, tau):
     c, swap = _c.as_c_field(totalCostMap)
     init = np.asarray(initWaypoint, dtype=np.float64).reshape(-1)[:2]
     end = np.asarray(endWaypoint, dtype=np.float64).reshape(-1)[:2]
-    if swap:
-        init, end = init[::-1].copy(), end[::-1].copy()
     dev = _c.device()
     Td = torch.from_numpy(np.ascontiguousarray(c)).to(dev)
+    if swap:
+        # unlike the solver, the tracer is NOT symmetric in x and y (the reference normalises dx
+        # first and reuses it for dy, FastMarching.py:226-227), so an F-ordered field is put back
+        # into [y, x] order on the device instead of tracing in swapped coordinates
+        Td = Td.T.contiguous()
     out, count, status = engine.trace2d(Td, init[None, :], end[None, :], tau)
     n, st = int(count[0]), int(status[0])
     _c.raise_trace(st)
-    path = out[0, :n].cpu().numpy()
-    if swap:
-        path = path[:, ::-1].copy()
-    return path
+    return out[0, :n].cpu().numpy()
 
 
 def computeGradient(cost, point=[]):

@@ -49,6 +49,13 @@ def _as_seeds(seeds, nq: int, dim: int, device) -> torch.Tensor:
     return s
 
 
+def _as_points(p, dim: int, device) -> torch.Tensor:
+    if isinstance(p, torch.Tensor):
+        return p.to(device=device, dtype=torch.float64).reshape(-1, dim).contiguous()
+    import numpy as np
+    return torch.from_numpy(np.ascontiguousarray(np.asarray(p, dtype=np.float64).reshape(-1, dim))).to(device)
+
+
 def last_stats() -> dict:
     """Counters of the most recent finished solve on the current device."""
     return dict(_LAST_STATS.get(torch.cuda.current_device(), {}))
@@ -131,8 +138,8 @@ def trace2d(T: torch.Tensor, init, end, tau: float = 0.5, field_of_path=None,
     T = T.contiguous()
     nf, rows, cols = T.shape
     dev = T.device
-    i = torch.as_tensor(init, dtype=torch.float64).reshape(-1, 2).to(dev).contiguous()
-    e = torch.as_tensor(end, dtype=torch.float64).reshape(-1, 2).to(dev).contiguous()
+    i = _as_points(init, 2, dev)
+    e = _as_points(end, 2, dev)
     npaths = i.shape[0]
     if e.shape[0] != npaths:
         raise ValueError("init and end must have the same number of rows")
@@ -206,8 +213,8 @@ def trace3d(T: torch.Tensor, init, end, tau: float = 0.5, field_of_path=None,
     T = T.contiguous()
     nf, ny, nx, nz = T.shape
     dev = T.device
-    i = torch.as_tensor(init, dtype=torch.float64).reshape(-1, 3).to(dev).contiguous()
-    e = torch.as_tensor(end, dtype=torch.float64).reshape(-1, 3).to(dev).contiguous()
+    i = _as_points(init, 3, dev)
+    e = _as_points(end, 3, dev)
     npaths = i.shape[0]
     if field_of_path is None:
         if nf == 1 and npaths > 1:
