@@ -27,7 +27,8 @@ struct Problem2D {
     int *tile_state;         // [nq*ntx*nty]
     Queue q;
     int step_cap;            // in-tile iteration cap (DEV_STEPCAP beyond)
-    int handoff;             // 1: a finishing warp keeps one of the tiles it activated (skips the queue)
+    unsigned long long *tile_prio;   // [nq*ntx*nty] ordered bits of the lowest activating value (best-first mode)
+    int best_first;          // 1: ring carries query ids, workers claim the lowest-priority queued tile
 };
 
 // FastMarching.py:17-29 getEikonal, written branch-for-branch on the values
@@ -49,7 +50,9 @@ __device__ __forceinline__ real eikonal_update(real a, real b, real c) {
 template <typename real, int TW>
 struct Tile2D {
     static constexpr int PT = TW + 2;                         // smem row pitch (even, PT-1 odd: conflict-free skews)
-    static constexpr int T_ELEMS = (TILE_H + 2) * PT;
+    // row j (-1..32) starts at (j+1)*PT: [+1] left halo, [+2 .. +TW+1] interior (16-byte aligned
+    // for cp.async), [+TW+2] right halo (= slot 0 of the next row, which is otherwise unused)
+    static constexpr int T_ELEMS = (TILE_H + 2) * PT + 2;
     static constexpr int C_ELEMS = TILE_H * PT;
     static constexpr int WARP_ELEMS = T_ELEMS + C_ELEMS;
     static constexpr size_t WARP_BYTES = sizeof(real) * WARP_ELEMS;
@@ -70,7 +73,10 @@ __global__ void init_fill2d_kernel(Problem2D<real> P, int ring_slots) {
         P.T[q * P.T_qstride + y * P.T_pitch + x] = INF;
     }
     const long long ntiles = (long long)P.nq * P.ntx * P.nty;
-    for (long long i = tid; i < ntiles; i += nth) P.tile_state[i] = ST_IDLE;
+    for (long long i = tid; i < ntiles; i += nth) {
+        P.tile_state[i] = ST_IDLE;
+        if (P.best_first) P.tile_prio[i] = 0x7ff0000000000000ULL;
+    }
     for (long long i = tid; i < ring_slots; i += nth) P.q.ring[i] = -1;
     if (tid == 0) {
         QueueCtl z = {};
@@ -97,35 +103,91 @@ __global__ void init_seed2d_kernel(Problem2D<real> P) {
     for (int k = 0; k < 5; ++k) {
         if (cand[k][0] < 0) continue;
         int item = base + cand[k][1] * P.ntx + cand[k][0];
-        if (tile_activate(P.tile_state, P.q.ctl, item)) { q_push(P.q, item); atomicAdd(&P.q.ctl->pushes, 1ULL); }
+        if (tile_activate(P.tile_state, P.q.ctl, item)) {
+            if (P.best_first) P.tile_prio[item] = 0ULL;
+            q_push(P.q, P.best_first ? q : item);
+            atomicAdd(&P.q.ctl->pushes, 1ULL);
+        }
     }
 }
 
 // ---------------------------------------------------------------------------
 // persistent solver
-template <typename real, int TW, int WARPS>
+//
+// BEST = false: tiles are popped in FIFO order (best for ONE large map: speculative early
+//               visits hide the serial chain of tile visits, tools/sched_model.c).
+// BEST = true : the ring carries query ids; a worker that holds a ticket for query q claims
+//               the QUEUED tile of q with the lowest priority (smallest value that activated
+//               it).  Per-query best-first order cuts re-visits several-fold when many
+//               independent queries share the GPU (batched planning).
+template <typename real, int TW, int WARPS, bool BEST>
 __global__ void __launch_bounds__(WARPS * 32) solve2d_kernel(Problem2D<real> P) {
     using TL = Tile2D<real, TW>;
     constexpr int PT = TL::PT;
+    constexpr unsigned ROWMASK = (TW == 32) ? 0xffffffffu : ((1u << TW) - 1u);
+    constexpr int ROWS_PER_IT = 32 / TW;                  // tile rows covered by one 32-lane load
+    constexpr int NIT_T = (TILE_H + 2) * TW / 32;         // 32-lane loads for T rows -1..32
+    constexpr int NIT_C = TILE_H * TW / 32;
     FMB_DYN_SMEM(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     real *sT = reinterpret_cast<real *>(smem_raw) + (size_t)warp * TL::WARP_ELEMS;
     real *sC = sT + TL::T_ELEMS;
     const real INF = num<real>::inf();
     const int tiles_per_q = P.ntx * P.nty;
+    const unsigned long long PRIO_INF = 0x7ff0000000000000ULL;
 
     unsigned long long n_visits = 0, n_steps = 0, n_evals = 0, n_pushes = 0, n_written = 0;
     long long c_wait = 0, c_load = 0, c_relax = 0, c_store = 0;
-    int item = -1;
 
     for (;;) {
         const long long tc0 = clock64();
-        if (item < 0) {
+        int item;
+        {
             int it = -1;
             if (lane == 0) it = q_pop_lane0(P.q);
             item = __shfl_sync(FULL, it, 0);
             if (item < 0) break;
         }
+        if (BEST) {
+            // `item` is a query id: claim its lowest-priority queued tile (QUEUED -> RUNNING)
+            const int base = item * tiles_per_q;
+            const long long t0 = clock64();
+            int claimed = -1;
+            while (claimed < 0) {
+                unsigned long long bp = ~0ULL;
+                int bt = -1;
+                for (int t = lane; t < tiles_per_q; t += 32) {
+                    if (ld_volatile(&P.tile_state[base + t]) == ST_QUEUED) {
+                        const unsigned long long pr = *reinterpret_cast<const volatile unsigned long long *>(&P.tile_prio[base + t]);
+                        if (pr < bp) { bp = pr; bt = t; }
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const unsigned long long op = __shfl_xor_sync(FULL, bp, o);
+                    const int ot = __shfl_xor_sync(FULL, bt, o);
+                    if (op < bp || (op == bp && ot >= 0 && (bt < 0 || ot < bt))) { bp = op; bt = ot; }
+                }
+                int ok = 0;
+                if (lane == 0 && bt >= 0) ok = atomicCAS(&P.tile_state[base + bt], ST_QUEUED, ST_RUNNING) == ST_QUEUED;
+                ok = __shfl_sync(FULL, ok, 0);
+                if (ok) { claimed = base + bt; break; }
+                int bail = 0;
+                if (lane == 0) {
+                    if (ld_volatile(&P.q.ctl->abort)) bail = 1;
+                    else if (clock64() - t0 > P.q.watchdog_cycles) { atomicCAS(&P.q.ctl->abort, 0, DEV_WATCHDOG); bail = 1; }
+                }
+                if (__shfl_sync(FULL, bail, 0)) break;
+            }
+            if (claimed < 0) break;
+            item = claimed;
+            if (lane == 0) { atomicExch(&P.tile_prio[item], PRIO_INF); __threadfence(); }
+        } else {
+            // QUEUED -> RUNNING *before* sampling T: anything published after this point flips
+            // the state to DIRTY and the tile is run again.
+            if (lane == 0) { atomicExch(&P.tile_state[item], ST_RUNNING); __threadfence(); }
+        }
+        __syncwarp();
         const long long tc1 = clock64();
         const int q = item / tiles_per_q;
         const int t = item - q * tiles_per_q;
@@ -134,51 +196,99 @@ __global__ void __launch_bounds__(WARPS * 32) solve2d_kernel(Problem2D<real> P) 
         const real *cq = P.cost + (long long)q * P.cost_qstride;
         real *Tq = P.T + (long long)q * P.T_qstride;
 
-        // QUEUED -> RUNNING *before* sampling T: anything published after this
-        // point flips the state to DIRTY and the tile is run again.
-        if (lane == 0) { atomicExch(&P.tile_state[item], ST_RUNNING); __threadfence(); }
-        __syncwarp();
-
-        // ---- stage tile + halo (rows -1..32 of TW cells, coalesced) ----------
-        for (int idx = lane; idx < (TILE_H + 2) * TW; idx += 32) {
-            const int j = idx / TW - 1, i = idx - (j + 1) * TW;
-            const int y = y0 + j, x = x0 + i;
-            real v = INF;
-            if (y >= 0 && y < P.rows && x < P.cols) v = ld_T(&Tq[(long long)y * P.T_pitch + x]);
-            sT[(j + 1) * PT + i + 1] = v;
-        }
-        {   // left / right halo columns (lane == row)
-            const int y = y0 + lane;
+        // ---- stage tile + halo ------------------------------------------------------------
+        // interior tiles with 16-byte aligned rows: every 16-byte chunk of the 34 T rows and the 32
+        // cost rows is put in flight with cp.async.cg (L2 only) and waited for once; edge / unaligned
+        // tiles take the register path (loads issued in batches before their smem stores).
+        unsigned cmask = 0;                              // cells that can ever be relaxed (finite cost)
+        {
+            const int y = y0 + lane;                     // left / right halo columns (lane == row)
             real vl = INF, vr = INF;
             if (y < P.rows) {
                 if (x0 > 0) vl = ld_T(&Tq[(long long)y * P.T_pitch + x0 - 1]);
                 if (x0 + TW < P.cols) vr = ld_T(&Tq[(long long)y * P.T_pitch + x0 + TW]);
             }
-            sT[(lane + 1) * PT] = vl;
-            sT[(lane + 1) * PT + TW + 1] = vr;
-        }
-        for (int idx = lane; idx < TILE_H * TW; idx += 32) {
-            const int j = idx / TW, i = idx - j * TW;
-            const int y = y0 + j, x = x0 + i;
-            real c = INF;
-            if (y < P.rows && x < P.cols) c = __ldg(&cq[(long long)y * P.cost_pitch + x]);
-            sC[j * PT + i] = c;
+            constexpr int EPC = 16 / (int)sizeof(real);                 // elements per 16-byte chunk
+            constexpr int CPR = TW / EPC;                               // chunks per tile row
+            // (fp32 rows are only 8-byte aligned in this smem layout: they take the register path)
+            const bool fast = sizeof(real) == 8 && y0 >= 1 && y0 + TILE_H < P.rows && x0 + TW <= P.cols &&
+                              (P.T_pitch % EPC) == 0 && (P.cost_pitch % EPC) == 0 &&
+                              ((size_t)Tq % 16) == 0 && ((size_t)cq % 16) == 0;
+            if (fast) {
+#pragma unroll
+                for (int c = lane; c < (TILE_H + 2) * CPR; c += 32) {
+                    const int row = c / CPR, col = (c % CPR) * EPC;
+                    cp_async16_cg(&sT[row * PT + 2 + col], &Tq[(long long)(y0 - 1 + row) * P.T_pitch + x0 + col]);
+                }
+#pragma unroll
+                for (int c = lane; c < TILE_H * CPR; c += 32) {
+                    const int row = c / CPR, col = (c % CPR) * EPC;
+                    cp_async16_cg(&sC[row * PT + col], &cq[(long long)(y0 + row) * P.cost_pitch + x0 + col]);
+                }
+                cp_async_wait_all();
+                __syncwarp();
+#pragma unroll 4
+                for (int j = 0; j < TILE_H; ++j) {
+                    const unsigned bal = __ballot_sync(FULL, lane < TW && sC[j * PT + (lane < TW ? lane : 0)] < INF);
+                    if (lane == j) cmask = bal;
+                }
+            } else {
+                constexpr int BT = 9;
+#pragma unroll
+                for (int b0 = 0; b0 < NIT_T; b0 += BT) {
+                    real v[BT];
+#pragma unroll
+                    for (int u = 0; u < BT; ++u) {
+                        const int idx = (b0 + u) * 32 + lane;
+                        const int j = idx / TW - 1, i = idx % TW;
+                        const int yy = y0 + j, xx = x0 + i;
+                        v[u] = INF;
+                        if (b0 + u < NIT_T && yy >= 0 && yy < P.rows && xx < P.cols) v[u] = ld_T(&Tq[(long long)yy * P.T_pitch + xx]);
+                    }
+#pragma unroll
+                    for (int u = 0; u < BT; ++u) {
+                        const int idx = (b0 + u) * 32 + lane;
+                        if (b0 + u < NIT_T) sT[(idx / TW) * PT + idx % TW + 2] = v[u];
+                    }
+                }
+                constexpr int BC = 8;
+#pragma unroll
+                for (int b0 = 0; b0 < NIT_C; b0 += BC) {
+                    real c[BC];
+#pragma unroll
+                    for (int u = 0; u < BC; ++u) {
+                        const int idx = (b0 + u) * 32 + lane;
+                        const int j = idx / TW, i = idx % TW;
+                        const int yy = y0 + j, xx = x0 + i;
+                        c[u] = INF;
+                        if (yy < P.rows && xx < P.cols) c[u] = __ldg(&cq[(long long)yy * P.cost_pitch + xx]);
+                    }
+#pragma unroll
+                    for (int u = 0; u < BC; ++u) {
+                        const int idx = (b0 + u) * 32 + lane;
+                        sC[(idx / TW) * PT + idx % TW] = c[u];
+                        const unsigned bal = __ballot_sync(FULL, c[u] < INF);
+#pragma unroll
+                        for (int sft = 0; sft < ROWS_PER_IT; ++sft)
+                            if (lane == (b0 + u) * ROWS_PER_IT + sft) cmask = (bal >> (sft * TW)) & ROWMASK;
+                    }
+                }
+            }
+            sT[(lane + 1) * PT + 1] = vl;
+            sT[(lane + 1) * PT + TW + 2] = vr;
         }
         __syncwarp();
 
-        // ---- per-row masks ---------------------------------------------------
-        real *rowT = sT + (lane + 1) * PT + 1;      // rowT[k] = T(row lane, col k); rowT[-1], rowT[TW] halos
+        // ---- arm the cells next to a lower halo value -------------------------
+        real *rowT = sT + (lane + 1) * PT + 2;      // rowT[k] = T(row lane, col k); rowT[-1], rowT[TW] halos
         const real *rowC = sC + lane * PT;
-        unsigned cmask = 0;                         // cells that can ever be relaxed (finite cost)
-#pragma unroll 8
-        for (int k = 0; k < TW; ++k) cmask |= (rowC[k] < INF ? 1u : 0u) << k;
         unsigned mask = 0;
         if (rowT[-1] < rowT[0]) mask |= 1u;
         if (rowT[TW] < rowT[TW - 1]) mask |= 1u << (TW - 1);
         {
             const bool in = lane < TW;
-            unsigned bt = __ballot_sync(FULL, in && sT[lane + 1] < sT[PT + lane + 1]);
-            unsigned bb = __ballot_sync(FULL, in && sT[(TILE_H + 1) * PT + lane + 1] < sT[TILE_H * PT + lane + 1]);
+            const unsigned bt = __ballot_sync(FULL, in && sT[lane + 2] < sT[PT + lane + 2]);
+            const unsigned bb = __ballot_sync(FULL, in && sT[(TILE_H + 1) * PT + lane + 2] < sT[TILE_H * PT + lane + 2]);
             if (lane == 0) mask |= bt;
             if (lane == TILE_H - 1) mask |= bb;
         }
@@ -195,104 +305,132 @@ __global__ void __launch_bounds__(WARPS * 32) solve2d_kernel(Problem2D<real> P) 
         mask &= cmask;
 
         // ---- relax to the fixed point ---------------------------------------
+        // One armed cell per lane per lock-step iteration.  Lanes that evaluate run converged, so
+        // every lane's shared-memory reads of an iteration precede that iteration's writes (a
+        // Jacobi step) and a single __syncwarp per iteration publishes the writes.
         const long long tc2 = clock64();
-        unsigned dirty = 0;
-        int last = 0, dir = 1, steps = 0;
-        bool fail = false;
+        unsigned dirty = 0, last = 0;
+        bool up = true;
+        int steps = 0;
+        real vmin = INF;
         unsigned active;
         while ((active = __ballot_sync(FULL, mask != 0)) != 0) {
-            int k = -1;
-            real v = INF, cur = INF, l = INF, r = INF, u = INF, d = INF;
+            unsigned up_msg = 0, dn_msg = 0;
             if (mask) {
-                // continue in the current direction along the row, turn round at the end
+                // keep sweeping in the current direction along the row, turn round at its end
                 const unsigned hi = mask & (~0u << last);
                 const unsigned lo = mask & ((2u << last) - 1u);
-                if (dir > 0) {
-                    if (hi) k = __ffs(hi) - 1; else { k = 31 - __clz(lo); dir = -1; }
-                } else {
-                    if (lo) k = 31 - __clz(lo); else { k = __ffs(hi) - 1; dir = 1; }
-                }
+                up = up ? (hi != 0) : (lo == 0);
+                const unsigned k = up ? (unsigned)(__ffs(hi) - 1) : (unsigned)(31 - __clz(lo));
                 last = k;
-                mask &= ~(1u << k);
-                const real *p = rowT + k;
-                l = p[-1]; r = p[1]; u = p[-PT]; d = p[PT]; cur = p[0];
-                v = eikonal_update<real>(fmin(l, r), fmin(u, d), rowC[k]);
+                const unsigned bit = 1u << k;
+                mask &= ~bit;
+                real *p = rowT + k;
+                const real l = p[-1], r = p[1], u = p[-PT], d = p[PT], cur = p[0];
+                const real v = eikonal_update<real>(l < r ? l : r, u < d ? u : d, rowC[k]);
+                if (v < cur) {
+                    *p = v;
+                    dirty |= bit;
+                    mask |= (l > v ? bit >> 1 : 0u) | (r > v ? bit << 1 : 0u);   // only neighbours that can still improve
+                    up_msg = u > v ? bit : 0u;
+                    dn_msg = d > v ? bit : 0u;
+                    if (BEST) vmin = v < vmin ? v : vmin;
+                }
             }
-            __syncwarp();                     // every lane has read before anyone writes (Jacobi step)
-            int up_msg = -1, dn_msg = -1;
-            if (k >= 0 && v < cur) {
-                rowT[k] = v;
-                dirty |= 1u << k;
-                if (k > 0 && l > v) mask |= 1u << (k - 1);
-                if (k < TW - 1 && r > v) mask |= 1u << (k + 1);
-                if (u > v) up_msg = k;
-                if (d > v) dn_msg = k;
-            }
-            const int from_below = __shfl_down_sync(FULL, up_msg, 1);   // lane+1 asks me to re-check column
-            const int from_above = __shfl_up_sync(FULL, dn_msg, 1);
-            if (lane < TILE_H - 1 && from_below >= 0) mask |= 1u << from_below;
-            if (lane > 0 && from_above >= 0) mask |= 1u << from_above;
-            mask &= cmask;
-            __syncwarp();                     // writes visible to the next iteration's reads
+            unsigned from_below = __shfl_down_sync(FULL, up_msg, 1);   // row+1 improved and my cell above it is larger
+            unsigned from_above = __shfl_up_sync(FULL, dn_msg, 1);
+            if (lane == TILE_H - 1) from_below = 0;
+            if (lane == 0) from_above = 0;
+            mask = (mask | from_below | from_above) & cmask;
+            __syncwarp();
             n_evals += __popc(active);
-            if (++steps > P.step_cap) { fail = true; break; }
+            if (++steps > P.step_cap) break;
         }
         n_steps += steps;
         ++n_visits;
-        if (fail) {
+        if (steps > P.step_cap) {
             if (lane == 0) atomicCAS(&P.q.ctl->abort, 0, DEV_STEPCAP);
             break;
         }
         const long long tc3 = clock64();
 
-        // ---- write back changed cells (row by row, coalesced) ----------------
-        for (int j = 0; j < TILE_H; ++j) {
-            const unsigned dj = __shfl_sync(FULL, dirty, j);
-            if (dj == 0) continue;
-            if (lane < TW && ((dj >> lane) & 1u)) {
-                st_T(&Tq[(long long)(y0 + j) * P.T_pitch + x0 + lane], sT[(j + 1) * PT + lane + 1]);
+        // ---- write back changed cells (dirty rows only, coalesced) ---------------
+        {
+            unsigned rows_dirty = __ballot_sync(FULL, dirty != 0);
+            while (rows_dirty) {
+                const int j = __ffs(rows_dirty) - 1;
+                rows_dirty &= rows_dirty - 1;
+                const unsigned dj = __shfl_sync(FULL, dirty, j);
+                if (lane < TW && ((dj >> lane) & 1u))
+                    st_T(&Tq[(long long)(y0 + j) * P.T_pitch + x0 + lane], sT[(j + 1) * PT + lane + 2]);
+                n_written += __popc(dj);
             }
-            n_written += __popc(dj);
         }
         // ---- which neighbours can still improve? ----------------------------
-        // only an edge cell that changed in this visit AND undercuts the value
-        // across the edge can lower anything in the neighbour (causality).
+        // only an edge cell that changed in this visit AND undercuts the value across the edge
+        // can lower anything in the neighbour (causality).
         const bool nl = (dirty & 1u) && rowT[0] < rowT[-1];
         const bool nr = ((dirty >> (TW - 1)) & 1u) && rowT[TW - 1] < rowT[TW];
         const unsigned d_top = __shfl_sync(FULL, dirty, 0), d_bot = __shfl_sync(FULL, dirty, TILE_H - 1);
-        const bool nt = lane < TW && ((d_top >> lane) & 1u) && sT[PT + lane + 1] < sT[lane + 1];
-        const bool nb = lane < TW && ((d_bot >> lane) & 1u) && sT[TILE_H * PT + lane + 1] < sT[(TILE_H + 1) * PT + lane + 1];
-        const bool actL = __any_sync(FULL, nl) && tx > 0;
-        const bool actR = __any_sync(FULL, nr) && tx < P.ntx - 1;
-        const bool actT = __any_sync(FULL, nt) && ty > 0;
-        const bool actB = __any_sync(FULL, nb) && ty < P.nty - 1;
-        __threadfence();          // my T stores are device-visible ...
-        __syncwarp();             // ... before lane 0 publishes the activations
-        int next = -1;
-        if (lane == 0) {
-            __threadfence();
-            const int nbr[4] = {item - 1, item + 1, item - P.ntx, item + P.ntx};
-            const bool act[4] = {actL, actR, actT, actB};
+        const bool nt = lane < TW && ((d_top >> lane) & 1u) && sT[PT + lane + 2] < sT[lane + 2];
+        const bool nb = lane < TW && ((d_bot >> lane) & 1u) && sT[TILE_H * PT + lane + 2] < sT[(TILE_H + 1) * PT + lane + 2];
+        unsigned act = 0;
+        if (__any_sync(FULL, nl) && tx > 0) act |= 1u;
+        if (__any_sync(FULL, nr) && tx < P.ntx - 1) act |= 2u;
+        if (__any_sync(FULL, nt) && ty > 0) act |= 4u;
+        if (__any_sync(FULL, nb) && ty < P.nty - 1) act |= 8u;
+        unsigned long long pbits = PRIO_INF;
+        if (BEST) {     // priority handed to the neighbours: the lowest value this visit produced
 #pragma unroll
-            for (int s = 0; s < 4; ++s) {
-                if (!act[s]) continue;
-                if (tile_activate(P.tile_state, P.q.ctl, nbr[s])) {
-                    if (next < 0 && P.handoff) next = nbr[s];     // keep one for myself: no queue round trip
-                    else { q_push(P.q, nbr[s]); ++n_pushes; }
-                }
-            }
-            if (tile_finish(P.tile_state, P.q.ctl, item)) {
-                if (next < 0 && P.handoff) next = item;
-                else { q_push(P.q, item); ++n_pushes; }
-            }
-            if (ld_volatile(&P.q.ctl->abort)) next = -2;     // somebody failed: leave (warp-uniform via shfl)
+            for (int o = 16; o > 0; o >>= 1) { const real ov = __shfl_xor_sync(FULL, vmin, o); vmin = ov < vmin ? ov : vmin; }
+            pbits = (unsigned long long)__double_as_longlong((double)vmin);
         }
-        item = __shfl_sync(FULL, next, 0);
+        // Publishing.  `pending` is raised for every candidate first (fire-and-forget, ordered by the
+        // same fence as the T stores) and corrected afterwards, so it never under-counts.  Lanes 0..3
+        // then try one neighbour each and lane 4 retires this tile IN THE SAME compare-and-swap
+        // instruction, so the common case costs one atomic round trip instead of five.
+        const int nact = __popc(act);
+        if (lane == 0 && nact) atomicAdd(&P.q.ctl->pending, nact);
+        if (BEST && lane < 4 && ((act >> lane) & 1u))
+            atomicMin(&P.tile_prio[item + (lane == 0 ? -1 : lane == 1 ? 1 : lane == 2 ? -P.ntx : P.ntx)], pbits);
+        __threadfence();          // T stores (+ pending, priorities) are device-visible ...
+        __syncwarp();             // ... before any state transition is published
+        bool pushed = false, newly = false, requeue = false;
+        {
+            const bool is_nbr = lane < 4 && ((act >> lane) & 1u);
+            const bool is_self = lane == 4;
+            const int tgt = is_self ? item : item + (lane == 0 ? -1 : lane == 1 ? 1 : lane == 2 ? -P.ntx : P.ntx);
+            if (is_nbr || is_self) {
+                int *st = &P.tile_state[tgt];
+                int old = atomicCAS(st, is_self ? ST_RUNNING : ST_IDLE, is_self ? ST_IDLE : ST_QUEUED);
+                if (is_self) {
+                    if (old != ST_RUNNING) { atomicExch(st, ST_QUEUED); requeue = true; }     // was DIRTY: run again
+                } else {
+                    for (;;) {
+                        if (old == ST_IDLE) { newly = true; break; }
+                        if (old == ST_QUEUED || old == ST_DIRTY) break;
+                        if (atomicCAS(st, ST_RUNNING, ST_DIRTY) == ST_RUNNING) break;          // ask the runner to go again
+                        old = atomicCAS(st, ST_IDLE, ST_QUEUED);
+                    }
+                }
+                if (newly || requeue) { q_push(P.q, BEST ? q : tgt); pushed = true; }
+            }
+        }
+        const int n_new = __popc(__ballot_sync(FULL, newly));
+        const int n_req = __popc(__ballot_sync(FULL, requeue));
+        n_pushes += __popc(__ballot_sync(FULL, pushed));
+        int stop = 0;
+        if (lane == 0) {
+            const int drop = (nact - n_new) + (n_req ? 0 : 1);
+            if (drop) atomicSub(&P.q.ctl->pending, drop);
+            stop = ld_volatile(&P.q.ctl->abort);
+        }
+        stop = __shfl_sync(FULL, stop, 0);
         const long long tc4 = clock64();
         c_wait += tc1 - tc0; c_load += tc2 - tc1; c_relax += tc3 - tc2; c_store += tc4 - tc3;
-        if (item == -2) break;
+        if (stop) break;
     }
-    // per-warp counters (lane 0 holds the per-warp ones; evals/steps are warp-uniform)
+    // per-warp counters (warp-uniform values; lane 0 reports)
     if (lane == 0) {
         atomicAdd(&P.q.ctl->cyc_wait, (unsigned long long)c_wait);
         atomicAdd(&P.q.ctl->cyc_load, (unsigned long long)c_load);

@@ -66,7 +66,7 @@ unsigned pow2_at_least(long long v) {
 
 // workspace layout: [QueueCtl | pad to 256] [tile_state: ntiles ints] [ring: slots ints]
 struct WsLayout {
-    size_t ctl_off, state_off, ring_off, total;
+    size_t ctl_off, state_off, ring_off, prio_off, total;
     unsigned ring_slots;
 };
 WsLayout ws_layout(long long ntiles) {
@@ -76,7 +76,8 @@ WsLayout ws_layout(long long ntiles) {
     size_t st = ((size_t)ntiles * sizeof(int) + 255) & ~(size_t)255;
     L.ring_off = L.state_off + st;
     L.ring_slots = pow2_at_least(ntiles);
-    L.total = L.ring_off + (size_t)L.ring_slots * sizeof(int);
+    L.prio_off = (L.ring_off + (size_t)L.ring_slots * sizeof(int) + 255) & ~(size_t)255;
+    L.total = L.prio_off + (size_t)ntiles * sizeof(unsigned long long);
     return L;
 }
 
@@ -87,11 +88,11 @@ long long tiles2d(int rows, int cols, int tw) {
     return (long long)((cols + tw - 1) / tw) * ((rows + fmb::TILE_H - 1) / fmb::TILE_H);
 }
 
-template <typename real, int TW>
+template <typename real, int TW, bool BEST>
 int launch_solve2d(fmb::Problem2D<real> P, const WsLayout &L, cudaStream_t st) {
     using TL = fmb::Tile2D<real, TW>;
     const size_t smem = TL::WARP_BYTES * WARPS;
-    auto kern = fmb::solve2d_kernel<real, TW, WARPS>;
+    auto kern = fmb::solve2d_kernel<real, TW, WARPS, BEST>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(solve2d)");
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem), "occupancy(solve2d)");
@@ -144,10 +145,18 @@ int solve2d(const real *d_cost, int64_t cost_pitch, int64_t cost_qstride, real *
     P.q.ring_mask = L.ring_slots - 1;
     P.q.watchdog_cycles = (long long)env_int("FMB_WATCHDOG_MS", 20000) * 2000000LL;   // ~2 GHz
     P.step_cap = env_int("FMB_STEP_CAP", 1 << 20);
-    P.handoff = env_int("FMB_HANDOFF", 0);
+    P.tile_prio = (unsigned long long *)(ws + L.prio_off);
+    // best-first per query pays off when many queries share the GPU and a query's tile table is
+    // small enough to scan per claim; one large map is faster in plain FIFO order
+    const long long tiles_per_q = ntiles / nq;
+    P.best_first = env_int("FMB_BEST_FIRST", (nq >= 8 && tiles_per_q <= 4096) ? 1 : 0);
     cudaStream_t st = (cudaStream_t)stream;
-    if (tw == 16) return launch_solve2d<real, 16>(P, L, st);
-    return launch_solve2d<real, 32>(P, L, st);
+    if (P.best_first) {
+        if (tw == 16) return launch_solve2d<real, 16, true>(P, L, st);
+        return launch_solve2d<real, 32, true>(P, L, st);
+    }
+    if (tw == 16) return launch_solve2d<real, 16, false>(P, L, st);
+    return launch_solve2d<real, 32, false>(P, L, st);
 }
 
 }  // namespace

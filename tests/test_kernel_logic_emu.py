@@ -23,6 +23,17 @@ def test_solve2d_random(shape, goal, tw):
     assert st["visits"] > 0
 
 
+@pytest.mark.parametrize("tw", [32, 16])
+def test_solve2d_interior_tiles_take_the_cp_async_path(tw):
+    """100x100 has fully interior tiles (16-byte aligned rows): exercises the bulk-staging path."""
+    c = rand_map((100, 100), 0)
+    T, _ = emu.solve2d(c, [[25, 25]], tw=tw)
+    assert rel_err(T[0], O.computeTmap(c, [25, 25])) < TOL64
+    c = rand_map((101, 99), 1)                 # odd pitch: register path everywhere
+    T, _ = emu.solve2d(c, [[70, 40]], tw=tw)
+    assert rel_err(T[0], O.computeTmap(c, [70, 40])) < TOL64
+
+
 def test_solve2d_plateau_and_walls():
     c = plateau_map(80, 3)
     c[30:50, 40] = np.inf              # a wall
@@ -52,7 +63,7 @@ def test_solve2d_batch_shared_and_per_query_maps():
 
 
 def test_solve2d_fp32_variant():
-    c = rand_map((64, 64), 4)
+    c = rand_map((100, 100), 4)
     T, _ = emu.solve2d(c.astype(np.float32), [[10, 50]])
     ref = O.computeTmap(c.astype(np.float32).astype(np.float64), [10, 50])
     assert rel_err(T[0].astype(np.float64), ref) < TOL32

@@ -35,7 +35,7 @@ namespace emu {
 
 struct dim3_ { unsigned x = 1, y = 1, z = 1; };
 
-enum Coll { C_NONE = 0, C_SHFL, C_SHFL_UP, C_SHFL_DOWN, C_BALLOT, C_ANY, C_SYNC };
+enum Coll { C_NONE = 0, C_SHFL, C_SHFL_UP, C_SHFL_DOWN, C_SHFL_XOR, C_BALLOT, C_ANY, C_SYNC };
 
 struct Warp;
 struct Lane {
@@ -95,6 +95,7 @@ inline void resolve(Warp *w) {
             case C_SHFL: l.result = w->lanes[l.arg & 31].payload; break;
             case C_SHFL_UP: l.result = (i - l.arg >= 0) ? w->lanes[i - l.arg].payload : l.payload; break;
             case C_SHFL_DOWN: l.result = (i + l.arg < 32) ? w->lanes[i + l.arg].payload : l.payload; break;
+            case C_SHFL_XOR: l.result = w->lanes[(i ^ l.arg) & 31].payload; break;
             case C_BALLOT: l.result = ballot; break;
             case C_ANY: l.result = ballot != 0; break;
             default: l.result = 0; break;
@@ -164,6 +165,7 @@ template <typename T> inline T emu_unbits(uint64_t b) { T v; memcpy(&v, &b, size
 template <typename T> inline T __shfl_sync(unsigned, T v, int src) { return emu_unbits<T>(emu::collective(emu::C_SHFL, emu_bits(v), src)); }
 template <typename T> inline T __shfl_up_sync(unsigned, T v, int d) { return emu_unbits<T>(emu::collective(emu::C_SHFL_UP, emu_bits(v), d)); }
 template <typename T> inline T __shfl_down_sync(unsigned, T v, int d) { return emu_unbits<T>(emu::collective(emu::C_SHFL_DOWN, emu_bits(v), d)); }
+template <typename T> inline T __shfl_xor_sync(unsigned, T v, int m) { return emu_unbits<T>(emu::collective(emu::C_SHFL_XOR, emu_bits(v), m)); }
 inline unsigned __ballot_sync(unsigned, bool p) { return (unsigned)emu::collective(emu::C_BALLOT, p ? 1 : 0, 0); }
 inline bool __any_sync(unsigned, bool p) { return emu::collective(emu::C_ANY, p ? 1 : 0, 0) != 0; }
 inline void __syncwarp() { emu::collective(emu::C_SYNC, 0, 0); }
@@ -175,12 +177,21 @@ inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_S
 inline int atomicSub(int *p, int v) { return __atomic_fetch_sub(p, v, __ATOMIC_SEQ_CST); }
 inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline int atomicExch(int *p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned long long atomicMin(unsigned long long *p, unsigned long long v) {
+    unsigned long long old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+    while (v < old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+    return old;
+}
+inline unsigned long long atomicExch(unsigned long long *p, unsigned long long v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
+inline long long __double_as_longlong(double v) { long long b; memcpy(&b, &v, 8); return b; }
 inline int atomicCAS(int *p, int cmp, int v) { __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST); return cmp; }
 
 template <typename T> inline T __ldcg(const T *p) { return *(const volatile T *)p; }
 template <typename T> inline T __ldg(const T *p) { return *p; }
 template <typename T> inline void __stcg(T *p, T v) { *(volatile T *)p = v; }
 
+inline void cp_async16_cg_emu(void *d, const void *s) { memcpy(d, s, 16); }
+namespace fmb { inline void cp_async16_cg(void *d, const void *s) { memcpy(d, s, 16); } inline void cp_async_wait_all() {} }
 inline int __ffs(unsigned v) { return v ? __builtin_ctz(v) + 1 : 0; }
 inline int __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }

@@ -29,10 +29,14 @@ int run2d(const real *cost, long long cost_qstride, real *T, int rows, int cols,
     std::vector<int> state(ntiles), ring(pow2_at_least(ntiles));
     fmb::QueueCtl ctl;
     P.tile_state = state.data(); P.q.ctl = &ctl; P.q.ring = ring.data(); P.q.ring_mask = (unsigned)ring.size() - 1;
-    P.q.watchdog_cycles = 1LL << 40; P.step_cap = 1 << 20; P.handoff = getenv("FMB_HANDOFF") ? atoi(getenv("FMB_HANDOFF")) : 0;
+    P.q.watchdog_cycles = 1LL << 40; P.step_cap = 1 << 20;
+    std::vector<unsigned long long> prio(ntiles);
+    P.tile_prio = prio.data();
+    P.best_first = getenv("FMB_BEST_FIRST") ? atoi(getenv("FMB_BEST_FIRST")) : 0;
     emu::launch(2, 64, 0, [&] { fmb::init_fill2d_kernel<real>(P, (int)ring.size()); });
     emu::launch(1, 32 * ((nq + 31) / 32), 0, [&] { fmb::init_seed2d_kernel<real, TW>(P); });
-    emu::launch(nblocks, WARPS * 32, fmb::Tile2D<real, TW>::WARP_BYTES * WARPS, [&] { fmb::solve2d_kernel<real, TW, WARPS>(P); });
+    if (P.best_first) emu::launch(nblocks, WARPS * 32, fmb::Tile2D<real, TW>::WARP_BYTES * WARPS, [&] { fmb::solve2d_kernel<real, TW, WARPS, true>(P); });
+    else emu::launch(nblocks, WARPS * 32, fmb::Tile2D<real, TW>::WARP_BYTES * WARPS, [&] { fmb::solve2d_kernel<real, TW, WARPS, false>(P); });
     if (stats) { stats[0] = ctl.visits; stats[1] = ctl.steps; stats[2] = ctl.evals; stats[3] = ctl.pushes; stats[4] = ctl.cells_written; }
     return ctl.abort ? ctl.abort : (ctl.pending != 0 ? -1 : 0);
 }
