@@ -47,7 +47,9 @@ def parse():
     ap.add_argument("--size", type=int, default=4096, help="map side (default: the metric's 4096)")
     ap.add_argument("--map", default="mars", choices=["mars", "random"])
     ap.add_argument("--no-batch", action="store_true", help="skip the batched-queries section")
-    ap.add_argument("--batch-queries", type=int, default=256, help="512^2 queries per GPU in the batched section")
+    ap.add_argument("--batch-queries", type=int, default=1024, help="512^2 queries per GPU in the batched section")
+    ap.add_argument("--no-3d", action="store_true", help="skip the 3D (arm-workspace volume) section")
+    ap.add_argument("--size3d", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -289,9 +291,19 @@ def own_arm(args):
     peak, peak_src = measured_peak()
     alg_bytes = 2 * 8 * cells
     achieved = alg_bytes / (solve_ms * 1e-3) / 1e9
+    traffic, traffic_src = None, None
+    try:        # DRAM bytes of one launch of this kernel on this workload, from the committed ncu capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        if n == 4096 and args.map == "mars":
+            ent = tj["solve2d_kernel<double,32,4,false>|4096x4096 mars seed0|fifo"]
+            traffic, traffic_src = ent["dram_bytes_read"] + ent["dram_bytes_write"], ent["source"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "solve2d_kernel<double,32,4>", "kernel_ms": solve_ms,
-                "algorithmic_bytes": alg_bytes, "peak_source": peak_src}
+                "traffic": traffic, "traffic_source": traffic_src,
+                "kernel": "solve2d_kernel<double,32,4,false>", "kernel_ms": solve_ms,
+                "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
+                "note": "single-source solve is dependency-latency bound (DESIGN.md 5); see batch.roofline_frac_solve_kernel for the throughput regime"}
 
     # ---- end to end through the public API with host buffers
     T_h = torch.empty((1, n, n), dtype=torch.float64).pin_memory()
@@ -364,6 +376,40 @@ def own_arm(args):
                  "roofline_frac_solve_kernel": (2 * 8 * bcells / (sb["solve_kernel_ms"] * 1e-3) / 1e9) / peak,
                  "evals_per_cell": sb["evals"] / bcells}
 
+    # ---- coupled plan, 3D half (config 3): arm-workspace cost volume solve + path
+    vol = None
+    if not args.no_3d and rank == 0:
+        from planning_motion_planning_b200 import synth
+        m3 = args.size3d
+        cache = f"/tmp/fmb_vol_{m3}.npz"
+        if os.path.exists(cache):
+            z = np.load(cache)
+            c3, g3, s3 = z["c"], z["g"].tolist(), z["s"].tolist()
+        else:
+            c3, g3, s3 = synth.arm_volume((m3, m3, m3), 0)
+            try:
+                np.savez(cache, c=c3, g=np.array(g3), s=np.array(s3))
+            except Exception:
+                pass
+        c3d = torch.from_numpy(c3).to(dev)
+        T3 = torch.empty((1, m3, m3, m3), dtype=torch.float64, device=dev)
+        ks, ts = [], []
+        for _ in range(4):
+            engine.solve3d(c3d, [g3], out=T3, nq=1, sync=False)
+            s3d = engine.finish(dev)
+            ks.append(s3d["solve_kernel_ms"])
+            e0.record()
+            o3, n3, st3 = engine.trace3d(T3, [s3], [g3], tau)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        k3 = float(np.mean(ks[1:]))
+        vol = {"workload": f"{m3}^3 fp64 planner-like arm-workspace volume: full-field solve + 1 path",
+               "solve_kernel_ms": k3, "trace_ms": float(np.mean(ts[1:])), "cells_per_s": m3 ** 3 / (k3 * 1e-3),
+               "roofline_frac_solve_kernel": (2 * 8 * m3 ** 3 / (k3 * 1e-3) / 1e9) / peak,
+               "evals_per_cell": s3d["evals"] / m3 ** 3, "path_rows": int(n3[0]), "path_status": int(st3[0])}
+        del c3d, T3
+
     # ---- CPU baseline beside it (rank 0, N == 1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -397,7 +443,7 @@ def own_arm(args):
             "breakdown_ms": {"init_fill": init_ms, "solve_kernel": solve_ms, "trace_kernel": trace_ms},
             "solver_stats": {k: stats[k] for k in ("tile_visits", "steps", "evals", "pushes", "cells_written")},
             "evals_per_cell": stats["evals"] / cells,
-            "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "batch": batch,
+            "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "batch": batch, "volume3d": vol,
             "gpu_launches": 4 * K, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

@@ -77,12 +77,14 @@ template <typename real, int TZ>
 struct Tile3D {
     static constexpr int PZ = TZ + 2;                          // z pitch incl. halo
     static constexpr int PS = (T3X + 2) * PZ;                  // y-slab pitch
-    static constexpr int T_ELEMS = (T3Y + 2) * PS;
+    // column (y,x) starts at (y+1)*PS + (x+1)*PZ: [+1] low z halo, [+2 .. +TZ+1] interior (16-byte
+    // aligned for cp.async), [+TZ+2] high z halo (= slot 0 of the next column, otherwise unused)
+    static constexpr int T_ELEMS = (T3Y + 2) * PS + 2;
     static constexpr int C_ELEMS = T3Y * T3X * PZ;
     static constexpr int WARP_ELEMS = T_ELEMS + C_ELEMS;
     static constexpr size_t WARP_BYTES = sizeof(real) * WARP_ELEMS;
     // element index of cell (y,x,z) with y in [-1,T3Y], x in [-1,T3X], z in [-1,TZ]
-    static __device__ __forceinline__ int at(int y, int x, int z) { return (y + 1) * PS + (x + 1) * PZ + z + 1; }
+    static __device__ __forceinline__ int at(int y, int x, int z) { return (y + 1) * PS + (x + 1) * PZ + z + 2; }
 };
 
 template <typename real>
@@ -143,15 +145,20 @@ __global__ void __launch_bounds__(WARPS * 32) solve3d_kernel(Problem3D<real> P) 
     const long long sy_ = (long long)P.nx * P.nz, sx_ = P.nz;   // global strides
 
     unsigned long long n_visits = 0, n_steps = 0, n_evals = 0, n_pushes = 0, n_written = 0;
-    int item = -1;
+    long long c_wait = 0, c_load = 0, c_relax = 0, c_store = 0;
 
     for (;;) {
-        if (item < 0) {
+        const long long tc0 = clock64();
+        int item;
+        {
             int it = -1;
             if (lane == 0) it = q_pop_lane0(P.q);
             item = __shfl_sync(FULL, it, 0);
             if (item < 0) break;
         }
+        if (lane == 0) { atomicExch(&P.tile_state[item], ST_RUNNING); __threadfence(); }
+        __syncwarp();
+        const long long tc1 = clock64();
         const int q = item / tiles_per_q;
         int t = item - q * tiles_per_q;
         const int tz = t % P.ntz; t /= P.ntz;
@@ -160,48 +167,77 @@ __global__ void __launch_bounds__(WARPS * 32) solve3d_kernel(Problem3D<real> P) 
         const real *cq = P.cost + (long long)q * P.cost_qstride;
         real *Tq = P.T + (long long)q * P.T_qstride;
 
-        if (lane == 0) { atomicExch(&P.tile_state[item], ST_RUNNING); __threadfence(); }
-        __syncwarp();
-
-        // ---- stage T: every (y,x) column of the haloed tile except the 4 corner columns,
-        //      z = z0 .. z0+TZ-1 across lanes (coalesced) -----------------------------
-        for (int c = 0; c < (T3Y + 2) * (T3X + 2); ++c) {
-            const int yy = c / (T3X + 2) - 1, xx = c % (T3X + 2) - 1;
-            const bool ycorner = (yy < 0 || yy >= T3Y), xcorner = (xx < 0 || xx >= T3X);
-            if (ycorner && xcorner) continue;
-            for (int zz = lane; zz < TZ; zz += 32) {
-                const int y = y0 + yy, x = x0 + xx, z = z0 + zz;
-                real v = INF;
-                if (y >= 0 && y < P.ny && x >= 0 && x < P.nx && z < P.nz) v = ld_T(&Tq[y * sy_ + x * sx_ + z]);
-                sT[TL::at(yy, xx, zz)] = v;
-            }
-        }
-        {   // z halos of my own column
-            const int y = y0 + ly, x = x0 + lx;
-            real lo = INF, hi = INF;
-            if (y < P.ny && x < P.nx) {
-                if (z0 > 0) lo = ld_T(&Tq[y * sy_ + x * sx_ + z0 - 1]);
-                if (z0 + TZ < P.nz) hi = ld_T(&Tq[y * sy_ + x * sx_ + z0 + TZ]);
-            }
-            sT[TL::at(ly, lx, -1)] = lo;
-            sT[TL::at(ly, lx, TZ)] = hi;
-        }
+        // ---- stage T (56 z-columns incl. lateral halos) and cost (32 columns) ------------------
         unsigned cmask = 0;
-        for (int c = 0; c < 32; ++c) {
-            const int yy = c >> 3, xx = c & 7;
-            unsigned b = 0;
-            for (int zz = lane; zz < TZ; zz += 32) {      // executes once (TZ <= 32)
-                const int y = y0 + yy, x = x0 + xx, z = z0 + zz;
-                real cv = INF;
-                if (y < P.ny && x < P.nx && z < P.nz) cv = __ldg(&cq[y * sy_ + x * sx_ + z]);
-                sC[c * PZ + zz] = cv;
+        {
+            const int y = y0 + ly, x = x0 + lx;       // z halos of my own column
+            real zlo = INF, zhi = INF;
+            if (y < P.ny && x < P.nx) {
+                if (z0 > 0) zlo = ld_T(&Tq[y * sy_ + x * sx_ + z0 - 1]);
+                if (z0 + TZ < P.nz) zhi = ld_T(&Tq[y * sy_ + x * sx_ + z0 + TZ]);
             }
-            {
-                const int zz = lane;
-                const real cv = (zz < TZ) ? sC[c * PZ + zz] : INF;
-                b = __ballot_sync(FULL, zz < TZ && cv < INF);
+            constexpr int NCOL = (T3Y + 2) * (T3X + 2);
+            constexpr int EPC = 16 / (int)sizeof(real);
+            constexpr int CPC = TZ / EPC;                              // 16-byte chunks per column
+            const bool fast = sizeof(real) == 8 && y0 >= 1 && y0 + T3Y < P.ny && x0 >= 1 && x0 + T3X < P.nx &&
+                              z0 + TZ <= P.nz && (P.nz % EPC) == 0 && ((size_t)Tq % 16) == 0 && ((size_t)cq % 16) == 0;
+            if (fast) {
+                // every 16-byte chunk of every column in flight at once (cp.async.cg: L2 only)
+#pragma unroll 4
+                for (int c = lane; c < NCOL * CPC; c += 32) {
+                    const int col = c / CPC, zz = (c % CPC) * EPC;
+                    const int yy = col / (T3X + 2) - 1, xx = col % (T3X + 2) - 1;
+                    const bool corner = (yy < 0 || yy >= T3Y) && (xx < 0 || xx >= T3X);
+                    if (!corner) cp_async16_cg(&sT[TL::at(yy, xx, zz)], &Tq[(y0 + yy) * sy_ + (x0 + xx) * sx_ + z0 + zz]);
+                }
+#pragma unroll 4
+                for (int c = lane; c < 32 * CPC; c += 32) {
+                    const int col = c / CPC, zz = (c % CPC) * EPC;
+                    cp_async16_cg(&sC[col * PZ + zz], &cq[(y0 + (col >> 3)) * sy_ + (x0 + (col & 7)) * sx_ + z0 + zz]);
+                }
+                cp_async_wait_all();
+                __syncwarp();
+            } else {
+                constexpr int BT = 8;
+                for (int b0 = 0; b0 < NCOL; b0 += BT) {
+                    real v[BT];
+#pragma unroll
+                    for (int u = 0; u < BT; ++u) {
+                        const int col = b0 + u;
+                        const int yy = col / (T3X + 2) - 1, xx = col % (T3X + 2) - 1;
+                        const int gy = y0 + yy, gx = x0 + xx, gz = z0 + lane;
+                        v[u] = INF;
+                        if (col < NCOL && lane < TZ && gy >= 0 && gy < P.ny && gx >= 0 && gx < P.nx && gz < P.nz)
+                            v[u] = ld_T(&Tq[gy * sy_ + gx * sx_ + gz]);
+                    }
+#pragma unroll
+                    for (int u = 0; u < BT; ++u) {
+                        const int col = b0 + u;
+                        const int yy = col / (T3X + 2) - 1, xx = col % (T3X + 2) - 1;
+                        const bool corner = (yy < 0 || yy >= T3Y) && (xx < 0 || xx >= T3X);
+                        if (col < NCOL && lane < TZ && !corner) sT[TL::at(yy, xx, lane)] = v[u];
+                    }
+                }
+                for (int b0 = 0; b0 < 32; b0 += BT) {
+                    real v[BT];
+#pragma unroll
+                    for (int u = 0; u < BT; ++u) {
+                        const int col = b0 + u;
+                        const int gy = y0 + (col >> 3), gx = x0 + (col & 7), gz = z0 + lane;
+                        v[u] = INF;
+                        if (lane < TZ && gy < P.ny && gx < P.nx && gz < P.nz) v[u] = __ldg(&cq[gy * sy_ + gx * sx_ + gz]);
+                    }
+#pragma unroll
+                    for (int u = 0; u < BT; ++u) if (lane < TZ) sC[(b0 + u) * PZ + lane] = v[u];
+                }
+                __syncwarp();
             }
-            if (lane == c) cmask = b;
+            sT[TL::at(ly, lx, -1)] = zlo;
+            sT[TL::at(ly, lx, TZ)] = zhi;
+            for (int c = 0; c < 32; ++c) {           // finite-cost mask per column (lane == z for the vote)
+                const unsigned b = __ballot_sync(FULL, lane < TZ && sC[c * PZ + (lane < TZ ? lane : 0)] < INF);
+                if (lane == c) cmask = b;
+            }
         }
         __syncwarp();
 
@@ -238,110 +274,132 @@ __global__ void __launch_bounds__(WARPS * 32) solve3d_kernel(Problem3D<real> P) 
         }
         mask &= cmask;
 
-        // ---- relax to the fixed point ---------------------------------------
-        unsigned dirty = 0;
-        int last = 0, dir = 1, steps = 0;
-        bool fail = false;
+        // ---- relax to the fixed point (same lock-step scheme as 2D; see eikonal2d.cuh) --------
+        const long long tc2 = clock64();
+        unsigned dirty = 0, last = 0;
+        bool up = true;
+        int steps = 0;
         unsigned active;
         while ((active = __ballot_sync(FULL, mask != 0)) != 0) {
-            int k = -1;
-            real v = INF, cur = INF, zm = INF, zp = INF, xm = INF, xp = INF, ym = INF, yp = INF;
+            unsigned m_xm = 0, m_xp = 0, m_ym = 0, m_yp = 0;
             if (mask) {
                 const unsigned hi = mask & (~0u << last);
                 const unsigned lo = mask & ((2u << last) - 1u);
-                if (dir > 0) {
-                    if (hi) k = __ffs(hi) - 1; else { k = 31 - __clz(lo); dir = -1; }
-                } else {
-                    if (lo) k = 31 - __clz(lo); else { k = __ffs(hi) - 1; dir = 1; }
-                }
+                up = up ? (hi != 0) : (lo == 0);
+                const unsigned k = up ? (unsigned)(__ffs(hi) - 1) : (unsigned)(31 - __clz(lo));
                 last = k;
-                mask &= ~(1u << k);
-                const real *p = col + k;
-                zm = p[-1]; zp = p[1]; xm = p[-PZ]; xp = p[PZ]; ym = p[-PS]; yp = p[PS]; cur = p[0];
+                const unsigned bit = 1u << k;
+                mask &= ~bit;
+                real *p = col + k;
+                const real zm = p[-1], zp = p[1], xm = p[-PZ], xp = p[PZ], ym = p[-PS], yp = p[PS], cur = p[0];
                 // FastMarching3D.py:44-57: per-axis minimum, Tarray = [Tx, Ty, Tz]
-                v = solve3d_update<real>(xm < xp ? xm : xp, ym < yp ? ym : yp, zm < zp ? zm : zp, colC[k]);
+                const real v = solve3d_update<real>(xm < xp ? xm : xp, ym < yp ? ym : yp, zm < zp ? zm : zp, colC[k]);
+                if (v < cur) {
+                    *p = v;
+                    dirty |= bit;
+                    mask |= (zm > v ? bit >> 1 : 0u) | (zp > v ? bit << 1 : 0u);
+                    m_xm = xm > v ? bit : 0u;
+                    m_xp = xp > v ? bit : 0u;
+                    m_ym = ym > v ? bit : 0u;
+                    m_yp = yp > v ? bit : 0u;
+                }
             }
-            __syncwarp();
-            int m_xm = -1, m_xp = -1, m_ym = -1, m_yp = -1;
-            if (k >= 0 && v < cur) {
-                col[k] = v;
-                dirty |= 1u << k;
-                if (k > 0 && zm > v) mask |= 1u << (k - 1);
-                if (k < TZ - 1 && zp > v) mask |= 1u << (k + 1);
-                if (xm > v) m_xm = k;
-                if (xp > v) m_xp = k;
-                if (ym > v) m_ym = k;
-                if (yp > v) m_yp = k;
-            }
-            const int r_xp = __shfl_down_sync(FULL, m_xm, 1);   // my x+ neighbour improved and I am its x-
-            const int r_xm = __shfl_up_sync(FULL, m_xp, 1);
-            const int r_yp = __shfl_down_sync(FULL, m_ym, 8);
-            const int r_ym = __shfl_up_sync(FULL, m_yp, 8);
-            if (lx < T3X - 1 && r_xp >= 0) mask |= 1u << r_xp;
-            if (lx > 0 && r_xm >= 0) mask |= 1u << r_xm;
-            if (ly < T3Y - 1 && r_yp >= 0) mask |= 1u << r_yp;
-            if (ly > 0 && r_ym >= 0) mask |= 1u << r_ym;
-            mask &= cmask;
+            unsigned r_xp = __shfl_down_sync(FULL, m_xm, 1);   // my x+ neighbour improved and I am its x-
+            unsigned r_xm = __shfl_up_sync(FULL, m_xp, 1);
+            unsigned r_yp = __shfl_down_sync(FULL, m_ym, 8);
+            unsigned r_ym = __shfl_up_sync(FULL, m_yp, 8);
+            if (lx == T3X - 1) r_xp = 0;
+            if (lx == 0) r_xm = 0;
+            if (ly == T3Y - 1) r_yp = 0;
+            if (ly == 0) r_ym = 0;
+            mask = (mask | r_xp | r_xm | r_yp | r_ym) & cmask;
             __syncwarp();
             n_evals += __popc(active);
-            if (++steps > P.step_cap) { fail = true; break; }
+            if (++steps > P.step_cap) break;
         }
         n_steps += steps;
         ++n_visits;
-        if (fail) {
+        if (steps > P.step_cap) {
             if (lane == 0) atomicCAS(&P.q.ctl->abort, 0, DEV_STEPCAP);
             break;
         }
+        const long long tc3 = clock64();
 
-        // ---- write back + face tests (lane == z) --------------------------------
+        // ---- write back dirty columns + face tests (lane == z) --------------------------------
         bool f_xm = false, f_xp = false, f_ym = false, f_yp = false;
-        for (int c = 0; c < 32; ++c) {
-            const unsigned dj = __shfl_sync(FULL, dirty, c);
-            if (dj == 0) continue;
-            const int yy = c >> 3, xx = c & 7;
-            if (lane < TZ && ((dj >> lane) & 1u)) {
-                const real nv = sT[TL::at(yy, xx, lane)];
-                st_T(&Tq[(y0 + yy) * sy_ + (x0 + xx) * sx_ + z0 + lane], nv);
-                if (xx == 0 && nv < sT[TL::at(yy, -1, lane)]) f_xm = true;
-                if (xx == T3X - 1 && nv < sT[TL::at(yy, T3X, lane)]) f_xp = true;
-                if (yy == 0 && nv < sT[TL::at(-1, xx, lane)]) f_ym = true;
-                if (yy == T3Y - 1 && nv < sT[TL::at(T3Y, xx, lane)]) f_yp = true;
+        {
+            unsigned cols_dirty = __ballot_sync(FULL, dirty != 0);
+            while (cols_dirty) {
+                const int c = __ffs(cols_dirty) - 1;
+                cols_dirty &= cols_dirty - 1;
+                const unsigned dj = __shfl_sync(FULL, dirty, c);
+                const int yy = c >> 3, xx = c & 7;
+                if (lane < TZ && ((dj >> lane) & 1u)) {
+                    const real nv = sT[TL::at(yy, xx, lane)];
+                    st_T(&Tq[(y0 + yy) * sy_ + (x0 + xx) * sx_ + z0 + lane], nv);
+                    if (xx == 0 && nv < sT[TL::at(yy, -1, lane)]) f_xm = true;
+                    if (xx == T3X - 1 && nv < sT[TL::at(yy, T3X, lane)]) f_xp = true;
+                    if (yy == 0 && nv < sT[TL::at(-1, xx, lane)]) f_ym = true;
+                    if (yy == T3Y - 1 && nv < sT[TL::at(T3Y, xx, lane)]) f_yp = true;
+                }
+                n_written += __popc(dj);
             }
-            n_written += __popc(dj);
         }
         const bool f_zm = (dirty & 1u) && col[0] < col[-1];
         const bool f_zp = ((dirty >> (TZ - 1)) & 1u) && col[TZ - 1] < col[TZ];
-        const bool a_zm = __any_sync(FULL, f_zm) && tz > 0;
-        const bool a_zp = __any_sync(FULL, f_zp) && tz < P.ntz - 1;
-        const bool a_xm = __any_sync(FULL, f_xm) && tx > 0;
-        const bool a_xp = __any_sync(FULL, f_xp) && tx < P.ntx - 1;
-        const bool a_ym = __any_sync(FULL, f_ym) && ty > 0;
-        const bool a_yp = __any_sync(FULL, f_yp) && ty < P.nty - 1;
+        unsigned act = 0;                     // bit s: neighbour s = z-, z+, x-, x+, y-, y+
+        if (__any_sync(FULL, f_zm) && tz > 0) act |= 1u;
+        if (__any_sync(FULL, f_zp) && tz < P.ntz - 1) act |= 2u;
+        if (__any_sync(FULL, f_xm) && tx > 0) act |= 4u;
+        if (__any_sync(FULL, f_xp) && tx < P.ntx - 1) act |= 8u;
+        if (__any_sync(FULL, f_ym) && ty > 0) act |= 16u;
+        if (__any_sync(FULL, f_yp) && ty < P.nty - 1) act |= 32u;
+        const int nact = __popc(act);
+        if (lane == 0 && nact) atomicAdd(&P.q.ctl->pending, nact);
         __threadfence();
         __syncwarp();
-        int next = -1;
-        if (lane == 0) {
-            __threadfence();
-            const int nbr[6] = {item - 1, item + 1, item - P.ntz, item + P.ntz, item - P.ntx * P.ntz, item + P.ntx * P.ntz};
-            const bool act[6] = {a_zm, a_zp, a_xm, a_xp, a_ym, a_yp};
-#pragma unroll
-            for (int s = 0; s < 6; ++s) {
-                if (!act[s]) continue;
-                if (tile_activate(P.tile_state, P.q.ctl, nbr[s])) {
-                    if (next < 0) next = nbr[s];
-                    else { q_push(P.q, nbr[s]); ++n_pushes; }
+        bool pushed = false, newly = false, requeue = false;
+        {
+            const bool is_nbr = lane < 6 && ((act >> lane) & 1u);
+            const bool is_self = lane == 6;
+            const int off = lane == 0 ? -1 : lane == 1 ? 1 : lane == 2 ? -P.ntz : lane == 3 ? P.ntz
+                            : lane == 4 ? -P.ntx * P.ntz : P.ntx * P.ntz;
+            const int tgt = is_self ? item : item + off;
+            if (is_nbr || is_self) {
+                int *st = &P.tile_state[tgt];
+                int old = atomicCAS(st, is_self ? ST_RUNNING : ST_IDLE, is_self ? ST_IDLE : ST_QUEUED);
+                if (is_self) {
+                    if (old != ST_RUNNING) { atomicExch(st, ST_QUEUED); requeue = true; }
+                } else {
+                    for (;;) {
+                        if (old == ST_IDLE) { newly = true; break; }
+                        if (old == ST_QUEUED || old == ST_DIRTY) break;
+                        if (atomicCAS(st, ST_RUNNING, ST_DIRTY) == ST_RUNNING) break;
+                        old = atomicCAS(st, ST_IDLE, ST_QUEUED);
+                    }
                 }
+                if (newly || requeue) { q_push(P.q, tgt); pushed = true; }
             }
-            if (tile_finish(P.tile_state, P.q.ctl, item)) {
-                if (next < 0) next = item;
-                else { q_push(P.q, item); ++n_pushes; }
-            }
-            if (ld_volatile(&P.q.ctl->abort)) next = -2;
         }
-        item = __shfl_sync(FULL, next, 0);
-        if (item == -2) break;
+        const int n_new = __popc(__ballot_sync(FULL, newly));
+        const int n_req = __popc(__ballot_sync(FULL, requeue));
+        n_pushes += __popc(__ballot_sync(FULL, pushed));
+        int stop = 0;
+        if (lane == 0) {
+            const int drop = (nact - n_new) + (n_req ? 0 : 1);
+            if (drop) atomicSub(&P.q.ctl->pending, drop);
+            stop = ld_volatile(&P.q.ctl->abort);
+        }
+        stop = __shfl_sync(FULL, stop, 0);
+        const long long tc4 = clock64();
+        c_wait += tc1 - tc0; c_load += tc2 - tc1; c_relax += tc3 - tc2; c_store += tc4 - tc3;
+        if (stop) break;
     }
     if (lane == 0) {
+        atomicAdd(&P.q.ctl->cyc_wait, (unsigned long long)c_wait);
+        atomicAdd(&P.q.ctl->cyc_load, (unsigned long long)c_load);
+        atomicAdd(&P.q.ctl->cyc_relax, (unsigned long long)c_relax);
+        atomicAdd(&P.q.ctl->cyc_store, (unsigned long long)c_store);
         atomicAdd(&P.q.ctl->visits, n_visits);
         atomicAdd(&P.q.ctl->steps, n_steps);
         atomicAdd(&P.q.ctl->evals, n_evals);

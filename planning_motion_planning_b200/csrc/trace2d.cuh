@@ -33,6 +33,11 @@ struct TraceArgs2D {
     int *count, *status;
 };
 
+#ifndef FMB_HOST_EMU
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+#else
+inline void prefetch_l1(const void *) {}
+#endif
 __device__ __forceinline__ double dsq(double a) { return __dmul_rn(a, a); }
 __device__ __forceinline__ double dhyp2(double a, double b) { return __dsqrt_rn(__dadd_rn(dsq(a), dsq(b))); }
 __device__ __forceinline__ bool d_isinf(double v) { return fabs(v) == __longlong_as_double(0x7ff0000000000000LL); }
@@ -99,6 +104,11 @@ __global__ void __launch_bounds__(WARPS * 32) trace2d_kernel(TraceArgs2D<real> A
         }
         const int i = (int)fi, j = (int)fj;
         const double a = __dsub_rn(px, (double)i), b = __dsub_rn(py, (double)j);
+        // the idle lanes pull the rows the path is about to enter into L1 (one line each)
+        if (lane >= 8) {
+            const int pj = min(max(j - 20 + lane, 0), m - 1);
+            prefetch_l1(&T[(long long)pj * A.T_pitch + i]);
+        }
         double gx, gy;
         grad_node2d<real>(T, A.T_pitch, m, n, i + (lane & 1), j + ((lane >> 1) & 1), gx, gy);
         const double x00 = __shfl_sync(FULL, gx, 0), x01 = __shfl_sync(FULL, gx, 1);
@@ -147,7 +157,9 @@ __global__ void __launch_bounds__(WARPS * 32) trace2d_kernel(TraceArgs2D<real> A
         py = __dsub_rn(py, __dmul_rn(A.tau, ny));
         if (lane == 0) { out[2 * K] = px; out[2 * K + 1] = py; }
         ++K;
-        if (dhyp2(__dsub_rn(px, ex), __dsub_rn(py, ey)) < 1.5) break;
+        // stop within 1.5 cells of `end` (:231).  sqrt(s) < 1.5 <=> s < 2.25 exactly for a correctly
+        // rounded sqrt (1.5^2 is representable), which keeps the square root off the step chain.
+        if (__dadd_rn(dsq(__dsub_rn(px, ex)), dsq(__dsub_rn(py, ey))) < 2.25) break;
     }
     if (append_end) {
         if (lane == 0) { out[2 * K] = ex; out[2 * K + 1] = ey; }

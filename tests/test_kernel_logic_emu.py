@@ -69,7 +69,7 @@ def test_solve2d_fp32_variant():
     assert rel_err(T[0].astype(np.float64), ref) < TOL32
 
 
-@pytest.mark.parametrize("shape,goal,tz", [((9, 9, 9), [4, 4, 4], 32), ((20, 20, 20), [4, 4, 4], 32),
+@pytest.mark.parametrize("shape,goal,tz", [((9, 9, 9), [4, 4, 4], 32), ((20, 20, 20), [4, 4, 4], 32), ((13, 26, 64), [20, 3, 50], 32),
                                            ((13, 21, 40), [10, 5, 33], 16), ((10, 12, 28), [8, 7, 6], 32)])
 def test_solve3d_random(shape, goal, tz):
     c = rand_map(shape, 5)

@@ -19,7 +19,7 @@
 static int N, NT;
 static double *cost, *T;
 static double CYC_STEP = 620, CYC_OVH = 30000, CYC_POP = 1500;
-static int VARIANT = 0; static double STEP2_FACTOR = 1.25;
+static int VARIANT = 0; static double STEP2_FACTOR = 1.25; static int SLICE = 1 << 30;
 
 static inline double eik(double a, double b, double c) {
     double m = a < b ? a : b, d = a - b;
@@ -53,11 +53,11 @@ static void fmm(double *F, int sx, int sy) {
 }
 
 enum { IDLE, QUEUED, RUNNING, DIRTY };
-static int *state; static double *prio;
+static int *state; static double *prio; static unsigned *saved_mask;
 static long total_evals, total_visits, total_steps, armed_sum, armed_n, hist[5], lanes_active_sum;
 
 /* in-tile cell FIM (same as visit2 of tile_model.c); works on a private buffer */
-typedef struct { double buf[(TS + 2) * (TS + 2)]; unsigned dirty[TS]; int steps; } visit_t;
+typedef struct { double buf[(TS + 2) * (TS + 2)]; unsigned dirty[TS]; int steps; int unfinished; unsigned left[TS]; } visit_t;
 static void run_visit(int t, visit_t *V, int sx, int sy) {
     int tx = t % NT, ty = t / NT, P = TS + 2;
     static double cb[TS * TS], nb[(TS + 2) * (TS + 2)];
@@ -89,6 +89,7 @@ static void run_visit(int t, visit_t *V, int sx, int sy) {
 #define CI(l, k) (transposed ? (l) : (k))
     for (int l = 0; l < TS; ++l) { mask[l] = 0; V->dirty[l] = 0; lastA[l] = 0; lastB[l] = TS - 1; dirn[l] = 1; }
     for (int j = 0; j < TS; ++j) for (int i = 0; i < TS; ++i) if (arm[j] >> i & 1) { if (transposed) mask[i] |= 1u << j; else mask[j] |= 1u << i; }
+    for (int l = 0; l < TS; ++l) { mask[l] |= saved_mask[t * TS + l]; saved_mask[t * TS + l] = 0; }   /* armed cells left by a time-sliced visit */
     int steps = 0; double cyc = 0;
     for (;;) {
         int any = 0; for (int l = 0; l < TS; ++l) if (mask[l]) any = 1;
@@ -132,7 +133,10 @@ static void run_visit(int t, visit_t *V, int sx, int sy) {
         memcpy(buf, nb, sizeof(nb));
         for (int l = 0; l < TS; ++l) mask[l] |= addm[l];
         cyc += two ? STEP2_FACTOR : 1.0;
+        if (steps >= SLICE) break;          /* time slice: publish what we have, go again later */
     }
+    V->unfinished = 0; for (int l = 0; l < TS; ++l) if (mask[l]) V->unfinished = 1;
+    for (int l = 0; l < TS; ++l) V->left[l] = mask[l];
     V->steps = (int)(cyc + 0.5); total_steps += steps; total_visits++;
 }
 
@@ -167,7 +171,7 @@ static void activate(int t, double p) {
 int main(int argc, char **argv) {
     N = argc > 1 ? atoi(argv[1]) : 1024; int W = argc > 2 ? atoi(argv[2]) : 1776; policy = argc > 3 ? atoi(argv[3]) : 0;
     double dtiles = argc > 4 ? atof(argv[4]) : 1.0; WINDOW = argc > 5 ? atoi(argv[5]) : 2;
-    if (getenv("OVH")) CYC_OVH = atof(getenv("OVH")); if (getenv("STEP")) CYC_STEP = atof(getenv("STEP"));
+    if (getenv("SLICE")) SLICE = atoi(getenv("SLICE")); if (getenv("OVH")) CYC_OVH = atof(getenv("OVH")); if (getenv("STEP")) CYC_STEP = atof(getenv("STEP"));
     if (getenv("VARIANT")) VARIANT = atoi(getenv("VARIANT")); if (getenv("STEP2")) STEP2_FACTOR = atof(getenv("STEP2"));
     NT = (N + TS - 1) / TS;
     cost = malloc(sizeof(double) * N * N); T = malloc(sizeof(double) * N * N);
@@ -177,7 +181,7 @@ int main(int argc, char **argv) {
     DELTA = dtiles * TS * cmin;
     int sx = N / 4, sy = N / 4;
     while (isinf(cost[sy * N + sx]) || cost[sy * N + sx] > 2) { sx++; }
-    state = calloc(NT * NT, sizeof(int)); prio = malloc(sizeof(double) * NT * NT);
+    state = calloc(NT * NT, sizeof(int)); prio = malloc(sizeof(double) * NT * NT); saved_mask = calloc((size_t)NT * NT * TS, sizeof(unsigned));
     ring = malloc(sizeof(int) * NT * NT * 4); ph = malloc(sizeof(he) * NT * NT * 8);
     for (int i = 0; i < N * N; ++i) T[i] = INFINITY;
     T[sy * N + sx] = 0;
@@ -213,12 +217,13 @@ int main(int argc, char **argv) {
             if (j == 0 && v < buf[i + 1]) { act[2] = 1; ap[2] = fmin(ap[2], v); }
             if (j == TS - 1 && v < buf[(TS + 1) * P + i + 1]) { act[3] = 1; ap[3] = fmin(ap[3], v); }
         }
+        for (int l = 0; l < TS; ++l) saved_mask[t * TS + l] |= e.V->left[l];
         freev[nfree++] = (int)(e.V - pool);
         if (act[0] && tx > 0) activate(t - 1, ap[0]);
         if (act[1] && tx < NT - 1) activate(t + 1, ap[1]);
         if (act[2] && ty > 0) activate(t - NT, ap[2]);
         if (act[3] && ty < NT - 1) activate(t + NT, ap[3]);
-        if (state[t] == DIRTY) { state[t] = QUEUED; q_push(t); } else state[t] = IDLE;
+        if (state[t] == DIRTY || e.V->unfinished) { if (state[t] != DIRTY) prio[t] = e.p; state[t] = QUEUED; q_push(t); } else state[t] = IDLE;
     }
     double *F = malloc(sizeof(double) * N * N); fmm(F, sx, sy);
     double maxrel = 0; long nfin = 0, infmis = 0;
