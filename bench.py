@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--size", type=int, default=4096, help="map side (default: the metric's 4096)")
     ap.add_argument("--map", default="mars", choices=["mars", "random"])
     ap.add_argument("--no-batch", action="store_true", help="skip the batched-queries section")
-    ap.add_argument("--batch-queries", type=int, default=1024, help="512^2 queries per GPU in the batched section")
+    ap.add_argument("--batch-queries", type=int, default=4096, help="512^2 queries per GPU in the batched section")
     ap.add_argument("--no-3d", action="store_true", help="skip the 3D (arm-workspace volume) section")
     ap.add_argument("--size3d", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -38,7 +38,7 @@ struct Problem2D {
 template <typename real>
 __device__ __forceinline__ real eikonal_update(real a, real b, real c) {
     using N = num<real>;
-    real m = fmin(a, b);
+    real m = a < b ? a : b;          // inputs are never NaN here; cheaper than fmin()
     real d = N::sub(a, b);
     // one-sided when the other side is too far (or +inf): covers the reference's
     // isinf() branches and `cost < |Thor - Tver|`; (inf - inf) = NaN lands here too
@@ -156,11 +156,20 @@ __global__ void __launch_bounds__(WARPS * 32) solve2d_kernel(Problem2D<real> P) 
             while (claimed < 0) {
                 unsigned long long bp = ~0ULL;
                 int bt = -1;
-                for (int t = lane; t < tiles_per_q; t += 32) {
-                    if (ld_volatile(&P.tile_state[base + t]) == ST_QUEUED) {
-                        const unsigned long long pr = *reinterpret_cast<const volatile unsigned long long *>(&P.tile_prio[base + t]);
-                        if (pr < bp) { bp = pr; bt = t; }
+                // four tiles per lane per batch, all eight loads in flight before any is used
+                for (int tb = 0; tb < tiles_per_q; tb += 128) {
+                    int stv[4];
+                    unsigned long long prv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int t = tb + u * 32 + lane;
+                        const bool in = t < tiles_per_q;
+                        stv[u] = in ? ld_volatile(&P.tile_state[base + t]) : ST_IDLE;
+                        prv[u] = in ? *reinterpret_cast<const volatile unsigned long long *>(&P.tile_prio[base + t]) : ~0ULL;
                     }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (stv[u] == ST_QUEUED && prv[u] < bp) { bp = prv[u]; bt = tb + u * 32 + lane; }
                 }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {

@@ -149,7 +149,7 @@ int solve2d(const real *d_cost, int64_t cost_pitch, int64_t cost_qstride, real *
     // best-first per query pays off when many queries share the GPU and a query's tile table is
     // small enough to scan per claim; one large map is faster in plain FIFO order
     const long long tiles_per_q = ntiles / nq;
-    P.best_first = env_int("FMB_BEST_FIRST", (nq >= 8 && tiles_per_q <= 4096) ? 1 : 0);
+    P.best_first = env_int("FMB_BEST_FIRST", (nq >= 8 && tiles_per_q <= 1024) ? 1 : 0);     // claim = scan of the query's tile table
     cudaStream_t st = (cudaStream_t)stream;
     if (P.best_first) {
         if (tw == 16) return launch_solve2d<real, 16, true>(P, L, st);

@@ -94,6 +94,8 @@ __global__ void __launch_bounds__(WARPS * 32) trace2d_kernel(TraceArgs2D<real> A
     bool append_end = true;
     if (lane == 0) { out[0] = px; out[1] = py; }
     K = 1;
+    int ci = -1, cj = -1;                                   // cell whose node gradients are cached
+    double x00 = 0, x01 = 0, x10 = 0, x11 = 0, y00 = 0, y01 = 0, y10 = 0, y11 = 0;
 
     for (int step = 0; step < A.max_steps; ++step) {
         if (isnan(px) || isnan(py)) { status = TR_VALUEERROR; append_end = false; break; }   // int(nan) at :250
@@ -104,17 +106,22 @@ __global__ void __launch_bounds__(WARPS * 32) trace2d_kernel(TraceArgs2D<real> A
         }
         const int i = (int)fi, j = (int)fj;
         const double a = __dsub_rn(px, (double)i), b = __dsub_rn(py, (double)j);
-        // the idle lanes pull the rows the path is about to enter into L1 (one line each)
-        if (lane >= 8) {
-            const int pj = min(max(j - 20 + lane, 0), m - 1);
-            prefetch_l1(&T[(long long)pj * A.T_pitch + i]);
+        // The four node gradients are a pure function of T and of the cell (i, j); the path moves
+        // at most tau per step, so they are recomputed only when it enters another cell
+        // (same values as the reference's per-step recomputation, shorter dependent chain).
+        if (i != ci || j != cj) {
+            ci = i; cj = j;
+            if (lane >= 8) {      // idle lanes pull the rows the path is about to enter into L1
+                const int pj = min(max(j - 20 + lane, 0), m - 1);
+                prefetch_l1(&T[(long long)pj * A.T_pitch + i]);
+            }
+            double gx, gy;
+            grad_node2d<real>(T, A.T_pitch, m, n, i + (lane & 1), j + ((lane >> 1) & 1), gx, gy);
+            x00 = __shfl_sync(FULL, gx, 0); x01 = __shfl_sync(FULL, gx, 1);
+            x10 = __shfl_sync(FULL, gx, 2); x11 = __shfl_sync(FULL, gx, 3);
+            y00 = __shfl_sync(FULL, gy, 0); y01 = __shfl_sync(FULL, gy, 1);
+            y10 = __shfl_sync(FULL, gy, 2); y11 = __shfl_sync(FULL, gy, 3);
         }
-        double gx, gy;
-        grad_node2d<real>(T, A.T_pitch, m, n, i + (lane & 1), j + ((lane >> 1) & 1), gx, gy);
-        const double x00 = __shfl_sync(FULL, gx, 0), x01 = __shfl_sync(FULL, gx, 1);
-        const double x10 = __shfl_sync(FULL, gx, 2), x11 = __shfl_sync(FULL, gx, 3);
-        const double y00 = __shfl_sync(FULL, gy, 0), y01 = __shfl_sync(FULL, gy, 1);
-        const double y10 = __shfl_sync(FULL, gy, 2), y11 = __shfl_sync(FULL, gy, 3);
         const double dx = bilinear_ref(x00, x01, x10, x11, a, b);
         const double dy = bilinear_ref(y00, y01, y10, y11, a, b);
 

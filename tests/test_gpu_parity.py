@@ -135,6 +135,81 @@ def test_solve2d_is_exact_fixed_point_4096(eng):
     assert rel_err(T.cpu().numpy(), ref) < TOL64
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_solve2d_differential_random_obstacles(eng, seed):
+    """Seeded differential test: random size, random walls/blocks (inf), mixed cost scales."""
+    from oracle import oracle as O
+    rng = np.random.default_rng(1000 + seed)
+    rows, cols = int(rng.integers(40, 300)), int(rng.integers(40, 300))
+    c = rand_map((rows, cols), seed)
+    c[np.isfinite(c)] *= rng.choice([1.0, 10.0, 300.0], size=int(np.isfinite(c).sum()), p=[.8, .15, .05])
+    for _ in range(int(rng.integers(3, 12))):
+        y, x = int(rng.integers(1, rows - 1)), int(rng.integers(1, cols - 1))
+        if rng.random() < .5:
+            c[y, x:min(cols - 1, x + int(rng.integers(5, 80)))] = np.inf
+        else:
+            c[y:min(rows - 1, y + int(rng.integers(5, 80))), x] = np.inf
+    free = np.argwhere(np.isfinite(c))
+    gy, gx = free[int(rng.integers(0, len(free)))]
+    T = _gpu2d(eng, c, [[int(gx), int(gy)]])[0]
+    assert rel_err(T, O.computeTmap(c, [int(gx), int(gy)])) < TOL64
+
+
+def test_best_first_and_fifo_agree(eng, monkeypatch):
+    """The two work orders of the persistent kernel reach the same fixed point."""
+    import torch
+    from oracle import oracle as O
+    c = rand_map((160, 200), 9)
+    goals = [[int(5 + 7 * i) % 190 + 2, int(3 + 11 * i) % 150 + 2] for i in range(16)]
+    outs = []
+    for bf in ("0", "1"):
+        monkeypatch.setenv("FMB_BEST_FIRST", bf)
+        outs.append(_gpu2d(eng, c, goals))
+    for q, g in enumerate(goals):
+        ref = O.computeTmap(c, g)
+        assert rel_err(outs[0][q], ref) < TOL64 and rel_err(outs[1][q], ref) < TOL64
+
+
+def test_batch_api_single_rank(eng):
+    from oracle import oracle as O
+    from planning_motion_planning_b200 import batch, synth
+    c = synth.mars_costmap(256, 5)
+    rng = np.random.default_rng(3)
+    ok = np.argwhere(np.isfinite(c) & (c <= 2.0))
+    goals = ok[rng.integers(0, len(ok), size=20)][:, ::-1].tolist()
+    starts = ok[rng.integers(0, len(ok), size=20)][:, ::-1].tolist()
+    lo, res = batch.solve_queries(c, goals, starts, chunk=8)
+    assert lo == 0 and len(res) == 20
+    for (p, st), g, s in zip(res, goals, starts):
+        po, so = O.getPathGDM(O.computeTmap(c, g), np.array(s, dtype=np.float64), g, 0.5, return_status=True)
+        assert st == so and p.shape == po.shape and (len(po) == 0 or np.abs(p - po).max() < TOLP)
+
+
+def test_solve2d_8192_fixed_point_property(eng):
+    """Config 5 size on one GPU (1 GiB of fields): no oracle run (tens of seconds on the host),
+    only the size-independent property that no free cell can be improved by one more update."""
+    import torch
+    from planning_motion_planning_b200 import synth
+    n = 8192
+    c = synth.random_costmap((n, n), 11)
+    cd = torch.from_numpy(c).cuda()
+    del c
+    T = eng.solve2d(cd, [[n // 3, n // 5]])[0]
+    inf = float("inf")
+    P = torch.nn.functional.pad(T, (1, 1, 1, 1), value=inf)
+    a = torch.minimum(P[1:-1, :-2], P[1:-1, 2:])
+    b = torch.minimum(P[:-2, 1:-1], P[2:, 1:-1])
+    del P
+    d = a - b
+    U = torch.where(~(d.abs() <= cd), torch.minimum(a, b) + cd, 0.5 * ((a + b) + torch.sqrt(2 * (cd * cd) - d * d)))
+    del a, b, d
+    free = torch.isfinite(cd)
+    free[n // 5, n // 3] = False
+    assert bool(torch.isfinite(T[free]).all())
+    gap = (U - T)[free]
+    assert float(gap.min()) >= 0.0 and float((gap / T[free].clamp_min(1.0)).max()) < 1e-14
+
+
 # ------------------------------------------------------------------ 3D solve
 @pytest.mark.parametrize("tz", ["32", "16"])
 @pytest.mark.parametrize("shape,goal", [((9, 9, 9), [4, 4, 4]), ((24, 24, 24), [5, 6, 7]), ((13, 21, 40), [10, 5, 33]),
