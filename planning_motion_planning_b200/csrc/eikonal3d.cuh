@@ -43,7 +43,7 @@ __device__ __forceinline__ real solve3d_update(real t0, real t1, real t2, real C
             real S = N::add(t0, N::add(t1, t2));
             real Q = N::add(N::mul(t0, t0), N::add(N::mul(t1, t1), N::mul(t2, t2)));
             real disc = N::sub(N::add(N::mul((real)3, C2), N::mul(S, S)), N::mul((real)3, Q));
-            return N::div(N::add(S, N::sqrt(disc)), (real)3);
+            return N::div3(N::add(S, N::sqrt(disc)));
         }
         // Tarray.remove(Tmax): keep the other two in order
         if (im == 0) { t0 = t1; t1 = t2; } else if (im == 1) { t1 = t2; }

@@ -143,3 +143,20 @@ def test_truncate_rebuilds_reference_partial_fields():
     r3 = emu._ranks(F3)
     out, ovf = emu.truncate(F3, c3, r3[(17 * 24 + 18) * 24 + 16], r3)
     assert ovf == 0 and np.array_equal(out, T3)
+
+
+def test_div3_is_correctly_rounded():
+    """num<double>::div3 (FMA-corrected multiply used by the 3D update) == IEEE x / 3."""
+    import ctypes as C
+    L = emu.lib()
+    L.emu_div3.argtypes = [emu.dp, emu.dp, C.c_longlong]
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.random(2_000_000) * 10.0 ** rng.integers(-8, 9, 2_000_000),
+                        -rng.random(100_000) * 1e4, np.arange(0, 4097, dtype=np.float64),
+                        np.array([0.0, -0.0, np.inf, -np.inf, 1e308, 1e-308, 5e-324, 3.0, 1.0, 2.0 / 3.0])])
+    # neighbours of multiples of 3 (the hard rounding cases)
+    m = np.arange(1, 50_000, dtype=np.float64) * 3.0
+    x = np.concatenate([x, np.nextafter(m, np.inf), np.nextafter(m, 0.0)])
+    out = np.empty_like(x)
+    L.emu_div3(np.ascontiguousarray(x).ctypes.data_as(emu.dp), out.ctypes.data_as(emu.dp), x.size)
+    assert np.array_equal(out, x / 3.0)

@@ -203,6 +203,7 @@ inline double __dsub_rn(double a, double b) { return a - b; }
 inline double __dmul_rn(double a, double b) { return a * b; }
 inline double __ddiv_rn(double a, double b) { return a / b; }
 inline double __dsqrt_rn(double a) { return sqrt(a); }
+inline double __fma_rn(double a, double b, double c) { return fma(a, b, c); }
 inline float __fadd_rn(float a, float b) { return a + b; }
 inline float __fsub_rn(float a, float b) { return a - b; }
 inline float __fmul_rn(float a, float b) { return a * b; }

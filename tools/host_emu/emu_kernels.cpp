@@ -115,4 +115,6 @@ int emu_truncate3d_f64(const double *F, const double *cost, const int *rank, int
     return overflow;
 }
 
+void emu_div3(const double *x, double *out, long long n) { for (long long i = 0; i < n; ++i) out[i] = fmb::num<double>::div3(x[i]); }
+
 }  // extern "C"
