@@ -326,34 +326,66 @@ def own_arm(args):
                 "note": "single-source solve is dependency-latency bound (DESIGN.md 5); see batch.roofline_frac_solve_kernel for the throughput regime"}
 
     # ---- end to end through the public API with host buffers
+    # Every step copies its costmap from pinned host memory, solves, traces, and copies the field,
+    # the path and its length back.  Copies run on two side streams so that step k's field
+    # download overlaps its own trace and step k+1's upload overlaps step k's solve (two device
+    # input buffers); all of it is inside the timed region, which ends with a full synchronize.
     T_h = torch.empty((1, n, n), dtype=torch.float64).pin_memory()
     cap = int(round(15000 / tau)) + 2
     path_h = torch.empty((1, cap, 2), dtype=torch.float64).pin_memory()
     cnt_h = torch.empty(1, dtype=torch.int32).pin_memory()
+    s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream()
+    cbuf = [torch.empty_like(cost_d), torch.empty_like(cost_d)]
+    ev_in = [torch.cuda.Event(), torch.cuda.Event()]
+    ev_free = [torch.cuda.Event(), torch.cuda.Event()]
+    ev_solved, ev_T_out = torch.cuda.Event(), torch.cuda.Event()
 
-    def step_e2e():
-        cd = cost_h.to(dev, non_blocking=True)
-        engine.solve2d(cd, seeds_d, out=T_d, nq=1, sync=False)
-        out, cnt, st = engine.trace2d(T_d, init, end, tau)
-        T_h.copy_(T_d, non_blocking=True)
-        path_h.copy_(out, non_blocking=True)
-        cnt_h.copy_(cnt, non_blocking=True)
+    def upload(k):
+        b = k & 1
+        with torch.cuda.stream(s_in):
+            s_in.wait_event(ev_free[b])                 # the solve that last read this buffer is done
+            cbuf[b].copy_(cost_h, non_blocking=True)
+            ev_in[b].record(s_in)
+
+    def run_e2e(K_):
+        for b in (0, 1):
+            ev_free[b].record(main)
+        ev_T_out.record(s_out)
+        upload(0)
+        for k in range(K_):
+            b = k & 1
+            main.wait_event(ev_in[b])
+            main.wait_event(ev_T_out)                   # previous field download finished reading T_d
+            engine.solve2d(cbuf[b], seeds_d, out=T_d, nq=1, sync=False)
+            ev_free[b].record(main)
+            ev_solved.record(main)
+            if k + 1 < K_:
+                upload(k + 1)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_solved)
+                T_h.copy_(T_d, non_blocking=True)
+                ev_T_out.record(s_out)
+            out, cnt, st = engine.trace2d(T_d, init, end, tau)
+            path_h.copy_(out, non_blocking=True)
+            cnt_h.copy_(cnt, non_blocking=True)
         torch.cuda.synchronize()
 
-    for _ in range(2):
-        step_e2e()
+    run_e2e(2)
+    engine.finish(dev)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(K):
-        step_e2e()
+    run_e2e(K)
     barrier()
     e2e_s = time.perf_counter() - t0
+    engine.finish(dev)
     if world > 1:
         tt = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt[0])
     e2e = {"value": world * cells * K / e2e_s, "unit": UNIT, "ms_per_step": 1e3 * e2e_s / K,
-           "h2d_bytes_per_step": int(cost_h.numel() * 8), "d2h_bytes_per_step": int(T_h.numel() * 8 + path_h.numel() * 8 + 4)}
+           "h2d_bytes_per_step": int(cost_h.numel() * 8), "d2h_bytes_per_step": int(T_h.numel() * 8 + path_h.numel() * 8 + 4),
+           "pipelining": "uploads/downloads on side streams overlap the next solve / the trace"}
 
     # ---- batched independent queries (config 4 style): Q goal queries on one 512^2 map per GPU
     batch = None

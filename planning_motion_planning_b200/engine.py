@@ -100,8 +100,6 @@ def solve2d(cost: torch.Tensor, seeds, out: Optional[torch.Tensor] = None, nq: O
         raise ValueError("cost must be (rows, cols) or (nq, rows, cols)")
     if cost.stride(-1) != 1:
         cost = cost.contiguous()
-    if not shared and cost.stride(0) % 1 != 0:
-        cost = cost.contiguous()
     dev = cost.device
     s = _as_seeds(seeds, nq, 2, dev)
     if out is None:
