@@ -94,6 +94,17 @@ int fmb_solve2d_f32(const float *d_cost, int64_t cost_pitch, int64_t cost_qstrid
                     int rows, int cols, int nq, const int32_t *d_seeds,
                     void *d_ws, size_t ws_bytes, void *stream);
 
+/* Resume a single 2D solve from the CURRENT contents of d_T (no re-initialisation): used by the
+ * row-slab domain decomposition of very large maps, where halo rows received from the neighbour
+ * slabs are written into d_T between calls (they carry cost = +inf locally, so they are inputs
+ * only).  d_seed: int32[2] [x,y] of a source inside this array, or an out-of-range node for none.
+ * activate: bit 0 = queue the first tile row, bit 1 = the last tile row, bit 2 = every tile.
+ * halo_rows: bit 0 / bit 1 = array row 0 / rows-1 is such a halo row (its tiles re-arm all cells).
+ * The reference has no counterpart (single process, FastMarching.py:92-112). */
+int fmb_resolve2d_f64(const double *d_cost, int64_t cost_pitch, double *d_T, int64_t T_pitch,
+                      int rows, int cols, const int32_t *d_seed, int activate, int halo_rows,
+                      void *d_ws, size_t ws_bytes, void *stream);
+
 /* ---- 3D Eikonal solve ------------------------------------------------------
  * volumes are dense [ny][nx][nz] arrays with z contiguous.
  * d_seeds int32 [nq][3] = [x,y,z].

@@ -46,6 +46,7 @@ SIGNATURES = {
     "fmb_workspace_bytes_2d": (_sz, [_i32, _i32, _i32]),
     "fmb_solve2d_f64": (C.c_int, [_vp, _i64, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
     "fmb_solve2d_f32": (C.c_int, [_vp, _i64, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
+    "fmb_resolve2d_f64": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _vp, _i32, _i32, _vp, _sz, _vp]),
     "fmb_workspace_bytes_3d": (_sz, [_i32, _i32, _i32, _i32]),
     "fmb_solve3d_f64": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
     "fmb_solve3d_f32": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),

@@ -29,6 +29,8 @@ struct Problem2D {
     int step_cap;            // in-tile iteration cap (DEV_STEPCAP beyond)
     unsigned long long *tile_prio;   // [nq*ntx*nty] ordered bits of the lowest activating value (best-first mode)
     int best_first;          // 1: ring carries query ids, workers claim the lowest-priority queued tile
+    int arm_rows;            // bit 0 / bit 1: the first / last tile row holds a halo row written from outside
+                             // (domain decomposition): every visit of those tiles re-arms all their cells
 };
 
 // FastMarching.py:17-29 getEikonal, written branch-for-branch on the values
@@ -109,6 +111,31 @@ __global__ void init_seed2d_kernel(Problem2D<real> P) {
             atomicAdd(&P.q.ctl->pushes, 1ULL);
         }
     }
+}
+
+// resume: keep T as it is (another solve, or halo rows received from a neighbour slab, already
+// live in it), reset the scheduler state and queue the tiles selected by `activate`
+// (bit 0: first tile row, bit 1: last tile row, bit 2: every tile) plus the seed's tiles.
+template <typename real>
+__global__ void init_resume2d_kernel(Problem2D<real> P, int ring_slots) {
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nth = (long long)gridDim.x * blockDim.x;
+    const long long ntiles = (long long)P.nq * P.ntx * P.nty;
+    for (long long i = tid; i < ntiles; i += nth) { P.tile_state[i] = ST_IDLE; P.tile_prio[i] = 0x7ff0000000000000ULL; }
+    for (long long i = tid; i < ring_slots; i += nth) P.q.ring[i] = -1;
+    if (tid == 0) { QueueCtl z = {}; *P.q.ctl = z; }
+}
+template <typename real>
+__global__ void activate_rows2d_kernel(Problem2D<real> P, int activate) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= P.ntx * P.nty) return;
+    const int ty = t / P.ntx;
+    // the last array row may sit alone in the last tile row: then the tile row above it (which sees
+    // that row through its shared-memory halo) is the one that has work
+    const bool last_alone = P.nty >= 2 && (P.rows - 1) % TILE_H == 0;
+    const bool on = ((activate & 1) && ty == 0) || (activate & 4) ||
+                    ((activate & 2) && (ty == P.nty - 1 || (last_alone && ty == P.nty - 2)));
+    if (on && tile_activate(P.tile_state, P.q.ctl, t)) { q_push(P.q, t); atomicAdd(&P.q.ctl->pushes, 1ULL); }
 }
 
 // ---------------------------------------------------------------------------
@@ -311,6 +338,7 @@ __global__ void __launch_bounds__(WARPS * 32) solve2d_kernel(Problem2D<real> P) 
                 if (lane == ly - 1 || lane == ly + 1) mask |= 1u << lx;
             }
         }
+        if (((P.arm_rows & 1) && ty == 0) || ((P.arm_rows & 2) && ty == P.nty - 1)) mask = cmask;
         mask &= cmask;
 
         // ---- relax to the fixed point ---------------------------------------

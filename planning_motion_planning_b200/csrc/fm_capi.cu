@@ -89,7 +89,7 @@ long long tiles2d(int rows, int cols, int tw) {
 }
 
 template <typename real, int TW, bool BEST>
-int launch_solve2d(fmb::Problem2D<real> P, const WsLayout &L, cudaStream_t st) {
+int launch_solve2d(fmb::Problem2D<real> P, const WsLayout &L, cudaStream_t st, int resume_activate = -1) {
     using TL = fmb::Tile2D<real, TW>;
     const size_t smem = TL::WARP_BYTES * WARPS;
     auto kern = fmb::solve2d_kernel<real, TW, WARPS, BEST>;
@@ -110,8 +110,14 @@ int launch_solve2d(fmb::Problem2D<real> P, const WsLayout &L, cudaStream_t st) {
     if (fill_blocks > (long long)sm_count() * 16) fill_blocks = (long long)sm_count() * 16;
     if (fill_blocks < 1) fill_blocks = 1;
     timing_begin(st);
-    fmb::init_fill2d_kernel<real><<<(unsigned)fill_blocks, 256, 0, st>>>(P, (int)L.ring_slots);
-    fmb::init_seed2d_kernel<real, TW><<<(P.nq + 127) / 128, 128, 0, st>>>(P);
+    if (resume_activate < 0) {
+        fmb::init_fill2d_kernel<real><<<(unsigned)fill_blocks, 256, 0, st>>>(P, (int)L.ring_slots);
+    } else {
+        fmb::init_resume2d_kernel<real><<<64, 256, 0, st>>>(P, (int)L.ring_slots);
+        if (resume_activate & 7)
+            fmb::activate_rows2d_kernel<real><<<(P.ntx * P.nty + 127) / 128, 128, 0, st>>>(P, resume_activate);
+    }
+    fmb::init_seed2d_kernel<real, TW><<<(P.nq + 127) / 128, 128, 0, st>>>(P);     // out-of-range seed = no seed
     timing_mid(st);
     kern<<<(unsigned)blocks, WARPS * 32, smem, st>>>(P);
     timing_end(st);
@@ -122,7 +128,7 @@ int launch_solve2d(fmb::Problem2D<real> P, const WsLayout &L, cudaStream_t st) {
 template <typename real>
 int solve2d(const real *d_cost, int64_t cost_pitch, int64_t cost_qstride, real *d_T, int64_t T_pitch,
             int64_t T_qstride, int rows, int cols, int nq, const int32_t *d_seeds, void *d_ws, size_t ws_bytes,
-            void *stream) {
+            void *stream, int resume_activate = -1, int arm_rows = 0) {
     if (!d_cost || !d_T || !d_seeds || !d_ws) return fail(FMB_E_INVALID, "null pointer argument%s");
     if (rows < 1 || cols < 1 || nq < 1) return fail(FMB_E_INVALID, "rows, cols and nq must be positive%s");
     if (cost_pitch < cols || T_pitch < cols) return fail(FMB_E_INVALID, "pitch smaller than cols%s");
@@ -150,13 +156,15 @@ int solve2d(const real *d_cost, int64_t cost_pitch, int64_t cost_qstride, real *
     // small enough to scan per claim; one large map is faster in plain FIFO order
     const long long tiles_per_q = ntiles / nq;
     P.best_first = env_int("FMB_BEST_FIRST", (nq >= 8 && tiles_per_q <= 1024) ? 1 : 0);     // claim = scan of the query's tile table
+    P.arm_rows = arm_rows;
+    if (resume_activate >= 0) P.best_first = 0;
     cudaStream_t st = (cudaStream_t)stream;
     if (P.best_first) {
         if (tw == 16) return launch_solve2d<real, 16, true>(P, L, st);
         return launch_solve2d<real, 32, true>(P, L, st);
     }
-    if (tw == 16) return launch_solve2d<real, 16, false>(P, L, st);
-    return launch_solve2d<real, 32, false>(P, L, st);
+    if (tw == 16) return launch_solve2d<real, 16, false>(P, L, st, resume_activate);
+    return launch_solve2d<real, 32, false>(P, L, st, resume_activate);
 }
 
 }  // namespace
@@ -183,6 +191,13 @@ int fmb_solve2d_f32(const float *d_cost, int64_t cost_pitch, int64_t cost_qstrid
                     size_t ws_bytes, void *stream) {
     return solve2d<float>(d_cost, cost_pitch, cost_qstride, d_T, T_pitch, T_qstride, rows, cols, nq, d_seeds, d_ws,
                           ws_bytes, stream);
+}
+
+int fmb_resolve2d_f64(const double *d_cost, int64_t cost_pitch, double *d_T, int64_t T_pitch, int rows, int cols,
+                      const int32_t *d_seed, int activate, int halo_rows, void *d_ws, size_t ws_bytes, void *stream) {
+    if (activate < 0 || activate > 7 || halo_rows < 0 || halo_rows > 3) return fail(FMB_E_INVALID, "bad activate / halo_rows%s");
+    return solve2d<double>(d_cost, cost_pitch, 0, d_T, T_pitch, 0, rows, cols, 1, d_seed, d_ws, ws_bytes, stream,
+                           activate, halo_rows);
 }
 
 int fmb_finish(void *d_ws, size_t ws_bytes, void *stream, fmb_stats *stats) {

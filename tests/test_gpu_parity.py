@@ -353,6 +353,40 @@ def test_dropin_early_exit_fields_match_reference_bitwise_pattern():
     assert p.shape == g3["kat4_path_trunc"].shape and np.abs(p - g3["kat4_path_trunc"]).max() < TOLP
 
 
+def test_domain_decomposition_local_slabs(eng):
+    """Row-slab decomposition with halo exchange (one process holding all slabs) == single solve."""
+    import torch
+    from planning_motion_planning_b200 import decomp, synth
+    c = synth.mars_costmap(1024, 2)
+    g = synth.free_cell_near(c, 700, 300)
+    cd = torch.from_numpy(c).cuda()
+    single = eng.solve2d(cd, [g])[0]
+    for nslabs in (2, 5):
+        T, rounds = decomp.solve2d_slabs_local(cd, g, nslabs)
+        assert rounds >= 2 and T.shape == single.shape
+        fin = torch.isfinite(single)
+        assert bool(torch.equal(torch.isfinite(T), fin))
+        assert float(((T - single).abs() / single.clamp_min(1e-300))[fin].max()) < 1e-12
+
+
+def test_device_side_failure_is_reported_not_hidden(eng, monkeypatch):
+    """A solve that cannot finish (in-tile iteration cap hit) raises; the next solve is unaffected."""
+    import torch
+    from oracle import oracle as O
+    from planning_motion_planning_b200 import _capi
+    c = rand_map((120, 120), 3)
+    cd = torch.from_numpy(c).cuda()
+    monkeypatch.setenv("FMB_STEP_CAP", "3")
+    with pytest.raises(_capi.FmbError) as ei:
+        eng.solve2d(cd, [[60, 60]])
+    assert ei.value.code == _capi.FMB_E_STEPCAP
+    monkeypatch.delenv("FMB_STEP_CAP")
+    T = eng.solve2d(cd, [[60, 60]])[0].cpu().numpy()
+    assert rel_err(T, O.computeTmap(c, [60, 60])) < TOL64
+    with pytest.raises(_capi.FmbError):           # bad arguments are rejected by the C ABI
+        _capi.check(_capi.lib().fmb_solve2d_f64(cd.data_ptr(), 10, 0, cd.data_ptr(), 120, 0, 120, 120, 1, None, None, 0, None))
+
+
 def test_dropin_errors():
     import FastMarching.FastMarching as FM
     c = rand_map((40, 40), 0)

@@ -33,6 +33,7 @@ int run2d(const real *cost, long long cost_qstride, real *T, int rows, int cols,
     std::vector<unsigned long long> prio(ntiles);
     P.tile_prio = prio.data();
     P.best_first = getenv("FMB_BEST_FIRST") ? atoi(getenv("FMB_BEST_FIRST")) : 0;
+    P.arm_rows = 0;
     emu::launch(2, 64, 0, [&] { fmb::init_fill2d_kernel<real>(P, (int)ring.size()); });
     emu::launch(1, 32 * ((nq + 31) / 32), 0, [&] { fmb::init_seed2d_kernel<real, TW>(P); });
     if (P.best_first) emu::launch(nblocks, WARPS * 32, fmb::Tile2D<real, TW>::WARP_BYTES * WARPS, [&] { fmb::solve2d_kernel<real, TW, WARPS, true>(P); });
@@ -116,5 +117,27 @@ int emu_truncate3d_f64(const double *F, const double *cost, const int *rank, int
 }
 
 void emu_div3(const double *x, double *out, long long n) { for (long long i = 0; i < n; ++i) out[i] = fmb::num<double>::div3(x[i]); }
+
+// resume a 2D solve from the current contents of T (domain decomposition tests)
+int emu_resolve2d_f64(const double *cost, double *T, int rows, int cols, const int *seed, int activate, int halo_rows,
+                      int nblocks) {
+    constexpr int TW = 32;
+    fmb::Problem2D<double> P;
+    P.cost = cost; P.cost_pitch = cols; P.cost_qstride = 0; P.T = T; P.T_pitch = cols; P.T_qstride = 0;
+    P.rows = rows; P.cols = cols; P.nq = 1;
+    P.ntx = (cols + TW - 1) / TW; P.nty = (rows + fmb::TILE_H - 1) / fmb::TILE_H;
+    P.seeds = seed;
+    const long long ntiles = (long long)P.ntx * P.nty;
+    std::vector<int> state(ntiles), ring(pow2_at_least(ntiles));
+    std::vector<unsigned long long> prio(ntiles);
+    fmb::QueueCtl ctl;
+    P.tile_state = state.data(); P.q.ctl = &ctl; P.q.ring = ring.data(); P.q.ring_mask = (unsigned)ring.size() - 1;
+    P.q.watchdog_cycles = 1LL << 40; P.step_cap = 1 << 20; P.tile_prio = prio.data(); P.best_first = 0; P.arm_rows = halo_rows;
+    emu::launch(2, 64, 0, [&] { fmb::init_resume2d_kernel<double>(P, (int)ring.size()); });
+    if (activate & 7) emu::launch((unsigned)((ntiles + 63) / 64), 64, 0, [&] { fmb::activate_rows2d_kernel<double>(P, activate); });
+    emu::launch(1, 32, 0, [&] { fmb::init_seed2d_kernel<double, TW>(P); });
+    emu::launch(nblocks, WARPS * 32, fmb::Tile2D<double, TW>::WARP_BYTES * WARPS, [&] { fmb::solve2d_kernel<double, TW, WARPS, false>(P); });
+    return ctl.abort ? ctl.abort : (ctl.pending != 0 ? -1 : 0);
+}
 
 }  // extern "C"
