@@ -19,7 +19,7 @@
 static int N, NT;
 static double *cost, *T;
 static double CYC_STEP = 620, CYC_OVH = 30000, CYC_POP = 1500;
-static int VARIANT = 0; static double STEP2_FACTOR = 1.25; static int SLICE = 1 << 30;
+static int VARIANT = 0; static double STEP2_FACTOR = 1.25; static int SLICE = 1 << 30; static int PUBSTEP = 0; static double CYC_PUB = 9000;
 
 static inline double eik(double a, double b, double c) {
     double m = a < b ? a : b, d = a - b;
@@ -57,7 +57,7 @@ static int *state; static double *prio; static unsigned *saved_mask;
 static long total_evals, total_visits, total_steps, armed_sum, armed_n, hist[5], lanes_active_sum;
 
 /* in-tile cell FIM (same as visit2 of tile_model.c); works on a private buffer */
-typedef struct { double buf[(TS + 2) * (TS + 2)]; unsigned dirty[TS]; int steps; int unfinished; unsigned left[TS]; } visit_t;
+typedef struct { double buf[(TS + 2) * (TS + 2)]; unsigned dirty[TS]; int steps; int unfinished; unsigned left[TS]; int has_mid; double midbuf[(TS + 2) * (TS + 2)]; unsigned middirty[TS]; } visit_t;
 static void run_visit(int t, visit_t *V, int sx, int sy) {
     int tx = t % NT, ty = t / NT, P = TS + 2;
     static double cb[TS * TS], nb[(TS + 2) * (TS + 2)];
@@ -87,6 +87,7 @@ static void run_visit(int t, visit_t *V, int sx, int sy) {
     /* line l, position k  ->  cell (j,i) = transposed ? (k,l) : (l,k) */
 #define CJ(l, k) (transposed ? (k) : (l))
 #define CI(l, k) (transposed ? (l) : (k))
+    V->has_mid = 0;
     for (int l = 0; l < TS; ++l) { mask[l] = 0; V->dirty[l] = 0; lastA[l] = 0; lastB[l] = TS - 1; dirn[l] = 1; }
     for (int j = 0; j < TS; ++j) for (int i = 0; i < TS; ++i) if (arm[j] >> i & 1) { if (transposed) mask[i] |= 1u << j; else mask[j] |= 1u << i; }
     for (int l = 0; l < TS; ++l) { mask[l] |= saved_mask[t * TS + l]; saved_mask[t * TS + l] = 0; }   /* armed cells left by a time-sliced visit */
@@ -133,6 +134,7 @@ static void run_visit(int t, visit_t *V, int sx, int sy) {
         memcpy(buf, nb, sizeof(nb));
         for (int l = 0; l < TS; ++l) mask[l] |= addm[l];
         cyc += two ? STEP2_FACTOR : 1.0;
+        if (PUBSTEP && steps == PUBSTEP) { V->has_mid = 1; memcpy(V->midbuf, buf, sizeof(V->midbuf)); memcpy(V->middirty, V->dirty, sizeof(V->middirty)); }
         if (steps >= SLICE) break;          /* time slice: publish what we have, go again later */
     }
     V->unfinished = 0; for (int l = 0; l < TS; ++l) if (mask[l]) V->unfinished = 1;
@@ -171,7 +173,7 @@ static void activate(int t, double p) {
 int main(int argc, char **argv) {
     N = argc > 1 ? atoi(argv[1]) : 1024; int W = argc > 2 ? atoi(argv[2]) : 1776; policy = argc > 3 ? atoi(argv[3]) : 0;
     double dtiles = argc > 4 ? atof(argv[4]) : 1.0; WINDOW = argc > 5 ? atoi(argv[5]) : 2;
-    if (getenv("SLICE")) SLICE = atoi(getenv("SLICE")); if (getenv("OVH")) CYC_OVH = atof(getenv("OVH")); if (getenv("STEP")) CYC_STEP = atof(getenv("STEP"));
+    if (getenv("PUBSTEP")) PUBSTEP = atoi(getenv("PUBSTEP")); if (getenv("SLICE")) SLICE = atoi(getenv("SLICE")); if (getenv("OVH")) CYC_OVH = atof(getenv("OVH")); if (getenv("STEP")) CYC_STEP = atof(getenv("STEP"));
     if (getenv("VARIANT")) VARIANT = atoi(getenv("VARIANT")); if (getenv("STEP2")) STEP2_FACTOR = atof(getenv("STEP2"));
     NT = (N + TS - 1) / TS;
     cost = malloc(sizeof(double) * N * N); T = malloc(sizeof(double) * N * N);
@@ -186,7 +188,7 @@ int main(int argc, char **argv) {
     for (int i = 0; i < N * N; ++i) T[i] = INFINITY;
     T[sy * N + sx] = 0;
     activate((sy / TS) * NT + sx / TS, 0);
-    typedef struct { double t; int tile; visit_t *V; double p; } ev;
+    typedef struct { double t; int tile; visit_t *V; double p; int mid; double tend; } ev;
     ev *run = malloc(sizeof(ev) * W); int nrun = 0;
     visit_t *pool = malloc(sizeof(visit_t) * W); int *freev = malloc(sizeof(int) * W); int nfree = W; for (int i = 0; i < W; ++i) freev[i] = i;
     double now = 0; long maxrun = 0; double busy = 0;
@@ -198,24 +200,35 @@ int main(int argc, char **argv) {
             state[t] = RUNNING;
             ev e; e.tile = t; e.p = prio[t]; e.V = &pool[freev[--nfree]];
             run_visit(t, e.V, sx, sy);
-            double dur = e.V->steps * CYC_STEP + CYC_OVH + CYC_POP;
-            e.t = now + dur; busy += dur;
+            double dur = e.V->steps * CYC_STEP + CYC_OVH + CYC_POP + (e.V->has_mid ? CYC_PUB : 0);
+            e.tend = now + dur; busy += dur; e.mid = 0;
+            if (e.V->has_mid) { e.mid = 1; e.t = now + CYC_POP + CYC_OVH * 0.3 + PUBSTEP * CYC_STEP + CYC_PUB; } else e.t = e.tend;
             run[nrun++] = e;
         }
         if (nrun > maxrun) maxrun = nrun;
         if (nrun == 0) break;
         int bi = 0; for (int i = 1; i < nrun; ++i) if (run[i].t < run[bi].t) bi = i;
-        ev e = run[bi]; run[bi] = run[--nrun]; now = e.t;
+        ev e = run[bi]; now = e.t;
         int t = e.tile, tx = t % NT, ty = t / NT, P = TS + 2;
-        double *buf = e.V->buf; int act[4] = {0, 0, 0, 0}; double ap[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
+        int is_mid = e.mid;
+        if (is_mid) { run[bi].mid = 0; run[bi].t = e.tend; } else run[bi] = run[--nrun];
+        double *buf = is_mid ? e.V->midbuf : e.V->buf; unsigned *dd = is_mid ? e.V->middirty : e.V->dirty;
+        int act[4] = {0, 0, 0, 0}; double ap[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
         for (int j = 0; j < TS; ++j) for (int i = 0; i < TS; ++i) {
-            if (!(e.V->dirty[j] >> i & 1)) continue;
+            if (!(dd[j] >> i & 1)) continue;
             int x = tx * TS + i, y = ty * TS + j; double v = buf[(j + 1) * P + i + 1];
             T[y * N + x] = v;
             if (i == 0 && v < buf[(j + 1) * P]) { act[0] = 1; ap[0] = fmin(ap[0], v); }
             if (i == TS - 1 && v < buf[(j + 1) * P + TS + 1]) { act[1] = 1; ap[1] = fmin(ap[1], v); }
             if (j == 0 && v < buf[i + 1]) { act[2] = 1; ap[2] = fmin(ap[2], v); }
             if (j == TS - 1 && v < buf[(TS + 1) * P + i + 1]) { act[3] = 1; ap[3] = fmin(ap[3], v); }
+        }
+        if (is_mid) {
+            if (act[0] && tx > 0) activate(t - 1, ap[0]);
+            if (act[1] && tx < NT - 1) activate(t + 1, ap[1]);
+            if (act[2] && ty > 0) activate(t - NT, ap[2]);
+            if (act[3] && ty < NT - 1) activate(t + NT, ap[3]);
+            continue;
         }
         for (int l = 0; l < TS; ++l) saved_mask[t * TS + l] |= e.V->left[l];
         freev[nfree++] = (int)(e.V - pool);
