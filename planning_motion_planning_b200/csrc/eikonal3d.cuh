@@ -73,6 +73,30 @@ __device__ __forceinline__ real solve3d_update(real t0, real t1, real t2, real C
     return num<real>::inf();                          // no finite neighbour (reference: max([]) raises)
 }
 
+// fp32 variant: the reference expression n*C^2 + S^2 - n*Q cancels catastrophically in single
+// precision once T >> C (hard part 3), so the float kernel solves the same quadratic in
+// shifted variables u_i = t_i - min(t): T = m + (Su + sqrt(n*C^2 + Su^2 - n*Qu)) / n.  Same
+// descending-dimension logic; only the fp64 path has to reproduce the reference's rounding.
+template <>
+__device__ __forceinline__ float solve3d_update<float>(float t0, float t1, float t2, float C) {
+    const float INF = num<float>::inf();
+    float lo = fminf(t0, fminf(t1, t2));
+    if (!(lo < INF)) return INF;
+    float u[3] = {t0 - lo, t1 - lo, t2 - lo};
+    // sort ascending (3 elements); +inf entries end up last and are dropped by the test below
+    if (u[0] > u[1]) { float x = u[0]; u[0] = u[1]; u[1] = x; }
+    if (u[1] > u[2]) { float x = u[1]; u[1] = u[2]; u[2] = x; }
+    if (u[0] > u[1]) { float x = u[0]; u[0] = u[1]; u[1] = x; }
+    const float C2 = C * C;
+    for (int n = 3; n >= 1; --n) {
+        const float mx = u[n - 1];
+        float sumT = 0.f, S = 0.f, Q = 0.f;
+        for (int i = 0; i < n; ++i) { const float d = mx - u[i]; sumT += d * d; S += u[i]; Q += u[i] * u[i]; }
+        if (C2 > sumT) return lo + (S + sqrtf(fmaxf((float)n * C2 + S * S - (float)n * Q, 0.f))) / (float)n;
+    }
+    return INF;
+}
+
 template <typename real, int TZ>
 struct Tile3D {
     static constexpr int PZ = TZ + 2;                          // z pitch incl. halo
