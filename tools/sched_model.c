@@ -126,6 +126,10 @@ static void run_visit(int t, visit_t *V, int sx, int sy) {
                         int jj = j + dj[d], ii = i + di[d];
                         if (jj < 0 || ii < 0 || jj >= TS || ii >= TS) continue;
                         if (!(B(jj, ii) > v) || isinf(cb[jj * TS + ii])) continue;
+                        if (VARIANT & 4) {   /* exact filter: v must become the axis-minimum of the neighbour */
+                            int oj = jj + dj[d], oi = ii + di[d];
+                            if (oj >= -1 && oi >= -1 && oj <= TS && oi <= TS && !(v < B(oj, oi))) continue;
+                        }
                         if (transposed) addm[ii] |= 1u << jj; else addm[jj] |= 1u << ii;
                     }
                 }
