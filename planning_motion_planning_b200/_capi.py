@@ -66,8 +66,8 @@ def lib():
     """Load (building first if stale and nvcc is present) the CUDA library."""
     global _LIB
     if _LIB is None:
-        path = _build.LIB_PATH
-        if _build.needs_build():
+        path = os.environ.get("FMB_LIB") or _build.LIB_PATH        # FMB_LIB: A/B builds of the same ABI
+        if path == _build.LIB_PATH and _build.needs_build():
             try:
                 _build.build()
             except Exception as e:  # no nvcc / compile error: loud, never a fallback

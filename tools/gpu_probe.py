@@ -25,7 +25,7 @@ ref = None
 for cfg in configs:
     kv = dict(x.split("=") for x in cfg.split(",") if x)
     for k in list(os.environ):
-        if k.startswith("FMB_") and k != "FMB_WATCHDOG_MS":
+        if k.startswith("FMB_") and k not in ("FMB_WATCHDOG_MS", "FMB_LIB"):
             del os.environ[k]
     os.environ.update(kv)
     best = None
