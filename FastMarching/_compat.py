@@ -75,14 +75,15 @@ def truncate(T: torch.Tensor, cost: torch.Tensor, rank: torch.Tensor, k: int) ->
     cost = cost.contiguous()
     rank = rank.contiguous()
     out = torch.empty_like(T)
-    ovf = torch.zeros(1, dtype=torch.int32, device=T.device)
+    scratch = torch.empty(T.numel(), dtype=torch.int32, device=T.device)      # compacted narrow-band cells
+    counters = torch.zeros(2, dtype=torch.int32, device=T.device)
     L = _capi.lib()
     stream = torch.cuda.current_stream().cuda_stream
     if T.dim() == 2:
         rc = L.fmb_truncate2d_f64(T.data_ptr(), cost.data_ptr(), rank.data_ptr(), T.shape[0], T.shape[1], int(k),
-                                  out.data_ptr(), ovf.data_ptr(), stream)
+                                  out.data_ptr(), scratch.data_ptr(), counters.data_ptr(), stream)
     else:
         rc = L.fmb_truncate3d_f64(T.data_ptr(), cost.data_ptr(), rank.data_ptr(), T.shape[0], T.shape[1], T.shape[2],
-                                  int(k), out.data_ptr(), ovf.data_ptr(), stream)
+                                  int(k), out.data_ptr(), scratch.data_ptr(), counters.data_ptr(), stream)
     _capi.check(rc)
     return out

@@ -145,13 +145,15 @@ int fmb_trace3d_f64(const double *d_T, int64_t T_qstride, int ny, int nx, int nz
  * rest is +inf.  Given the full field d_F, the costs, and d_rank (int32 pop rank of
  * every cell: source 0, unreached INT32_MAX; a stable ascending sort of d_F), these
  * rebuild that partial field for truncation after k pops.  Dense arrays.
- * d_overflow (int32, zeroed by the caller) counts narrow-band cells whose replay
- * exceeded the internal recursion depth (their value then falls back to d_F).
+ * d_list: int32 scratch with room for one entry per cell (the narrow-band cells are compacted into
+ * it so that the replay runs with full warps); d_counters: int32[2], zeroed by the caller; on return
+ * [0] = number of narrow-band cells, [1] = replays that hit the internal depth/work cap (their
+ * deepest contributions then fall back to the full-field value; damped by >= 2^-32).
  */
 int fmb_truncate2d_f64(const double *d_F, const double *d_cost, const int32_t *d_rank, int rows, int cols,
-                       int32_t k, double *d_out, int32_t *d_overflow, void *stream);
+                       int32_t k, double *d_out, int32_t *d_list, int32_t *d_counters, void *stream);
 int fmb_truncate3d_f64(const double *d_F, const double *d_cost, const int32_t *d_rank, int ny, int nx, int nz,
-                       int32_t k, double *d_out, int32_t *d_overflow, void *stream);
+                       int32_t k, double *d_out, int32_t *d_list, int32_t *d_counters, void *stream);
 
 #ifdef __cplusplus
 }

@@ -22,9 +22,9 @@
 
 namespace fmb {
 
-constexpr int TRUNC_MAX_DEPTH = 48;
-constexpr int TRUNC_MAX_EVALS = 1 << 14;   // work cap per narrow-band cell (safety net; never reached with the memo)
-constexpr int TRUNC_MEMO = 256;             // memo entries per thread (power of two)
+constexpr int TRUNC_MAX_DEPTH = 64;
+constexpr int TRUNC_MAX_EVALS = 1 << 16;   // work cap per narrow-band cell (safety net; never reached with the memo)
+constexpr int TRUNC_MEMO = 1024;            // memo entries per thread (power of two)
 
 template <int D> struct Grid;
 template <> struct Grid<2> {
@@ -94,18 +94,33 @@ __device__ __forceinline__ int last_update_time(const Grid<D> &g, const int *ran
     return best;
 }
 
+// pass 1: accepted cells and far cells are final here; narrow-band cells (free, not accepted, next
+// to an accepted cell) are collected into a dense list so that pass 2 runs with full warps.
 template <typename real, int D>
-__global__ void truncate_kernel(Grid<D> g, const real *F, const real *cost, const int *rank, int k, real *out,
-                                int *overflow) {
-    constexpr int NN = Grid<D>::NN;
+__global__ void truncate_mark_kernel(Grid<D> g, const real *F, const real *cost, const int *rank, int k, real *out,
+                                     int *list, int *count) {
     const real INF = num<real>::inf();
     const long long total = g.size();
-    struct Frame { long long c; int tp; int stage; real amin; real v[NN]; };
     for (long long c0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; c0 < total; c0 += (long long)gridDim.x * blockDim.x) {
         if (rank[c0] <= k) { out[c0] = F[c0]; continue; }
-        if (!(cost[c0] < INF)) { out[c0] = INF; continue; }
+        out[c0] = INF;
+        if (!(cost[c0] < INF)) continue;
+        if (last_update_time<D>(g, rank, c0, k) < 0) continue;
+        list[atomicAdd(count, 1)] = (int)c0;
+    }
+}
+
+// pass 2: replay the last relaxation of every narrow-band cell (one thread per listed cell)
+template <typename real, int D>
+__global__ void truncate_replay_kernel(Grid<D> g, const real *F, const real *cost, const int *rank, int k, real *out,
+                                       const int *list, const int *count, int *overflow) {
+    constexpr int NN = Grid<D>::NN;
+    const real INF = num<real>::inf();
+    const int n_list = *count;
+    struct Frame { long long c; int tp; int stage; real amin; real v[NN]; };
+    for (int li = blockIdx.x * blockDim.x + threadIdx.x; li < n_list; li += gridDim.x * blockDim.x) {
+        const long long c0 = list[li];
         const int t0 = last_update_time<D>(g, rank, c0, k);
-        if (t0 < 0) { out[c0] = INF; continue; }
         Frame st[TRUNC_MAX_DEPTH];
         int sp = 0;
         st[0].c = c0; st[0].tp = t0; st[0].stage = 0; st[0].amin = accepted_min<real, D>(g, rank, F, c0, t0);
@@ -142,7 +157,7 @@ __global__ void truncate_kernel(Grid<D> g, const real *F, const real *cost, cons
                         // memo lookup: tent(n, .) depends only on (n, tn)
                         unsigned h = ((unsigned)n * 2654435761u + (unsigned)tn * 40503u) & (TRUNC_MEMO - 1);
                         bool hit = false;
-                        for (int probe = 0; probe < 8; ++probe) {
+                        for (int probe = 0; probe < 16; ++probe) {
                             const unsigned e = (h + probe) & (TRUNC_MEMO - 1);
                             if (memo_cell[e] < 0) break;
                             if (memo_cell[e] == (int)n && memo_tp[e] == tn) { val = memo_val[e]; hit = true; break; }
@@ -159,9 +174,9 @@ __global__ void truncate_kernel(Grid<D> g, const real *F, const real *cost, cons
             if (descended) continue;
             result = Grid<D>::template update<real>(f.v, cost[f.c]);
             --budget;
-            if (sp > 0 && memo_used < TRUNC_MEMO / 2) {      // remember tent(f.c, f.tp)
+            if (sp > 0 && memo_used < (TRUNC_MEMO * 3) / 4) {      // remember tent(f.c, f.tp)
                 unsigned h = ((unsigned)f.c * 2654435761u + (unsigned)f.tp * 40503u) & (TRUNC_MEMO - 1);
-                for (int probe = 0; probe < 8; ++probe) {
+                for (int probe = 0; probe < 16; ++probe) {
                     const unsigned e = (h + probe) & (TRUNC_MEMO - 1);
                     if (memo_cell[e] < 0) { memo_cell[e] = (int)f.c; memo_tp[e] = f.tp; memo_val[e] = result; ++memo_used; break; }
                 }

@@ -105,15 +105,17 @@ void emu_trace3d_f64(const double *T, int ny, int nx, int nz, int npaths, const 
 
 int emu_truncate2d_f64(const double *F, const double *cost, const int *rank, int rows, int cols, int k, double *out) {
     fmb::Grid<2> g; g.rows = rows; g.cols = cols;
-    int overflow = 0;
-    emu::launch(4, 64, 0, [&] { fmb::truncate_kernel<double, 2>(g, F, cost, rank, k, out, &overflow); });
-    return overflow;
+    std::vector<int> list((size_t)rows * cols); int counters[2] = {0, 0};
+    emu::launch(4, 64, 0, [&] { fmb::truncate_mark_kernel<double, 2>(g, F, cost, rank, k, out, list.data(), counters); });
+    emu::launch(4, 64, 0, [&] { fmb::truncate_replay_kernel<double, 2>(g, F, cost, rank, k, out, list.data(), counters, counters + 1); });
+    return counters[1];
 }
 int emu_truncate3d_f64(const double *F, const double *cost, const int *rank, int ny, int nx, int nz, int k, double *out) {
     fmb::Grid<3> g; g.ny = ny; g.nx = nx; g.nz = nz;
-    int overflow = 0;
-    emu::launch(4, 64, 0, [&] { fmb::truncate_kernel<double, 3>(g, F, cost, rank, k, out, &overflow); });
-    return overflow;
+    std::vector<int> list((size_t)ny * nx * nz); int counters[2] = {0, 0};
+    emu::launch(4, 64, 0, [&] { fmb::truncate_mark_kernel<double, 3>(g, F, cost, rank, k, out, list.data(), counters); });
+    emu::launch(4, 64, 0, [&] { fmb::truncate_replay_kernel<double, 3>(g, F, cost, rank, k, out, list.data(), counters, counters + 1); });
+    return counters[1];
 }
 
 void emu_div3(const double *x, double *out, long long n) { for (long long i = 0; i < n; ++i) out[i] = fmb::num<double>::div3(x[i]); }
