@@ -99,7 +99,10 @@ int launch_solve2d(fmb::Problem2D<real> P, const WsLayout &L, cudaStream_t st, i
     if (per_sm < 1) return fail(FMB_E_CUDA, "solve2d kernel does not fit on an SM%s");
     const long long ntiles = (long long)P.nq * P.ntx * P.nty;
     long long blocks = (long long)per_sm * sm_count();
-    const long long need = (ntiles + WARPS - 1) / WARPS;
+    // One map: more workers than ~half the tiles only add speculative re-visits (measured: 400^2
+    // and 90x90x28 run faster with fewer warps); batches keep one worker per tile up to the machine.
+    const int div = env_int("FMB_WORKER_DIV", P.nq == 1 ? 2 : 1);
+    const long long need = (ntiles + (long long)WARPS * div - 1) / ((long long)WARPS * div);
     if (blocks > need) blocks = need;
     if (blocks < 1) blocks = 1;
     const int cap_blocks = env_int("FMB_MAX_BLOCKS", 0);
