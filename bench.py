@@ -63,8 +63,10 @@ def make_map(n, kind, seed=0):
         except Exception:
             pass
     c = synth.mars_costmap(n, seed) if kind == "mars" else synth.random_costmap((n, n), seed)
-    try:
-        np.save(cache, c)
+    try:        # atomic publish: several ranks may build the same cache concurrently
+        tmp = f"{cache}.{os.getpid()}.tmp.npy"
+        np.save(tmp, c)
+        os.replace(tmp, cache)
     except Exception:
         pass
     return c
@@ -440,7 +442,9 @@ def own_arm(args):
         else:
             c3, g3, s3 = synth.arm_volume((m3, m3, m3), 0)
             try:
-                np.savez(cache, c=c3, g=np.array(g3), s=np.array(s3))
+                tmp = f"{cache}.{os.getpid()}.tmp.npz"
+                np.savez(tmp, c=c3, g=np.array(g3), s=np.array(s3))
+                os.replace(tmp, cache)
             except Exception:
                 pass
         c3d = torch.from_numpy(c3).to(dev)
