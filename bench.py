@@ -7,8 +7,9 @@
 Workload (BASELINE.json metric: "Eikonal solve ms + cell-updates/s (4096^2 map); batched
 queries/s at 1/2/4/8 GPU"): one STEP = one full-field Eikonal solve of a 4096x4096 fp64
 planner-like costmap (SURVEY.md 8d "metric map", seed 0) from one goal + one gradient-descent
-path extraction over the result.  With N GPUs every rank solves its own goal on the same map
-(independent planning queries, no data-path collective): weak scaling.
+path extraction over the result.  With N GPUs every rank runs that query on its own GPU
+(replicas: identical per-GPU work, no data-path collective): weak scaling.  The batched section
+(`batch`) gives every rank its own 4096 distinct goal queries.
 
   value = cells solved per second over the whole job = N * 4096^2 * K / t, t = device time of
           the K timed steps (CUDA events), max over ranks; inputs resident in HBM.
@@ -80,7 +81,8 @@ def goals_for(c, n_ranks):
     fr = [(0.25, 0.25), (0.75, 0.25), (0.25, 0.75), (0.5, 0.5), (0.6, 0.2), (0.2, 0.6), (0.4, 0.8), (0.8, 0.4)]
     goals, starts = [], []
     for r in range(n_ranks):
-        fx, fy = fr[r % len(fr)]
+        fx, fy = fr[0]        # every rank solves the metric-map query: weak scaling = identical per-GPU work
+                              # (distinct goals per rank are exercised by the batched section and batch.py)
         goals.append(synth.free_cell_near(c, int(fx * n), int(fy * n)))
         starts.append(synth.free_cell_near(c, int((1 - fx) * n) if fx != 0.5 else int(0.1 * n), int((1 - fy) * n) if fy != 0.5 else int(0.1 * n)))
     return goals, starts
@@ -495,7 +497,7 @@ def own_arm(args):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{n}x{n} fp64 planner-like costmap ({args.map}, seed 0): full-field solve + 1 path "
                                    f"per GPU per step", "l2_policy": "inputs larger than L2 (cost + T = %d MiB)" % (2 * cells * 8 >> 20),
-                       "tau": tau, "path_rows": path_len, "path_status": path_status, "parallelism": f"{world} independent queries"},
+                       "tau": tau, "path_rows": path_len, "path_status": path_status, "parallelism": f"{world} replicas, one query per GPU per step"},
             "breakdown_ms": {"init_fill": init_ms, "solve_kernel": solve_ms, "trace_kernel": trace_ms},
             "solver_stats": {k: stats[k] for k in ("tile_visits", "steps", "evals", "pushes", "cells_written")},
             "evals_per_cell": stats["evals"] / cells,
