@@ -160,3 +160,17 @@ def test_div3_is_correctly_rounded():
     out = np.empty_like(x)
     L.emu_div3(np.ascontiguousarray(x).ctypes.data_as(emu.dp), out.ctypes.data_as(emu.dp), x.size)
     assert np.array_equal(out, x / 3.0)
+
+
+def test_edge_sizes_and_maps_without_inf_border():
+    """Ragged / minimal shapes and maps with no inf border (out-of-domain is treated as +inf)."""
+    rng = np.random.default_rng(0)
+    for shape, g in (((1, 1), [0, 0]), ((1, 7), [3, 0]), ((5, 1), [0, 2]), ((2, 2), [1, 1]), ((32, 32), [31, 31]),
+                     ((33, 33), [32, 0]), ((64, 32), [0, 63])):
+        c = 1 + 4 * rng.random(shape)
+        T, _ = emu.solve2d(c, [g])
+        assert rel_err(T[0], O.computeTmap(c, g)) < TOL64
+    for shape, g in (((1, 1, 1), [0, 0, 0]), ((2, 3, 4), [1, 0, 3]), ((4, 8, 16), [7, 3, 15]), ((5, 9, 17), [8, 4, 16])):
+        c = 1 + 4 * rng.random(shape)
+        T, _ = emu.solve3d(c, [g])
+        assert rel_err(T[0], O.computeTmap3D(c, g)) < TOL64
