@@ -66,7 +66,7 @@ def computeTmap(costMap, goal, start):
     s = _c.node2(start, swap)
     rows, cols = T0.shape
     if 0 <= s[0] < cols and 0 <= s[1] < rows and bool(torch.isfinite(T0[s[1], s[0]])):
-        rank = _c.pop_ranks(T0)
+        rank = _c.pop_ranks_lifo2d(T0, cd, _c.node2(goal, swap))
         T0 = _c.truncate(T0, cd, rank, int(rank[s[1], s[0]]))
     return _to_numpy_field(T0, swap)
 
@@ -78,7 +78,8 @@ def biComputeTmap(costMap, goal, start):
     reference (:161)."""
     T, cd, swap = _solve_fields(costMap, [goal, start])
     TG, TS = T[0], T[1]
-    rG, rS = _c.pop_ranks(TG), _c.pop_ranks(TS)
+    rG = _c.pop_ranks_lifo2d(TG, cd, _c.node2(goal, swap))
+    rS = _c.pop_ranks_lifo2d(TS, cd, _c.node2(start, swap))
     both = torch.isfinite(TG) & torch.isfinite(TS)
     if not bool(both.any()):
         raise NameError("name 'nodeJoin' is not defined")

@@ -59,13 +59,96 @@ def raise_trace(status: int):
 # The solver always produces the full field; pop ranks are recovered by a stable
 # sort of T (ties in row-major order) and the partial field is rebuilt from them.
 def pop_ranks(T: torch.Tensor) -> torch.Tensor:
-    """int32 rank[c] = number of nodes popped before-or-with c (source = 0, unreached = INT32_MAX)."""
+    """int32 rank[c] = number of nodes popped before-or-with c (source = 0, unreached = INT32_MAX).
+    Stable ascending sort of T: exact whenever no two cells carry exactly the same value."""
     flat = T.reshape(-1)
     order = torch.sort(flat, stable=True).indices
     rank = torch.empty(flat.numel(), dtype=torch.int32, device=T.device)
     rank[order] = torch.arange(flat.numel(), dtype=torch.int32, device=T.device)
     rank[~torch.isfinite(flat)] = torch.iinfo(torch.int32).max
     return rank.reshape(T.shape)
+
+
+_BIG = torch.iinfo(torch.int64).max
+
+
+def _shift(a, dy, dx, fill):
+    out = torch.full_like(a, fill)
+    H, W = a.shape
+    ys, yd = slice(max(0, dy), H + min(0, dy)), slice(max(0, -dy), H + min(0, -dy))
+    xs, xd = slice(max(0, dx), W + min(0, dx)), slice(max(0, -dx), W + min(0, -dx))
+    out[yd, xd] = a[ys, xs]
+    return out
+
+
+def _lex_order(T, k2, k3):
+    """argsort by (T, k2, k3) ascending via successive stable sorts."""
+    order = torch.sort(k3.reshape(-1), stable=True).indices
+    order = order[torch.sort(k2.reshape(-1)[order], stable=True).indices]
+    return order[torch.sort(T.reshape(-1)[order], stable=True).indices]
+
+
+def pop_ranks_lifo2d(T: torch.Tensor, cost: torch.Tensor, seed, max_iters: int = 64) -> torch.Tensor:
+    """Pop ranks of the reference's 2D front INCLUDING its order among exactly equal values.
+
+    The reference keeps the narrow band sorted with bisect_left + insert (FastMarching.py:65-67,
+    76-78): among equal T the node (re)inserted LAST pops first.  A node's final value is inserted
+    at the first pop of one of its neighbours at which all inputs of its final update already carry
+    their final values -- tentative neighbour values count (:57-62) -- and within one updateNode
+    call in child order (:46-54).  So the pop order is the ascending order of
+    (T, -insertion time, -child index), where insertion times depend on the ranks themselves:
+    iterate to the fixed point.  Maps without exact ties return after the plain sort.
+    Measured against the reference's true pop order (oracle): uniform and plateau maps exact or
+    within a handful of cells, versus thousands of misplaced cells for the plain sort."""
+    H, W = T.shape
+    fin = torch.isfinite(T)
+    flat = T.reshape(-1)
+    nfin = int(fin.sum())
+    if nfin == int(torch.unique(flat[fin.reshape(-1)]).numel()):
+        return pop_ranks(T)                                       # no ties: the sort is already exact
+    idx = torch.arange(H * W, device=T.device).reshape(H, W)
+    seed_idx = int(seed[1]) * W + int(seed[0])
+    order = _lex_order(T, torch.zeros_like(idx), idx)
+    rank = torch.empty_like(order)
+    rank[order] = torch.arange(order.numel(), device=T.device)
+    rank = rank.reshape(H, W)
+    tau = rank.clone()
+    INF = float("inf")
+    TL, TR, TU, TD = _shift(T, 0, -1, INF), _shift(T, 0, 1, INF), _shift(T, -1, 0, INF), _shift(T, 1, 0, INF)
+    for _ in range(max_iters):
+        r = torch.where(fin, rank, torch.full_like(rank, _BIG))
+        t0 = torch.where(fin, tau, torch.full_like(tau, _BIG))
+        r.view(-1)[seed_idx] = 0
+        t0.view(-1)[seed_idx] = -1                                # the source is final before anything pops
+        RL, RR, RU, RD = _shift(r, 0, -1, _BIG), _shift(r, 0, 1, _BIG), _shift(r, -1, 0, _BIG), _shift(r, 1, 0, _BIG)
+        AL, AR, AU, AD = _shift(t0, 0, -1, _BIG), _shift(t0, 0, 1, _BIG), _shift(t0, -1, 0, _BIG), _shift(t0, 1, 0, _BIG)
+        left = (TL < TR) | ((TL == TR) & (AL <= AR))
+        a, ta = torch.where(left, TL, TR), torch.where(left, AL, AR)
+        up = (TU < TD) | ((TU == TD) & (AU <= AD))
+        b, tb = torch.where(up, TU, TD), torch.where(up, AU, AD)
+        two = (a - b).abs() <= cost
+        ready = torch.where(two, torch.maximum(ta, tb), torch.where(a <= b, ta, tb))   # inputs final from here on
+        tau_new = torch.full_like(r, _BIG)
+        cidx = torch.zeros_like(r)
+        for R, ci in ((RL, 4), (RR, 3), (RU, 2), (RD, 1)):        # child index w.r.t. the popped neighbour
+            ok = (R >= ready) & (R < tau_new)
+            tau_new = torch.where(ok, R, tau_new)
+            cidx = torch.where(ok, torch.full_like(r, ci), cidx)
+        tau_new = torch.where(fin, tau_new, torch.full_like(tau_new, _BIG))
+        tau_new.view(-1)[seed_idx] = -1
+        k2 = torch.where(fin, -tau_new, torch.zeros_like(tau_new))
+        k3 = torch.where(fin, -cidx, torch.zeros_like(cidx))
+        order = _lex_order(T, k2, k3)
+        new_rank = torch.empty_like(order)
+        new_rank[order] = torch.arange(order.numel(), device=T.device)
+        new_rank = new_rank.reshape(H, W)
+        done = torch.equal(new_rank, rank) and torch.equal(tau_new, tau)
+        rank, tau = new_rank, tau_new
+        if done:
+            break
+    out = rank.to(torch.int32)
+    out[~fin] = torch.iinfo(torch.int32).max
+    return out
 
 
 def truncate(T: torch.Tensor, cost: torch.Tensor, rank: torch.Tensor, k: int) -> torch.Tensor:

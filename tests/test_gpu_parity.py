@@ -387,6 +387,22 @@ def test_device_side_failure_is_reported_not_hidden(eng, monkeypatch):
         _capi.check(_capi.lib().fmb_solve2d_f64(cd.data_ptr(), 10, 0, cd.data_ptr(), 120, 0, 120, 120, 1, None, None, 0, None))
 
 
+def test_dropin_partial_fields_on_tie_heavy_maps():
+    """Uniform-cost and block-plateau maps are full of exactly equal T values; the reference pops
+    those LIFO, which decides the join node and which cells are accepted when the fronts meet."""
+    import FastMarching.FastMarching as FM
+    from oracle import oracle as O
+    uniform = np.pad(np.ones((40, 40)), 1, constant_values=np.inf)
+    for c, g, s in ((uniform, [5, 5], [35, 30]), (uniform, [5, 20], [35, 20]), (plateau_map(80, 1), [8, 8], [70, 71]),
+                    (plateau_map(80, 3), [8, 8], [70, 71])):
+        TG, TS, j = FM.biComputeTmap(c, g, s)
+        oTG, oTS, oj = O.biComputeTmap(c, g, s)
+        assert np.array_equal(j, oj)
+        assert rel_err(TG, oTG) < TOL64 and rel_err(TS, oTS) < TOL64
+        T1 = FM.computeTmap(c, g, s)
+        assert rel_err(T1, O.computeTmap(c, g, s)) < TOL64
+
+
 def test_dropin_errors():
     import FastMarching.FastMarching as FM
     c = rand_map((40, 40), 0)

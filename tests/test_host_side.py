@@ -83,3 +83,20 @@ def test_product_never_imports_oracle():
                 if f.endswith((".py", ".cu", ".cuh", ".inc", ".h")):
                     src = open(os.path.join(root, f)).read()
                     assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, f
+
+
+def test_lifo_pop_order_emulation_matches_reference_order():
+    """FastMarching._compat.pop_ranks_lifo2d (torch, runs on CPU tensors here) against the
+    reference's true pop order (C oracle = bitwise restatement): exact ties pop LIFO."""
+    import torch
+    from conftest import plateau_map
+    from FastMarching import _compat
+    uniform = np.pad(np.ones((40, 40)), 1, constant_values=np.inf)
+    for c, g, max_bad in ((uniform, [20, 20], 0), (plateau_map(80, 1), [8, 8], 0), (plateau_map(80, 3), [8, 8], 0),
+                          (plateau_map(80, 2), [8, 8], 12), (rand_map((60, 60), 2), [9, 40], 0)):
+        T, order, _ = O.computeTmap(c, g, return_stats=True)
+        rank = _compat.pop_ranks_lifo2d(torch.from_numpy(T), torch.from_numpy(c), g).numpy().ravel()
+        mine = np.argsort(rank, kind="stable")[1:1 + len(order)]
+        plain = np.argsort(T.ravel(), kind="stable")[1:1 + len(order)]
+        assert int((mine != order).sum()) <= max_bad
+        assert int((mine != order).sum()) <= int((plain != order).sum())
