@@ -88,7 +88,7 @@ def _lex_order(T, k2, k3):
     return order[torch.sort(T.reshape(-1)[order], stable=True).indices]
 
 
-def pop_ranks_lifo2d(T: torch.Tensor, cost: torch.Tensor, seed, max_iters: int = 64) -> torch.Tensor:
+def pop_ranks_lifo2d(T: torch.Tensor, cost: torch.Tensor, seed, max_iters: int = 96) -> torch.Tensor:
     """Pop ranks of the reference's 2D front INCLUDING its order among exactly equal values.
 
     The reference keeps the narrow band sorted with bisect_left + insert (FastMarching.py:65-67,
@@ -106,8 +106,10 @@ def pop_ranks_lifo2d(T: torch.Tensor, cost: torch.Tensor, seed, max_iters: int =
     nfin = int(fin.sum())
     if nfin == int(torch.unique(flat[fin.reshape(-1)]).numel()):
         return pop_ranks(T)                                       # no ties: the sort is already exact
-    idx = torch.arange(H * W, device=T.device).reshape(H, W)
     seed_idx = int(seed[1]) * W + int(seed[0])
+    if T.is_cuda:
+        return _pop_ranks_lifo2d_cuda(T.contiguous(), cost.contiguous(), seed_idx, max_iters)
+    idx = torch.arange(H * W, device=T.device).reshape(H, W)
     order = _lex_order(T, torch.zeros_like(idx), idx)
     rank = torch.empty_like(order)
     rank[order] = torch.arange(order.numel(), device=T.device)
@@ -149,6 +151,42 @@ def pop_ranks_lifo2d(T: torch.Tensor, cost: torch.Tensor, seed, max_iters: int =
     out = rank.to(torch.int32)
     out[~fin] = torch.iinfo(torch.int32).max
     return out
+
+
+def _pop_ranks_lifo2d_cuda(T, cost, seed_idx: int, max_iters: int) -> torch.Tensor:
+    """Device path of :func:`pop_ranks_lifo2d`: the per-cell step is one kernel of libfm_b200
+    (csrc/tiekeys.cuh) and one stable sort of its packed key per iteration."""
+    H, W = T.shape
+    n = H * W
+    dev = T.device
+    flat = T.reshape(-1)
+    fin = torch.isfinite(flat)
+    order = torch.sort(flat, stable=True).indices
+    ts = flat[order]
+    grp_sorted = torch.cumsum(torch.cat([torch.zeros(1, dtype=torch.int32, device=dev), (ts[1:] != ts[:-1]).to(torch.int32)]), 0)
+    group = torch.empty(n, dtype=torch.int32, device=dev)
+    group[order] = grp_sorted.to(torch.int32)
+    ar = torch.arange(n, dtype=torch.int32, device=dev)
+    rank = torch.empty(n, dtype=torch.int32, device=dev)
+    rank[order] = ar
+    tau = rank.clone()
+    tau_new = torch.empty_like(tau)
+    key = torch.empty(n, dtype=torch.int64, device=dev)
+    L = _capi.lib()
+    stream = torch.cuda.current_stream().cuda_stream
+    for _ in range(max_iters):
+        _capi.check(L.fmb_tie_keys2d_f64(T.data_ptr(), cost.data_ptr(), rank.data_ptr(), tau.data_ptr(), group.data_ptr(),
+                                         H, W, seed_idx, tau_new.data_ptr(), key.data_ptr(), stream))
+        order = torch.sort(key, stable=True).indices
+        new_rank = torch.empty_like(rank)
+        new_rank[order] = ar
+        done = torch.equal(new_rank, rank) and torch.equal(tau_new, tau)
+        rank, tau, tau_new = new_rank, tau_new, tau
+        if done:
+            break
+    out = rank.clone()
+    out[~fin] = torch.iinfo(torch.int32).max
+    return out.reshape(H, W)
 
 
 def truncate(T: torch.Tensor, cost: torch.Tensor, rank: torch.Tensor, k: int) -> torch.Tensor:

@@ -155,6 +155,15 @@ int fmb_truncate2d_f64(const double *d_F, const double *d_cost, const int32_t *d
 int fmb_truncate3d_f64(const double *d_F, const double *d_cost, const int32_t *d_rank, int ny, int nx, int nz,
                        int32_t k, double *d_out, int32_t *d_list, int32_t *d_counters, void *stream);
 
+/* One refinement step of the reference's pop order among exactly equal T values (the reference
+ * keeps its narrow band with bisect_left + insert, FastMarching.py:65-67,76-78: last inserted pops
+ * first).  Inputs: full field, costs, current int32 pop ranks and insertion times, tie-group id of
+ * every cell (dense rank of its T value); outputs the new insertion times and a packed 64-bit key
+ * whose ascending stable sort gives the next ranks.  Iterated to a fixed point by the caller. */
+int fmb_tie_keys2d_f64(const double *d_T, const double *d_cost, const int32_t *d_rank, const int32_t *d_tau,
+                       const int32_t *d_group, int rows, int cols, int32_t seed_index,
+                       int32_t *d_tau_new, int64_t *d_key, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

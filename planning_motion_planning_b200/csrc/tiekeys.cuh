@@ -1,0 +1,52 @@
+// tiekeys.cuh -- one refinement step of the reference's pop order among exactly equal T values
+// (FastMarching.py:65-67,76-78: bisect_left + insert => the node (re)inserted last pops first).
+//
+// For every cell: the pop ("time") at which its final value is inserted = the first pop of one of
+// its neighbours at which every input of its final update already carries its final value
+// (tentative neighbour values count, :57-62), and its child index in that updateNode call (:46-54).
+// The sort key (tie group of T ascending, insertion time descending, child index descending) is
+// packed into 64 bits so that one stable sort per iteration yields the next ranks; the host loop
+// (FastMarching/_compat.py) iterates to the fixed point.  Same arithmetic as the torch reference
+// implementation there, which the tests compare against the reference's true pop order.
+#pragma once
+#include "fm_common.cuh"
+
+namespace fmb {
+
+__global__ void tie_keys2d_kernel(const double *T, const double *cost, const int *rank, const int *tau, const int *group,
+                                  int rows, int cols, int seed_idx, int *tau_new, long long *key) {
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    const long long BIG = 0x7fffffffLL;
+    const long long total = (long long)rows * cols;
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < total; c += (long long)gridDim.x * blockDim.x) {
+        const double t = T[c];
+        if (!(t < INF)) { tau_new[c] = 0x7fffffff; key[c] = 0x7fffffffffffffffLL; continue; }
+        const int y = (int)(c / cols), x = (int)(c - (long long)y * cols);
+        double tv[4]; long long rv[4], av[4];
+        const long long nb[4] = {x > 0 ? c - 1 : -1, x < cols - 1 ? c + 1 : -1, y > 0 ? c - cols : -1, y < rows - 1 ? c + cols : -1};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            tv[i] = INF; rv[i] = BIG; av[i] = BIG;
+            if (nb[i] >= 0) {
+                tv[i] = T[nb[i]];
+                if (tv[i] < INF) { rv[i] = rank[nb[i]]; av[i] = tau[nb[i]]; }
+                if (nb[i] == seed_idx) { rv[i] = 0; av[i] = -1; }
+            }
+        }
+        const bool left = (tv[0] < tv[1]) || (tv[0] == tv[1] && av[0] <= av[1]);
+        const double a = left ? tv[0] : tv[1]; const long long ta = left ? av[0] : av[1];
+        const bool up = (tv[2] < tv[3]) || (tv[2] == tv[3] && av[2] <= av[3]);
+        const double b = up ? tv[2] : tv[3]; const long long tb = up ? av[2] : av[3];
+        const bool two = fabs(a - b) <= cost[c];
+        const long long ready = two ? (ta > tb ? ta : tb) : (a <= b ? ta : tb);
+        long long best = BIG; int cidx = 0;
+        const int ci[4] = {4, 3, 2, 1};          // popped neighbour left/right/up/down => my child index in its updateNode
+#pragma unroll
+        for (int i = 0; i < 4; ++i) if (rv[i] >= ready && rv[i] < best) { best = rv[i]; cidx = ci[i]; }
+        if (c == seed_idx) best = -1;
+        tau_new[c] = (int)best;
+        key[c] = ((long long)group[c] << 35) | ((long long)(0xffffffffLL - (unsigned long long)(best + 1)) << 3) | (long long)(7 - cidx);
+    }
+}
+
+}  // namespace fmb

@@ -387,6 +387,23 @@ def test_device_side_failure_is_reported_not_hidden(eng, monkeypatch):
         _capi.check(_capi.lib().fmb_solve2d_f64(cd.data_ptr(), 10, 0, cd.data_ptr(), 120, 0, 120, 120, 1, None, None, 0, None))
 
 
+def test_tie_order_kernel_matches_torch_reference_and_oracle_order():
+    """csrc/tiekeys.cuh (device path of pop_ranks_lifo2d) == the torch implementation of the same
+    rule on the CPU, and both reproduce the reference's true pop order on tie-heavy maps."""
+    import torch
+    from FastMarching import _compat
+    from oracle import oracle as O
+    uniform = np.pad(np.ones((60, 60)), 1, constant_values=np.inf)
+    for c, g, max_bad in ((uniform, [30, 30], 0), (uniform, [12, 40], 40), (plateau_map(80, 1), [8, 8], 0),
+                          (plateau_map(80, 2), [8, 8], 12)):
+        T, order, _ = O.computeTmap(c, g, return_stats=True)
+        r_cpu = _compat.pop_ranks_lifo2d(torch.from_numpy(T), torch.from_numpy(c), g)
+        r_gpu = _compat.pop_ranks_lifo2d(torch.from_numpy(T).cuda(), torch.from_numpy(c).cuda(), g).cpu()
+        assert torch.equal(r_cpu, r_gpu)
+        mine = np.argsort(r_gpu.numpy().ravel(), kind="stable")[1:1 + len(order)]
+        assert int((mine != order).sum()) <= max_bad
+
+
 def test_dropin_partial_fields_on_tie_heavy_maps():
     """Uniform-cost and block-plateau maps are full of exactly equal T values; the reference pops
     those LIFO, which decides the join node and which cells are accepted when the fronts meet."""
