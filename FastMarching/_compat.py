@@ -174,13 +174,14 @@ def _pop_ranks_lifo2d_cuda(T, cost, seed_idx: int, max_iters: int) -> torch.Tens
     key = torch.empty(n, dtype=torch.int64, device=dev)
     L = _capi.lib()
     stream = torch.cuda.current_stream().cuda_stream
-    for _ in range(max_iters):
+    for it in range(max_iters):
         _capi.check(L.fmb_tie_keys2d_f64(T.data_ptr(), cost.data_ptr(), rank.data_ptr(), tau.data_ptr(), group.data_ptr(),
                                          H, W, seed_idx, tau_new.data_ptr(), key.data_ptr(), stream))
         order = torch.sort(key, stable=True).indices
         new_rank = torch.empty_like(rank)
         new_rank[order] = ar
-        done = torch.equal(new_rank, rank) and torch.equal(tau_new, tau)
+        # the convergence test synchronises with the device: only every fourth iteration
+        done = (it & 3) == 3 and torch.equal(new_rank, rank) and torch.equal(tau_new, tau)
         rank, tau, tau_new = new_rank, tau_new, tau
         if done:
             break
