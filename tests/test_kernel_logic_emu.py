@@ -174,3 +174,42 @@ def test_edge_sizes_and_maps_without_inf_border():
         c = 1 + 4 * rng.random(shape)
         T, _ = emu.solve3d(c, [g])
         assert rel_err(T[0], O.computeTmap3D(c, g)) < TOL64
+
+
+def test_tracers_fuzz_against_oracle_including_failure_modes():
+    """Seeded fuzz: partial fields with walls, integer / fractional / arbitrary start points.  Paths
+    (atol 1e-9) and status codes (early return, IndexError, ValueError, OverflowError) must match."""
+    rng = np.random.default_rng(123)
+    for _ in range(30):
+        n = int(rng.integers(12, 36))
+        c = rand_map((n, n + 3), int(rng.integers(0, 1000)))
+        for _w in range(int(rng.integers(0, 4))):
+            y, x = int(rng.integers(1, n - 1)), int(rng.integers(1, n))
+            c[y, x:x + int(rng.integers(1, 8))] = np.inf
+        free = np.argwhere(np.isfinite(c))
+        gy, gx = free[int(rng.integers(0, len(free)))]
+        sy, sx = free[int(rng.integers(0, len(free)))]
+        T = O.computeTmap(c, [int(gx), int(gy)], [int(sx), int(sy)] if rng.random() < .6 else None)
+        inits = [[float(sx), float(sy)], [sx + rng.random() * .9, sy + rng.random() * .9],
+                 [float(rng.random() * (n + 2)), float(rng.random() * (n - 1))]]
+        end = [float(gx), float(gy)]
+        p, s = emu.trace2d(T, inits, [end] * 3, field_of_path=[0, 0, 0])
+        for k, init in enumerate(inits):
+            po, so = O.getPathGDM(T, np.array(init), end, 0.5, return_status=True)
+            assert s[k] == so and p[k].shape == po.shape
+            assert len(po) == 0 or np.allclose(p[k], po, rtol=0, atol=1e-9, equal_nan=True)
+    for _ in range(12):
+        shp = tuple(int(v) for v in rng.integers(8, 15, size=3))
+        c = rand_map(shp, int(rng.integers(0, 1000)))
+        if rng.random() < .5:
+            c[shp[0] // 2, 2:shp[1] - 2, 2:shp[2] - 3] = np.inf
+        free = np.argwhere(np.isfinite(c))
+        g, s0 = free[int(rng.integers(0, len(free)))], free[int(rng.integers(0, len(free)))]
+        goal, start = [int(g[1]), int(g[0]), int(g[2])], [int(s0[1]), int(s0[0]), int(s0[2])]
+        T = O.computeTmap3D(c, goal, start if rng.random() < .6 else None)
+        inits = [[float(v) for v in start], [start[0] + rng.random() * .9, start[1] + rng.random() * .9, start[2] + rng.random() * .9]]
+        p, s = emu.trace3d(T, inits, [[float(v) for v in goal]] * 2, field_of_path=[0, 0])
+        for k, init in enumerate(inits):
+            po, so = O.getPathGDM3D(T, np.array(init), np.array(goal, dtype=float), 0.5, return_status=True)
+            assert s[k] == so and p[k].shape == po.shape
+            assert len(po) == 0 or np.allclose(p[k], po, rtol=0, atol=1e-9, equal_nan=True)
