@@ -124,16 +124,23 @@ def pop_ranks_lifo2d(T: torch.Tensor, cost: torch.Tensor, seed, max_iters: int =
         t0.view(-1)[seed_idx] = -1                                # the source is final before anything pops
         RL, RR, RU, RD = _shift(r, 0, -1, _BIG), _shift(r, 0, 1, _BIG), _shift(r, -1, 0, _BIG), _shift(r, 1, 0, _BIG)
         AL, AR, AU, AD = _shift(t0, 0, -1, _BIG), _shift(t0, 0, 1, _BIG), _shift(t0, -1, 0, _BIG), _shift(t0, 1, 0, _BIG)
-        left = (TL < TR) | ((TL == TR) & (AL <= AR))
-        a, ta = torch.where(left, TL, TR), torch.where(left, AL, AR)
-        up = (TU < TD) | ((TU == TD) & (AU <= AD))
-        b, tb = torch.where(up, TU, TD), torch.where(up, AU, AD)
-        two = (a - b).abs() <= cost
-        ready = torch.where(two, torch.maximum(ta, tb), torch.where(a <= b, ta, tb))   # inputs final from here on
+        # insertion time = the earliest neighbour pop at which the update, fed only with neighbour values
+        # that are already final by then (the others count as +inf), reproduces the final value
+        limit = T * (1.0 + 1e-14)
         tau_new = torch.full_like(r, _BIG)
         cidx = torch.zeros_like(r)
+        inf_t = torch.full_like(T, INF)
         for R, ci in ((RL, 4), (RR, 3), (RU, 2), (RD, 1)):        # child index w.r.t. the popped neighbour
-            ok = (R >= ready) & (R < tau_new)
+            lt = torch.where(AL <= R, TL, inf_t)
+            rt = torch.where(AR <= R, TR, inf_t)
+            ut = torch.where(AU <= R, TU, inf_t)
+            dt = torch.where(AD <= R, TD, inf_t)
+            a, b = torch.minimum(lt, rt), torch.minimum(ut, dt)
+            dd = a - b
+            one = torch.minimum(a, b) + cost
+            two = 0.5 * (a + b + torch.sqrt((2.0 * (cost * cost) - dd * dd).clamp_min(0.0)))
+            v = torch.where(dd.abs() <= cost, two, one)
+            ok = (R < _BIG) & (R < tau_new) & (v <= limit)
             tau_new = torch.where(ok, R, tau_new)
             cidx = torch.where(ok, torch.full_like(r, ci), cidx)
         tau_new = torch.where(fin, tau_new, torch.full_like(tau_new, _BIG))

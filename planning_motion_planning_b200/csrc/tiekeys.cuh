@@ -33,16 +33,25 @@ __global__ void tie_keys2d_kernel(const double *T, const double *cost, const int
                 if (nb[i] == seed_idx) { rv[i] = 0; av[i] = -1; }
             }
         }
-        const bool left = (tv[0] < tv[1]) || (tv[0] == tv[1] && av[0] <= av[1]);
-        const double a = left ? tv[0] : tv[1]; const long long ta = left ? av[0] : av[1];
-        const bool up = (tv[2] < tv[3]) || (tv[2] == tv[3] && av[2] <= av[3]);
-        const double b = up ? tv[2] : tv[3]; const long long tb = up ? av[2] : av[3];
-        const bool two = fabs(a - b) <= cost[c];
-        const long long ready = two ? (ta > tb ? ta : tb) : (a <= b ? ta : tb);
+        // insertion time = the earliest neighbour pop at which the update, fed only with neighbour
+        // values that are already final by then (the others count as +inf), reproduces the final value
+        const double c_cost = cost[c];
+        const double limit = t * (1.0 + 1e-14);               // the solver's field is a fixed point to a few ulp
         long long best = BIG; int cidx = 0;
         const int ci[4] = {4, 3, 2, 1};          // popped neighbour left/right/up/down => my child index in its updateNode
 #pragma unroll
-        for (int i = 0; i < 4; ++i) if (rv[i] >= ready && rv[i] < best) { best = rv[i]; cidx = ci[i]; }
+        for (int i = 0; i < 4; ++i) {
+            const long long ti = rv[i];
+            if (ti >= BIG || ti >= best) continue;
+            const double l = av[0] <= ti ? tv[0] : INF, r = av[1] <= ti ? tv[1] : INF;
+            const double u = av[2] <= ti ? tv[2] : INF, d = av[3] <= ti ? tv[3] : INF;
+            const double a = l < r ? l : r, b = u < d ? u : d;
+            const double m = a < b ? a : b, dd = a - b;
+            double v;
+            if (!(fabs(dd) <= c_cost)) v = m + c_cost;
+            else v = 0.5 * (a + b + sqrt(2.0 * (c_cost * c_cost) - dd * dd));
+            if (v <= limit) { best = ti; cidx = ci[i]; }
+        }
         if (c == seed_idx) best = -1;
         tau_new[c] = (int)best;
         key[c] = ((long long)group[c] << 35) | ((long long)(0xffffffffLL - (unsigned long long)(best + 1)) << 3) | (long long)(7 - cidx);
