@@ -164,6 +164,25 @@ int fmb_tie_keys2d_f64(const double *d_T, const double *d_cost, const int32_t *d
                        const int32_t *d_group, int rows, int cols, int32_t seed_index,
                        int32_t *d_tau_new, int64_t *d_key, void *stream);
 
+/* ---- 2D cost-map construction (the step right before the 2D solve) --------
+ * Replaces Coupled_motion_planner.py:37-80 (surface_normal), :83-95 (image_filling), :97-109
+ * (structural_disk) and the inline pipeline of main() :1144-1216: slope obstacles from the DEM,
+ * hole filling, opening by a disk of r_open, dilate / fill / erode by r_close, distance band
+ * (dilation by r_expand x exact Euclidean distance), 1 + 300*obstacle + 10*band, 50x50 box blur
+ * with 300 outside, +inf map limits.
+ *   d_dem     n x n zero-based DEM (the planner's Zs after :1101), C order
+ *   d_grid    n doubles: np.linspace(0, size, n) (the meshgrid axis of :41-43)
+ *   d_cost    out, n x n in [y][x] order == what the planner passes to biComputeTmap (cMap.T, :1226)
+ *   d_obst_raw / d_obst / d_pre   optional outs: obstacle map after the first filling, final obstacle
+ *             map (uint8), cost before the blur ([y][x]); NULL to skip
+ * Asynchronous on `stream`; fmb_costmap2d_finish synchronises and returns the number of cells with a
+ * positive distance-band value (0 means the reference would raise ValueError at :1198). */
+size_t fmb_workspace_bytes_costmap2d(int n);
+int fmb_costmap2d_f64(const double *d_dem, const double *d_grid, int n, double resolution, double slope_max,
+                      int r_open, int r_close, int r_expand, double *d_cost, uint8_t *d_obst_raw, uint8_t *d_obst,
+                      double *d_pre, void *d_ws, size_t ws_bytes, void *stream);
+int fmb_costmap2d_finish(void *d_ws, size_t ws_bytes, void *stream, int32_t *n_positive);
+
 #ifdef __cplusplus
 }
 #endif

@@ -246,3 +246,4 @@ int fmb_trace2d_f64(const double *d_T, int64_t T_pitch, int64_t T_qstride, int r
 }  // extern "C"
 
 #include "fm_capi3d.inc"
+#include "fm_capi_costmap.inc"

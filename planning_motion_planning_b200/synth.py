@@ -121,3 +121,32 @@ def arm_volume(shape, seed=0, dtype=np.float64):
     c[start[1], start[0], start[2]] = 4.0
     c[goal[1], goal[0], goal[2]] = 4.0
     return c.astype(dtype), goal.tolist(), start.tolist()
+
+
+def crater_dem(n, resolution, seed=0, craters=None, rocks=None):
+    """Zero-based DEM (metres) with gentle 1/f-like undulation, steep-rimmed craters (ring
+    obstacles whose floors the planner's hole filling closes, Coupled_motion_planner.py:1164)
+    and small rocks (removed by the opening of :1167-1169 when thinner than 21 cells, kept
+    otherwise).  Shapes scale with ``resolution`` so the slope threshold 0.20 rad (:1154)
+    bites at any grid size."""
+    rng = np.random.default_rng(seed)
+    size = n * resolution
+    ax = (np.arange(n) + 0.5) * resolution
+    X, Y = np.meshgrid(ax, ax)
+    Z = np.zeros((n, n))
+    for k in range(1, 5):                                   # smooth relief, slope well below the threshold
+        ph = rng.random(4) * 2 * np.pi
+        Z += 0.02 * size / (3.0 * k * k) * np.sin(2 * np.pi * k * X / size + ph[0]) * np.cos(2 * np.pi * k * Y / size + ph[1])
+    craters = max(1, n // 96) if craters is None else craters
+    rocks = max(2, n // 32) if rocks is None else rocks
+    for _ in range(craters):
+        cx, cy = rng.uniform(0.15, 0.85, 2) * size
+        R = rng.uniform(0.05, 0.12) * size
+        d = np.hypot(X - cx, Y - cy)
+        w = 0.18 * R
+        Z += 0.6 * w * np.exp(-((d - R) / w) ** 2)          # raised rim: steep on both flanks, flat floor inside
+    for _ in range(rocks):
+        cx, cy = rng.uniform(0.05, 0.95, 2) * size
+        R = rng.uniform(4, 30) * resolution
+        Z += 0.8 * R * np.exp(-((X - cx) ** 2 + (Y - cy) ** 2) / (2 * (0.5 * R) ** 2))
+    return Z - Z.min()

@@ -114,3 +114,21 @@ def truncate(F, cost, k, rank=None):
         L.emu_truncate3d_f64.argtypes = [dp, dp, ip, C.c_int, C.c_int, C.c_int, C.c_int, dp]
         ov = L.emu_truncate3d_f64(F.ctypes.data_as(dp), cost.ctypes.data_as(dp), rank.ctypes.data_as(ip), *F.shape, int(k), out.ctypes.data_as(dp))
     return out, ov
+
+
+def costmap2d(Zs, resolution, size, diagonal=0.9):
+    """Emulated csrc/costmap2d.cuh pipeline; returns (cost [y,x], raw, obst, pre_blur [y,x], n_positive)."""
+    Zs = np.ascontiguousarray(Zs, dtype=np.float64)
+    n = Zs.shape[0]
+    grid = np.linspace(0, size, n)
+    cost, pre = np.empty((n, n)), np.empty((n, n))
+    raw, obst = np.empty((n, n), np.uint8), np.empty((n, n), np.uint8)
+    npos = C.c_int(0)
+    u8 = C.POINTER(C.c_ubyte)
+    fn = lib().emu_costmap2d_f64
+    fn.argtypes = [dp, dp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, dp, u8, u8, dp, ip]
+    rc = fn(Zs.ctypes.data_as(dp), grid.ctypes.data_as(dp), n, resolution, 0.20, 10, int(round(diagonal / 2 / resolution)),
+            int(round(1 / resolution)), cost.ctypes.data_as(dp), raw.ctypes.data_as(u8), obst.ctypes.data_as(u8),
+            pre.ctypes.data_as(dp), C.byref(npos))
+    assert rc == 0
+    return cost, raw, obst, pre, npos.value

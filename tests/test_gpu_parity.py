@@ -467,3 +467,94 @@ def test_dropin_errors():
         FM.biComputeTmap(c, [5, 5], [30, 30])
     with pytest.raises(IndexError):
         FM.biComputeTmap(c, [5, 5], [40, 3])
+
+
+# ---- 2D cost-map builder --------------------------------------------------
+def _box_sum_50(a, fill):
+    """Row sums over x-25..x+24 then column sums over y-25..y+24 (`fill` outside), added one tap at a
+    time in ascending order -- the kernel's own order, so the comparison is exact at any size (scipy's
+    2500-tap convolve2d takes minutes at 2048^2 and beyond)."""
+    n = a.shape[0]
+    p = np.pad(a, ((0, 0), (25, 24)), constant_values=fill)
+    h = np.zeros_like(a)
+    for u in range(50):
+        h = h + p[:, u:u + n]
+    p = np.pad(h, ((25, 24), (0, 0)), constant_values=50 * fill)
+    v = np.zeros_like(a)
+    for u in range(50):
+        v = v + p[u:u + n, :]
+    return v
+
+
+@pytest.mark.parametrize("kind,n,res,seed,sigma", [("planner", 200, 0.05, 0, None), ("craters", 512, 0.05, 1, None),
+                                                  ("rough", 384, 0.06, 2, 0.09), ("coarse", 300, 0.1, 4, 0.12)])
+def test_costmap2d_vs_oracle(kind, n, res, seed, sigma):
+    """csrc/costmap2d.cuh through the C ABI against the cv2/scipy restatement of
+    Coupled_motion_planner.py:1144-1216: obstacle maps and the pre-blur cost bit-exact, the
+    blurred map to 1e-12 (summation order), identical +inf limits."""
+    import torch
+    from oracle import costmap_oracle as CO
+    from planning_motion_planning_b200 import costmap, synth
+    if kind == "planner":
+        Z = CO.planner_dem(n, res)
+    else:
+        Z = synth.crater_dem(n, res, seed)
+        if sigma:
+            Z = Z + np.random.default_rng(seed + 100).normal(0.0, sigma * res, Z.shape)
+            Z = Z - Z.min()
+    c, st = CO.costmap2d(Z, res, n * res, stages=True)
+    cost, dv = costmap.build_costmap_device(torch.from_numpy(Z).cuda(), res, n * res, stages=True)
+    assert np.array_equal(dv["raw"].cpu().numpy(), st["raw"])
+    assert np.array_equal(dv["obst"].cpu().numpy(), st["obst"].astype(np.uint8))
+    assert np.array_equal(dv["pre_blur"].cpu().numpy(), st["pre_blur"].T)
+    got = cost.cpu().numpy().T
+    fin = np.isfinite(c)
+    assert np.array_equal(np.isfinite(got), fin)
+    assert np.max(np.abs(got[fin] - c[fin]) / c[fin]) < 1e-12
+    if kind == "planner":     # and against the unmodified planner's own array
+        d = np.load(os.path.join(GOLDEN, "planner_calls.npz"), allow_pickle=True)
+        ref = d["bi_cost"]
+        f2 = np.isfinite(ref)
+        assert np.max(np.abs(cost.cpu().numpy()[f2] - ref[f2]) / ref[f2]) < 1e-12
+        assert np.array_equal(costmap.build_costmap(Z, res, n * res), got)
+
+
+def test_costmap2d_2048_stages_exact_and_blur_property():
+    import torch
+    from oracle import costmap_oracle as CO
+    from planning_motion_planning_b200 import costmap, synth
+    n, res = 2048, 0.05
+    Z = synth.crater_dem(n, res, 1)
+    _, st = CO.costmap2d(Z, res, n * res, stages=True, blur=False)
+    cost, dv = costmap.build_costmap_device(torch.from_numpy(Z).cuda(), res, n * res, stages=True)
+    assert np.array_equal(dv["raw"].cpu().numpy(), st["raw"])
+    assert np.array_equal(dv["obst"].cpu().numpy(), st["obst"].astype(np.uint8))
+    pre = dv["pre_blur"].cpu().numpy()
+    assert np.array_equal(pre, st["pre_blur"].T)
+    want = _box_sum_50(pre, 300.0) * (1.0 / 2500.0)
+    got = cost.cpu().numpy()
+    inner = (slice(1, -1), slice(1, -1))
+    assert np.all(np.isinf(got[0])) and np.all(np.isinf(got[-1])) and np.all(np.isinf(got[:, 0])) and np.all(np.isinf(got[:, -1]))
+    assert np.array_equal(got[inner], want[inner])
+
+
+def test_costmap2d_feeds_the_solver_like_the_planner():
+    """DEM -> device cost map -> biComputeTmap: same join node and paths as the unmodified planner run."""
+    import FastMarching.FastMarching as FM
+    from oracle import costmap_oracle as CO
+    from planning_motion_planning_b200 import costmap
+    d = np.load(os.path.join(GOLDEN, "planner_calls.npz"), allow_pickle=True)
+    n, res = int(d["n"]), float(d["res"])
+    cMap = costmap.build_costmap(CO.planner_dem(n, res), res, n * res)
+    TG, TS, join = FM.biComputeTmap(cMap.T, [int(v) for v in d["bi_goal"]], [int(v) for v in d["bi_start"]])
+    assert np.array_equal(join, d["bi_join"])
+    pG = FM.getPathGDM(TG, join, [int(v) for v in d["bi_goal"]], 0.5)
+    assert pG.shape == d["pathG"].shape and np.max(np.abs(pG - d["pathG"])) < TOLP
+
+
+def test_costmap2d_all_obstacle_map_raises_valueerror():
+    import torch
+    from planning_motion_planning_b200 import costmap, synth
+    n, res = 96, 0.03
+    with pytest.raises(ValueError):
+        costmap.build_costmap_device(torch.from_numpy(synth.crater_dem(n, res, 3)).cuda(), res, n * res)

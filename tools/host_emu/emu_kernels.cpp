@@ -11,6 +11,7 @@
 #include "../../planning_motion_planning_b200/csrc/trace2d.cuh"
 #include "../../planning_motion_planning_b200/csrc/trace3d.cuh"
 #include "../../planning_motion_planning_b200/csrc/truncate.cuh"
+#include "../../planning_motion_planning_b200/csrc/costmap2d.cuh"
 
 namespace {
 unsigned pow2_at_least(long long v) { unsigned p = 1024; while ((long long)p < v) p <<= 1; return p; }
@@ -140,6 +141,48 @@ int emu_resolve2d_f64(const double *cost, double *T, int rows, int cols, const i
     emu::launch(1, 32, 0, [&] { fmb::init_seed2d_kernel<double, TW>(P); });
     emu::launch(nblocks, WARPS * 32, fmb::Tile2D<double, TW>::WARP_BYTES * WARPS, [&] { fmb::solve2d_kernel<double, TW, WARPS, false>(P); });
     return ctl.abort ? ctl.abort : (ctl.pending != 0 ? -1 : 0);
+}
+
+// the whole cost-map pipeline of fm_capi_costmap.inc, same kernel sequence (2 blocks x 64 threads)
+int emu_costmap2d_f64(const double *dem, const double *grid, int n, double resolution, double slope_max, int r_open,
+                      int r_close, int r_expand, double *cost, unsigned char *raw, unsigned char *obst, double *pre,
+                      int *n_positive) {
+    const size_t nn = (size_t)n * n;
+    std::vector<unsigned char> A(nn), B(nn);
+    std::vector<int> g(nn), lab(nn);
+    std::vector<double> tmp(nn), pre_own(nn);
+    fmb::CostmapCtl ctl;
+    const unsigned G = 2, T = 64;
+    auto fill = [&](unsigned char *im) {
+        emu::launch(G, T, 0, [&] { fmb::cm_runs_kernel(im, n, lab.data()); });
+        emu::launch(G, T, 0, [&] { fmb::cm_link_kernel(im, n, lab.data()); });
+        emu::launch(G, T, 0, [&] { fmb::cm_fill_apply_kernel(im, n, lab.data(), im); });
+    };
+    auto morph = [&](const unsigned char *src, unsigned char *dst, int r, bool dilate) {
+        emu::launch(G, T, 0, [&] { fmb::cm_vscan_bounded_kernel(src, dilate ? 1 : 0, n, r, g.data()); });
+        emu::launch(G, T, 0, [&] { fmb::cm_hscan_threshold_kernel(g.data(), n, r, dilate ? 1 : 0, dst); });
+    };
+    emu::launch(1, 32, 0, [&] { fmb::cm_init_ctl_kernel(&ctl); });
+    emu::launch(G, T, 0, [&] { fmb::cm_slope_kernel(dem, grid, n, slope_max, A.data()); });
+    fill(A.data());
+    if (raw) memcpy(raw, A.data(), nn);
+    morph(A.data(), B.data(), r_open, false);
+    morph(B.data(), A.data(), r_open, true);
+    morph(A.data(), B.data(), r_close, true);
+    fill(B.data());
+    morph(B.data(), A.data(), r_close, false);
+    emu::launch(1, 64, 0, [&] { fmb::cm_set_border_kernel(A.data(), n, 1); });
+    if (obst) memcpy(obst, A.data(), nn);
+    morph(A.data(), B.data(), r_expand, true);
+    emu::launch(1, 64, 0, [&] { fmb::cm_vscan_full_kernel(A.data(), 1, n, g.data()); });
+    emu::launch(G, T, 0, [&] { fmb::cm_hscan_exact_kernel(g.data(), n, lab.data(), &ctl); });
+    emu::launch(G, T, 0, [&] { fmb::cm_band_min_kernel(B.data(), lab.data(), n, resolution, &ctl); });
+    double *p = pre ? pre : pre_own.data();
+    emu::launch(G, T, 0, [&] { fmb::cm_compose_kernel(A.data(), B.data(), lab.data(), n, resolution, &ctl, p); });
+    emu::launch(G, T, 0, [&] { fmb::cm_blur_rows_kernel(p, n, tmp.data()); });
+    emu::launch(G, T, 0, [&] { fmb::cm_blur_cols_kernel(tmp.data(), n, cost); });
+    if (n_positive) *n_positive = ctl.n_positive;
+    return 0;
 }
 
 }  // extern "C"
