@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--no-batch", action="store_true", help="skip the batched-queries section")
     ap.add_argument("--batch-queries", type=int, default=4096, help="512^2 queries per GPU in the batched section")
     ap.add_argument("--no-3d", action="store_true", help="skip the 3D (arm-workspace volume) section")
+    ap.add_argument("--no-costmap", action="store_true", help="skip the cost-map construction section")
     ap.add_argument("--size3d", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -501,6 +502,41 @@ def own_arm(args):
                "evals_per_cell": s3d["evals"] / m3 ** 3, "path_rows": int(n3[0]), "path_status": int(st3[0])}
         del c3d, T3
 
+    # ---- the cost-map construction that precedes the 2D solve (DEM -> cost map)
+    cmap = None
+    if not args.no_costmap and rank == 0:
+        from planning_motion_planning_b200 import costmap, synth
+        res_c = 0.05
+        Zc = torch.from_numpy(synth.crater_dem(n, res_c, 1)).to(dev)
+        for _ in range(2):
+            cm = costmap.build_costmap_device(Zc, res_c, n * res_c)
+        cts = []
+        for _ in range(5):
+            e0.record()
+            cm = costmap.build_costmap_device(Zc, res_c, n * res_c, sync=False)
+            e1.record()
+            torch.cuda.synchronize()
+            cts.append(e0.elapsed_time(e1))
+        cms = float(np.median(cts))
+        cmap = {"workload": f"{n}x{n} crater DEM (seed 1, resolution {res_c}) -> planner cost map, 26 kernel launches",
+                "ms": cms, "cells_per_s": cells / (cms * 1e-3),
+                "roofline_frac": (2 * 8 * cells / (cms * 1e-3) / 1e9) / peak,
+                "algorithmic_bytes": "read DEM once + write cost once = 16 B per cell"}
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import costmap_oracle as CO
+            nc = 1024
+            Zs = synth.crater_dem(nc, res_c, 1)
+            t0 = time.perf_counter()
+            cref = CO.costmap2d(Zs, res_c, nc * res_c)
+            dtc = time.perf_counter() - t0
+            got = costmap.build_costmap_device(torch.from_numpy(Zs).to(dev), res_c, nc * res_c).cpu().numpy().T
+            finc = np.isfinite(cref)
+            cmap["cpu_reference"] = {"sample": f"{nc}x{nc} DEM through the cv2/scipy restatement of Coupled_motion_planner.py:1144-1216",
+                                     "seconds": dtc, "cells_per_s": nc * nc / dtc,
+                                     "parity_max_rel_err": float(np.max(np.abs(got[finc] - cref[finc]) / cref[finc])),
+                                     "same_inf_pattern": bool(np.array_equal(np.isfinite(got), finc))}
+        del Zc, cm
+
     # ---- CPU baseline beside it (rank 0, N == 1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -536,7 +572,7 @@ def own_arm(args):
             "breakdown_ms": {"init_fill": init_ms, "solve_kernel": solve_ms, "trace_kernel": trace_ms},
             "solver_stats": {k: stats[k] for k in ("tile_visits", "steps", "evals", "pushes", "cells_written")},
             "evals_per_cell": stats["evals"] / cells,
-            "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "batch": batch, "volume3d": vol,
+            "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "batch": batch, "volume3d": vol, "costmap2d": cmap,
             "gpu_launches": 4 * K, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

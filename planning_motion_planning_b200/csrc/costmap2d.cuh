@@ -153,16 +153,43 @@ __global__ void cm_hscan_threshold_kernel(const int *g, int n, int r, int on_hit
         out[i] = (unsigned char)(hit ? on_hit : 1 - on_hit);
     }
 }
-// unbounded vertical scan: one thread per column, down then up
-__global__ void cm_vscan_full_kernel(const unsigned char *im, int fv, int n, int *g) {
-    CM_GRID_STRIDE(x, (long long)n) {
-        int d = CM_FAR;
-        for (int y = 0; y < n; ++y) {
+// unbounded vertical scan in two kernels, one thread per (64-row segment, column):
+//   cm_vseg_kernel   first / last feature row of every segment (-1 = none);
+//   cm_vscan_full_kernel  nearest feature above / below the segment from those summaries (<= n/64
+//                    reads each way instead of a walk over rows), then one sweep down and one up.
+constexpr int CM_SEG = 64;
+__global__ void cm_vseg_kernel(const unsigned char *im, int fv, int n, int *seg_first, int *seg_last) {
+    const int nseg = (n + CM_SEG - 1) / CM_SEG;
+    CM_GRID_STRIDE(t, (long long)nseg * n) {
+        const int sgm = (int)(t / n), x = (int)(t - (long long)sgm * n);
+        const int y0 = sgm * CM_SEG, y1 = min(y0 + CM_SEG, n);
+        int first = -1, last = -1;
+        for (int y = y0; y < y1; ++y)
+            if (im[(long long)y * n + x] == fv) { if (first < 0) first = y; last = y; }
+        seg_first[t] = first;
+        seg_last[t] = last;
+    }
+}
+__global__ void cm_vscan_full_kernel(const unsigned char *im, int fv, int n, const int *seg_first, const int *seg_last, int *g) {
+    const int nseg = (n + CM_SEG - 1) / CM_SEG;
+    CM_GRID_STRIDE(t, (long long)nseg * n) {
+        const int sgm = (int)(t / n), x = (int)(t - (long long)sgm * n);
+        const int y0 = sgm * CM_SEG, y1 = min(y0 + CM_SEG, n);
+        int d = CM_FAR;                                   // distance from row y0 - 1 to the nearest feature above
+        for (int q = sgm - 1; q >= 0; --q) {
+            const int l = seg_last[(long long)q * n + x];
+            if (l >= 0) { d = y0 - 1 - l; break; }
+        }
+        for (int y = y0; y < y1; ++y) {
             d = im[(long long)y * n + x] == fv ? 0 : min(d + 1, CM_FAR);
             g[(long long)y * n + x] = d;
         }
-        d = CM_FAR;
-        for (int y = n - 1; y >= 0; --y) {
+        d = CM_FAR;                                       // distance from row y1 to the nearest feature below
+        for (int q = sgm + 1; q < nseg; ++q) {
+            const int f = seg_first[(long long)q * n + x];
+            if (f >= 0) { d = f - y1; break; }
+        }
+        for (int y = y1 - 1; y >= y0; --y) {
             d = im[(long long)y * n + x] == fv ? 0 : min(d + 1, CM_FAR);
             const long long i = (long long)y * n + x;
             if (d < g[i]) g[i] = d;
@@ -176,15 +203,26 @@ __global__ void cm_hscan_exact_kernel(const int *g, int n, int *d2, CostmapCtl *
         const int x = (int)(i % n);
         const int g0 = g[i];
         int best = g0 * g0;
-        for (int dx = 1; dx * dx < best; ++dx) {
-            if (x - dx >= 0) { const int gv = g[i - dx]; const int v = dx * dx + gv * gv; best = v < best ? v : best; }
-            if (x + dx < n) { const int gv = g[i + dx]; const int v = dx * dx + gv * gv; best = v < best ? v : best; }
-            if (x - dx < 0 && x + dx >= n) break;
+        // four offsets per round, all eight loads issued before `best` is touched; offsets past the
+        // stopping bound are still genuine candidates, so looking at them cannot change the minimum
+        for (int dx = 1; dx * dx < best && (x - dx >= 0 || x + dx < n); dx += 4) {
+            int cand[8];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = dx + u;
+                const int gl = x - e >= 0 ? g[i - e] : CM_FAR, gr = x + e < n ? g[i + e] : CM_FAR;
+                cand[2 * u] = e * e + gl * gl;
+                cand[2 * u + 1] = e * e + gr * gr;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) best = cand[u] < best ? cand[u] : best;
         }
         d2[i] = best;
         local_max = best > local_max ? best : local_max;
     }
-    if (local_max > 0) atomicMax(&ctl->d2max, local_max);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const int v = __shfl_xor_sync(FULL, local_max, o); local_max = v > local_max ? v : local_max; }
+    if ((threadIdx.x & 31) == 0 && local_max > 0) atomicMax(&ctl->d2max, local_max);
 }
 
 // ---- distance band, composition, blur (:1186-1216) -----------------------------------------------
@@ -209,7 +247,13 @@ __global__ void cm_band_min_kernel(const unsigned char *dil, const int *d2, int 
         const double v = cm_band(dil[i], d2[i], res, maxd);
         if (v > 0.0) { const unsigned long long b = (unsigned long long)__double_as_longlong(v); local = b < local ? b : local; ++cnt; }
     }
-    if (cnt) { atomicMin(&ctl->min_pos, local); atomicAdd(&ctl->n_positive, cnt); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long v = __shfl_xor_sync(FULL, local, o);
+        local = v < local ? v : local;
+        cnt += __shfl_xor_sync(FULL, cnt, o);
+    }
+    if ((threadIdx.x & 31) == 0 && cnt) { atomicMin(&ctl->min_pos, local); atomicAdd(&ctl->n_positive, cnt); }
 }
 // pre-blur cost in [y][x] order: 1 + (obst*300 + band*10)   (the reference holds its transpose)
 __global__ void cm_compose_kernel(const unsigned char *obst, const unsigned char *dil, const int *d2, int n, double res,
@@ -235,19 +279,35 @@ __global__ void cm_blur_rows_kernel(const double *pre, int n, double *tmp) {
         tmp[i] = s;
     }
 }
-// 50-tap column sums over y-25 .. y+24, scaled by 1/2500; map limits become +inf (:1210-1214)
+// 50-tap column sums over y-25 .. y+24, scaled by 1/2500; map limits become +inf (:1210-1214).
+// One thread produces CM_VB vertically adjacent outputs from one pass over the 49 + CM_VB rows they
+// share (each output still adds its taps in ascending order).
+constexpr int CM_VB = 8;
 __global__ void cm_blur_cols_kernel(const double *tmp, int n, double *out) {
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
-    CM_GRID_STRIDE(i, (long long)n * n) {
-        const int y = (int)(i / n), x = (int)(i - (long long)y * n);
-        double s = 0.0;
-#pragma unroll 10
-        for (int v = -25; v < 25; ++v) {
-            const int yy = y + v;
-            s = __dadd_rn(s, (yy >= 0 && yy < n) ? tmp[i + (long long)v * n] : 15000.0);
+    const int nyb = (n + CM_VB - 1) / CM_VB;
+    CM_GRID_STRIDE(t, (long long)nyb * n) {
+        const int yb = (int)(t / n), x = (int)(t - (long long)yb * n);
+        const int y0 = yb * CM_VB;
+        double s[CM_VB];
+#pragma unroll
+        for (int k = 0; k < CM_VB; ++k) s[k] = 0.0;
+#pragma unroll 2
+        for (int j = 0; j < 49 + CM_VB; ++j) {             // row y0 - 25 + j feeds output k as its tap j - k
+            const int yy = y0 - 25 + j;
+            const double v = (yy >= 0 && yy < n) ? tmp[(long long)yy * n + x] : 15000.0;
+#pragma unroll
+            for (int k = 0; k < CM_VB; ++k)
+                if (j - k >= 0 && j - k < 50) s[k] = __dadd_rn(s[k], v);
         }
-        const bool edge = y == 0 || x == 0 || y == n - 1 || x == n - 1;
-        out[i] = edge ? inf : __dmul_rn(s, 1.0 / 2500.0);
+#pragma unroll
+        for (int k = 0; k < CM_VB; ++k) {
+            const int y = y0 + k;
+            if (y < n) {
+                const bool edge = y == 0 || x == 0 || y == n - 1 || x == n - 1;
+                out[(long long)y * n + x] = edge ? inf : __dmul_rn(s[k], 1.0 / 2500.0);
+            }
+        }
     }
 }
 

@@ -174,7 +174,9 @@ int emu_costmap2d_f64(const double *dem, const double *grid, int n, double resol
     emu::launch(1, 64, 0, [&] { fmb::cm_set_border_kernel(A.data(), n, 1); });
     if (obst) memcpy(obst, A.data(), nn);
     morph(A.data(), B.data(), r_expand, true);
-    emu::launch(1, 64, 0, [&] { fmb::cm_vscan_full_kernel(A.data(), 1, n, g.data()); });
+    std::vector<int> seg_first((size_t)((n + fmb::CM_SEG - 1) / fmb::CM_SEG) * n), seg_last(seg_first.size());
+    emu::launch(G, T, 0, [&] { fmb::cm_vseg_kernel(A.data(), 1, n, seg_first.data(), seg_last.data()); });
+    emu::launch(G, T, 0, [&] { fmb::cm_vscan_full_kernel(A.data(), 1, n, seg_first.data(), seg_last.data(), g.data()); });
     emu::launch(G, T, 0, [&] { fmb::cm_hscan_exact_kernel(g.data(), n, lab.data(), &ctl); });
     emu::launch(G, T, 0, [&] { fmb::cm_band_min_kernel(B.data(), lab.data(), n, resolution, &ctl); });
     double *p = pre ? pre : pre_own.data();
