@@ -183,6 +183,36 @@ int fmb_costmap2d_f64(const double *d_dem, const double *d_grid, int n, double r
                       double *d_pre, void *d_ws, size_t ws_bytes, void *stream);
 int fmb_costmap2d_finish(void *d_ws, size_t ws_bytes, void *stream, int32_t *n_positive);
 
+/* ---- 3D arm-workspace cost volume (feeds fmb_solve3d) ----------------------
+ * Replaces GetObstMap (Coupled_motion_planner.py:319-358), TunnelCost (:505-725) and the product
+ * Cmap1*Cmap2 (:1627).  The host wrapper prepares the small tables with the reference's scalar
+ * expressions; the device resolves the order-dependent scatter ("first writer wins", +inf always
+ * wins) with sequence numbers and writes the volumes.  All pointers are device pointers.
+ *   d_Zs        DEM crop, zs_rows x zs_cols (the planner's ZsMap, :1523-1526)
+ *   d_frames    (npose + 1) x 12 doubles: rows 0..2 of the base frame Toa per pose (:530-533), then
+ *               the frame of the closing half sphere (:661-664)
+ *   d_li, d_lk  np.linspace(-R, R, nX / nZ) of the tube cross-section (:546-547), R = rlim + 2 resX
+ *   d_norm, d_val  nX x nZ tables: sqrt(i**2 + k**2) (:560) and the graded cost (:573)
+ *   d_lr, d_hval   nK radii of the half sphere (:676) and their cost (:697)
+ *   d_angles    cos(theta)[100], sin(theta)[100], cos(sigma)[90], sin(sigma)[90] (:668-681)
+ *   fin / ini   sample node and initial end-effector node [x, y, z] (never blocked, :576, :641, :720)
+ * Outputs (any may be NULL): d_cmap = terrain * tunnel, d_tunnel (TunnelCost's Cmap, shape sY x sX x sZ),
+ * d_terrain (GetObstMap's finalMap, shape sX x sY x sZ).  Asynchronous on `stream`. */
+typedef struct fmb_costvolume_desc {
+    const double *d_Zs; int32_t zs_rows, zs_cols;
+    double resX, resY, resZ, xm, ym;
+    int32_t sX, sY, sZ;
+    const double *d_frames; int32_t npose;
+    const double *d_li, *d_lk; int32_t nX, nZ;
+    const double *d_norm, *d_val; double rlim;
+    const double *d_lr, *d_hval; int32_t nK;
+    const double *d_angles; double shell;
+    int64_t fin[3], ini[3];
+} fmb_costvolume_desc;
+size_t fmb_workspace_bytes_costvolume(int sX, int sY, int sZ);
+int fmb_costvolume_f64(const fmb_costvolume_desc *desc, double *d_cmap, double *d_tunnel, double *d_terrain,
+                       void *d_ws, size_t ws_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -218,10 +218,94 @@ def gen_planner(n=200, res=0.05):
           "3D", out.get("c3", np.zeros(0)).shape, "size %.0f kB" % (os.path.getsize(os.path.join(OUT, "planner_calls.npz")) / 1e3))
 
 
+def gen_costvolume(n=200, res=0.05):
+    """3D cost-volume builder: arguments and results of the UNMODIFIED
+    GetObstMap / TunnelCost (Coupled_motion_planner.py:319, :505) as called by the unmodified
+    planner main() on the synthetic DEM of gen_planner, plus seeded direct calls of the same
+    functions with rolled / pitched base frames.  The C restatement (oracle/costvol_oracle.c) must
+    give the same bits before anything is written."""
+    import importlib
+    from oracle import costvol as CV
+    sys.path.insert(0, R.REF_SRC)
+    sys.dont_write_bytecode = True
+    for k in [k for k in sys.modules if k == "FastMarching" or k.startswith("FastMarching.")]:
+        del sys.modules[k]
+    cmp_ = importlib.import_module("Coupled_motion_planner")
+    rec = {}
+
+    def wrap(fname):
+        orig = getattr(cmp_, fname)
+
+        def f(*a):
+            r = orig(*a)
+            rec[fname] = (a, r)
+            return r
+        setattr(cmp_, fname, f)
+        return orig
+    o1, o2 = wrap("GetObstMap"), wrap("TunnelCost")
+    size = n * res
+    ax = (np.arange(n) + 0.5) * res
+    X, Y = np.meshgrid(ax, ax)
+    Z = 0.03 * np.sin(2 * np.pi * X / (0.5 * size)) * np.cos(2 * np.pi * Y / (0.7 * size))
+    Z += 0.5 * np.exp(-((X - 0.5 * size) ** 2 + (Y - 0.45 * size) ** 2) / (2 * (0.06 * size) ** 2))
+    d = tempfile.mkdtemp()
+    with open(os.path.join(d, "PRL_DEM.txt"), "w") as f:
+        for row in Z:
+            f.write(",".join(repr(float(v)) for v in row) + "\n")
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            cmp_.main(0.8 * size, 0.8 * size, 0.2 * size, 0.2 * size, 0.0, d + "/", res, size)
+    except Exception as e:
+        print("planner main() raised after the builders:", type(e).__name__)
+    cmp_.GetObstMap, cmp_.TunnelCost = o1, o2
+    out = {}
+    (Zs, resX, resY, resZ, sX, sY, sZ, ob, xm, ym), (final, _, _) = rec["GetObstMap"]
+    out.update(p_Zs=np.asarray(Zs), p_res=np.array([resX, resY, resZ]), p_shape=np.array([sX, sY, sZ]),
+               p_obst=np.asarray(ob), p_xm_ym=np.array([xm, ym]), p_final=final)
+    same(CV.GetObstMap(Zs, resX, resY, resZ, sX, sY, sZ, ob, xm, ym), final, "planner GetObstMap")
+    (rlim, rO, rm, g2, sX, sY, sZ, resX, resY, resZ, head, fin, ini), cm2 = rec["TunnelCost"]
+    out.update(p_radii=np.array([rlim, rO, rm]), p_path=np.asarray(g2), p_heading=np.asarray(head),
+               p_fin=np.asarray(fin, dtype=np.int64), p_ini=np.asarray(ini, dtype=np.int64), p_tunnel=cm2)
+    same(CV.TunnelCost(rlim, rO, rm, g2, sX, sY, sZ, resX, resY, resZ, head, fin, ini), cm2, "planner TunnelCost")
+    print("planner volume", (sX, sY, sZ), "tunnel cells", int((cm2 != 10).sum()), "path points", len(g2))
+    for s in range(2):                                  # direct calls, tilted frames
+        rng = np.random.default_rng(40 + s)
+        sX = sY = 36 + 8 * s
+        sZ, m = 26 + 6 * s, 9 + 4 * s
+        resX = resY = 0.02 * rng.uniform(0.9, 1.1)
+        resZ = 0.02
+        Zs = 0.1 + 0.05 * rng.random((sX, sY))
+        ob = (rng.random((sX, sY)) < 0.1).astype(float)
+        xm, ym = resX * 7, resY * 9
+        final = cmp_.GetObstMap(Zs, resX, resY, resZ, sX, sY, sZ, ob, xm, ym)[0]
+        same(CV.GetObstMap(Zs, resX, resY, resZ, sX, sY, sZ, ob, xm, ym), final, f"direct GetObstMap {s}")
+        path = np.stack([np.linspace(0.2, 0.6, m) * sX * resX, np.linspace(0.3, 0.5, m) * sY * resY,
+                         0.3 + 0.02 * rng.random(m)], axis=1)
+        head = np.stack([0.15 * rng.normal(size=m), 0.15 * rng.normal(size=m),
+                         rng.uniform(-1, 1) + 0.05 * np.arange(m)], axis=1)
+        fin, ini = np.uint32([sX // 2, sY // 2, 5]), np.uint32([sX // 3, sY // 3, 12])
+        rlim, rO, rm = 0.2, 0.12, 0.05
+        cm2 = cmp_.TunnelCost(rlim, rO, rm, path, sX, sY, sZ, resX, resY, resZ, head, fin, ini)
+        same(CV.TunnelCost(rlim, rO, rm, path, sX, sY, sZ, resX, resY, resZ, head, fin, ini), cm2, f"direct TunnelCost {s}")
+        out.update({f"d{s}_Zs": Zs, f"d{s}_res": np.array([resX, resY, resZ]), f"d{s}_shape": np.array([sX, sY, sZ]),
+                    f"d{s}_obst": ob, f"d{s}_xm_ym": np.array([xm, ym]), f"d{s}_final": final,
+                    f"d{s}_radii": np.array([rlim, rO, rm]), f"d{s}_path": path, f"d{s}_heading": head,
+                    f"d{s}_fin": fin.astype(np.int64), f"d{s}_ini": ini.astype(np.int64), f"d{s}_tunnel": cm2})
+    np.savez_compressed(os.path.join(OUT, "costvolume.npz"), **out)
+    print("costvolume.npz: %.0f kB" % (os.path.getsize(os.path.join(OUT, "costvolume.npz")) / 1e3))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     if not R.available():
         raise SystemExit("reference tree not found: run this in the build container")
-    gen_2d()
-    gen_3d()
-    gen_planner()
+    which = sys.argv[1:] or ["2d", "3d", "planner", "costvolume"]
+    if "2d" in which:
+        gen_2d()
+    if "3d" in which:
+        gen_3d()
+    if "planner" in which:
+        gen_planner()
+    if "costvolume" in which:
+        gen_costvolume()

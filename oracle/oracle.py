@@ -23,8 +23,8 @@ TRACE_OK, TRACE_EARLY, TRACE_VALUEERROR, TRACE_INDEXERROR, TRACE_OVERFLOW = 0, 1
 
 def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "liboracle.so")
-    src = os.path.join(_HERE, "fmm_oracle.c")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("fmm_oracle.c", "costvol_oracle.c", "Makefile")]
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-s", "-C", _HERE, "-B", "liboracle.so"])
     return so
 

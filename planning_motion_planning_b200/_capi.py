@@ -59,6 +59,8 @@ SIGNATURES = {
     "fmb_workspace_bytes_costmap2d": (_sz, [_i32]),
     "fmb_costmap2d_f64": (C.c_int, [_vp, _vp, _i32, _dbl, _dbl, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "fmb_costmap2d_finish": (C.c_int, [_vp, _sz, _vp, C.POINTER(C.c_int32)]),
+    "fmb_workspace_bytes_costvolume": (_sz, [_i32, _i32, _i32]),
+    "fmb_costvolume_f64": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _sz, _vp]),
 }
 
 

@@ -132,3 +132,29 @@ def costmap2d(Zs, resolution, size, diagonal=0.9):
             pre.ctypes.data_as(dp), C.byref(npos))
     assert rc == 0
     return cost, raw, obst, pre, npos.value
+
+
+def costvolume(Zs, resX, resY, resZ, sX, sY, sZ, xm, ym, rlim, rO, rm, gamma2D, heading, fin, ini):
+    """Emulated csrc/costvolume.cuh; the small host tables come from the product wrapper
+    (planning_motion_planning_b200.costvolume._tables).  Returns (cmap, tunnel, terrain)."""
+    from planning_motion_planning_b200 import costvolume as CVP
+    tun = CVP._tables(rlim, rO, rm, np.asarray(gamma2D, dtype=np.float64), resX, resZ, np.asarray(heading, dtype=np.float64))
+    keep = {k: np.ascontiguousarray(tun[k], dtype=np.float64) for k in ("frames", "li", "lk", "norm", "val", "lr", "hval", "angles")}
+    Zs = np.ascontiguousarray(Zs, dtype=np.float64)
+    d = CVP._Desc()
+    d.d_Zs, d.zs_rows, d.zs_cols = Zs.ctypes.data, Zs.shape[0], Zs.shape[1]
+    d.resX, d.resY, d.resZ, d.xm, d.ym = resX, resY, resZ, xm, ym
+    d.sX, d.sY, d.sZ = sX, sY, sZ
+    for name, key in (("d_frames", "frames"), ("d_li", "li"), ("d_lk", "lk"), ("d_norm", "norm"), ("d_val", "val"),
+                      ("d_lr", "lr"), ("d_hval", "hval"), ("d_angles", "angles")):
+        setattr(d, name, keep[key].ctypes.data)
+    d.npose, d.nX, d.nZ, d.nK = keep["frames"].shape[0] - 1, tun["nX"], tun["nZ"], len(keep["lr"])
+    d.rlim, d.shell = rlim, tun["shell"]
+    for k in range(3):
+        d.fin[k], d.ini[k] = int(fin[k]), int(ini[k])
+    cells = sX * sY * sZ
+    cmap, tunnel, terrain = np.empty(cells), np.empty(cells), np.empty(cells)
+    fn = lib().emu_costvolume_f64
+    fn.argtypes = [C.c_void_p, dp, dp, dp]
+    assert fn(C.byref(d), cmap.ctypes.data_as(dp), tunnel.ctypes.data_as(dp), terrain.ctypes.data_as(dp)) == 0
+    return cmap.reshape(sX, sY, sZ), tunnel.reshape(sY, sX, sZ), terrain.reshape(sX, sY, sZ)

@@ -558,3 +558,70 @@ def test_costmap2d_all_obstacle_map_raises_valueerror():
     n, res = 96, 0.03
     with pytest.raises(ValueError):
         costmap.build_costmap_device(torch.from_numpy(synth.crater_dem(n, res, 3)).cuda(), res, n * res)
+
+
+# ---- 3D cost-volume builder ------------------------------------------------
+def _cv_cases():
+    d = np.load(os.path.join(GOLDEN, "costvolume.npz"))
+    out = {}
+    for tag in ("p", "d0", "d1"):
+        g = lambda k: d[f"{tag}_{k}"]      # noqa: E731
+        out[tag] = dict(Zs=g("Zs"), res=[float(v) for v in g("res")], shape=[int(v) for v in g("shape")], obst=g("obst"),
+                        xm_ym=[float(v) for v in g("xm_ym")], final=g("final"), radii=[float(v) for v in g("radii")],
+                        path=g("path"), heading=g("heading"), fin=g("fin"), ini=g("ini"), tunnel=g("tunnel"))
+    return out
+
+
+@pytest.mark.parametrize("tag", ["p", "d0", "d1"])
+def test_costvolume_vs_golden(tag):
+    """csrc/costvolume.cuh through the C ABI, called with the reference's own function signatures,
+    against arrays captured from the unmodified GetObstMap / TunnelCost: bit-exact."""
+    from planning_motion_planning_b200 import costvolume as CVP
+    c = _cv_cases()[tag]
+    (rx, ry, rz), (sX, sY, sZ) = c["res"], c["shape"]
+    final, obst, ground = CVP.GetObstMap(c["Zs"], rx, ry, rz, sX, sY, sZ, c["obst"], *c["xm_ym"])
+    assert np.array_equal(final, c["final"])
+    inner = (slice(1, -1),) * 3
+    assert np.array_equal((obst + ground)[inner], c["final"][inner])
+    assert not np.any(np.isinf(obst) & np.isinf(ground))
+    tunnel = CVP.TunnelCost(*c["radii"], c["path"], sX, sY, sZ, rx, ry, rz, c["heading"], c["fin"], c["ini"])
+    assert np.array_equal(tunnel, c["tunnel"])
+    cmap = CVP.build_cost_volume(c["Zs"], rx, ry, rz, sX, sY, sZ, *c["xm_ym"], *c["radii"], c["path"], c["heading"], c["fin"], c["ini"])
+    assert np.array_equal(cmap, c["final"] * c["tunnel"])
+
+
+def test_costvolume_feeds_the_3d_solver_like_the_planner(eng):
+    """DEM crop + base path -> device cost volume -> 3D solve + path == the planner's own volume and path."""
+    import FastMarching.FastMarching3D as FM3D
+    from planning_motion_planning_b200 import costvolume as CVP
+    p = np.load(os.path.join(GOLDEN, "planner_calls.npz"), allow_pickle=True)
+    c = _cv_cases()["p"]
+    (rx, ry, rz), (sX, sY, sZ) = c["res"], c["shape"]
+    vol = CVP.build_cost_volume_device(c["Zs"], rx, ry, rz, sX, sY, sZ, *c["xm_ym"], *c["radii"], c["path"], c["heading"],
+                                       c["fin"], c["ini"])
+    assert np.array_equal(vol.cpu().numpy(), p["c3"])
+    T = FM3D.computeTmap(vol.cpu().numpy(), np.uint32(p["g3"]), np.uint32(p["s3"]))
+    path = FM3D.getPathGDM(T, np.uint32(p["path3d_init"]), np.uint32(p["path3d_end"]), float(p["path3d_tau"]))
+    assert path.shape == p["path3d"].shape and np.max(np.abs(path - p["path3d"])) < TOLP
+
+
+def test_costvolume_large_vs_oracle():
+    """A 160^3 volume with a long, banking base path (2 x 10^6 scatter events) against the C restatement."""
+    from oracle import costvol as CV
+    from planning_motion_planning_b200 import costvolume as CVP
+    rng = np.random.default_rng(5)
+    sX = sY = sZ = 160
+    rx = ry = 0.0125
+    rz = 0.02
+    m = 120
+    Zs = 0.2 + 0.1 * rng.random((sX, sY))
+    s = np.linspace(0, 1, m)
+    path = np.stack([(0.2 + 0.6 * s) * sX * rx, (0.3 + 0.4 * s ** 2) * sY * ry, 1.2 + 0.3 * np.sin(3 * s)], axis=1)
+    head = np.stack([0.2 * np.sin(5 * s), 0.15 * np.cos(4 * s), 0.3 + 1.2 * s], axis=1)
+    fin, ini = np.uint32([120, 90, 70]), np.uint32([40, 50, 65])
+    rad = (0.527, 0.2673, 0.1105)
+    want = CV.GetObstMap(Zs, rx, ry, rz, sX, sY, sZ, np.zeros((sX, sY)), 0.3, 0.4) * \
+        CV.TunnelCost(*rad, path, sX, sY, sZ, rx, ry, rz, head, fin, ini)
+    got = CVP.build_cost_volume(Zs, rx, ry, rz, sX, sY, sZ, 0.3, 0.4, *rad, path, head, fin, ini)
+    assert np.array_equal(got, want)
+    assert 0.02 < np.mean((want != 20) & np.isfinite(want)) < 0.6        # the tunnel is really there

@@ -12,6 +12,8 @@
 #include "../../planning_motion_planning_b200/csrc/trace3d.cuh"
 #include "../../planning_motion_planning_b200/csrc/truncate.cuh"
 #include "../../planning_motion_planning_b200/csrc/costmap2d.cuh"
+#include "../../planning_motion_planning_b200/csrc/costvolume.cuh"
+#include "../../include/fm_b200.h"
 
 namespace {
 unsigned pow2_at_least(long long v) { unsigned p = 1024; while ((long long)p < v) p <<= 1; return p; }
@@ -184,6 +186,30 @@ int emu_costmap2d_f64(const double *dem, const double *grid, int n, double resol
     emu::launch(G, T, 0, [&] { fmb::cm_blur_rows_kernel(p, n, tmp.data()); });
     emu::launch(G, T, 0, [&] { fmb::cm_blur_cols_kernel(tmp.data(), n, cost); });
     if (n_positive) *n_positive = ctl.n_positive;
+    return 0;
+}
+
+// csrc/costvolume.cuh with host pointers in the descriptor (same kernel sequence as fmb_costvolume_f64)
+int emu_costvolume_f64(const fmb_costvolume_desc *d, double *cmap, double *tunnel, double *terrain) {
+    const size_t cells = (size_t)d->sX * d->sY * d->sZ;
+    std::vector<int> first(cells);
+    std::vector<unsigned char> blocked(cells);
+    fmb::CostVolumeArgs A;
+    A.Zs = d->d_Zs; A.zm = d->zs_rows; A.zn = d->zs_cols;
+    A.resX = d->resX; A.resY = d->resY; A.resZ = d->resZ; A.xm = d->xm; A.ym = d->ym;
+    A.sX = d->sX; A.sY = d->sY; A.sZ = d->sZ;
+    A.frames = d->d_frames; A.npose = d->npose;
+    A.li = d->d_li; A.lk = d->d_lk; A.nX = d->nX; A.nZ = d->nZ;
+    A.norm = d->d_norm; A.val = d->d_val; A.rlim = d->rlim;
+    A.lr = d->d_lr; A.hval = d->d_hval; A.nK = d->nK;
+    A.ct = d->d_angles; A.st = d->d_angles + 100; A.cs = d->d_angles + 200; A.ss = d->d_angles + 290;
+    A.shell = d->shell;
+    for (int k = 0; k < 3; ++k) { A.fin[k] = d->fin[k]; A.ini[k] = d->ini[k]; }
+    A.first = first.data(); A.blocked = blocked.data();
+    A.cmap = cmap; A.tunnel = tunnel; A.terrain = terrain;
+    emu::launch(2, 64, 0, [&] { fmb::cv_init_kernel(A); });
+    emu::launch(2, 64, 0, [&] { fmb::cv_scatter_kernel(A); });
+    emu::launch(2, 64, 0, [&] { fmb::cv_compose_kernel(A); });
     return 0;
 }
 
