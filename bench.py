@@ -537,6 +537,44 @@ def own_arm(args):
                                      "same_inf_pattern": bool(np.array_equal(np.isfinite(got), finc))}
         del Zc, cm
 
+    # ---- the 3D cost-volume construction that precedes the 3D solve
+    cvol = None
+    if not args.no_costmap and rank == 0:
+        from planning_motion_planning_b200 import costvolume as CVP
+        sv = args.size3d
+        rxy, rz = 2.0 / sv, 0.02
+        rngv = np.random.default_rng(5)
+        Zv = 0.2 + 0.1 * rngv.random((sv, sv))
+        mpose = 200
+        sp = np.linspace(0, 1, mpose)
+        pathv = np.stack([(0.2 + 0.6 * sp) * sv * rxy, (0.3 + 0.4 * sp ** 2) * sv * rxy, 0.4 * sv * rz + 0.3 * np.sin(3 * sp)], axis=1)
+        headv = np.stack([0.2 * np.sin(5 * sp), 0.15 * np.cos(4 * sp), 0.3 + 1.2 * sp], axis=1)
+        finv, iniv = np.uint32([int(0.75 * sv), int(0.6 * sv), int(0.4 * sv)]), np.uint32([int(0.25 * sv), int(0.3 * sv), int(0.4 * sv)])
+        cv_args = (Zv, rxy, rxy, rz, sv, sv, sv, 0.3, 0.4, 0.527, 0.2673, 0.1105, pathv, headv, finv, iniv)
+        t0 = time.perf_counter()
+        tun = CVP._tables(0.527, 0.2673, 0.1105, pathv, rxy, rz, headv)
+        host_ms = 1e3 * (time.perf_counter() - t0)
+        for _ in range(2):
+            volume = CVP.build_cost_volume_device(*cv_args)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        volume = CVP.build_cost_volume_device(*cv_args)
+        torch.cuda.synchronize()
+        call_ms = 1e3 * (time.perf_counter() - t0)
+        events = 2 * mpose * tun["nX"] * tun["nZ"] + tun["nX"] * tun["nZ"] + 9000 * (len(tun["lr"]) + 1)
+        cvol = {"workload": f"{sv}^3 volume, {mpose} base poses, {events} scatter events (GetObstMap + TunnelCost + product)",
+                "call_ms_incl_host_tables_and_uploads": call_ms, "host_tables_ms": host_ms,
+                "tunnel_voxels": int(((volume != 20) & torch.isfinite(volume)).sum())}
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import costvol as CVO
+            t0 = time.perf_counter()
+            want = CVO.GetObstMap(Zv, rxy, rxy, rz, sv, sv, sv, np.zeros((sv, sv)), 0.3, 0.4) * \
+                CVO.TunnelCost(0.527, 0.2673, 0.1105, pathv, sv, sv, sv, rxy, rxy, rz, headv, finv, iniv)
+            cvol["cpu_port_ms"] = 1e3 * (time.perf_counter() - t0)
+            cvol["bit_exact_vs_cpu_port"] = bool(np.array_equal(volume.cpu().numpy(), want))
+            cvol["reference_note"] = "the Python reference needs 2.4 s for 12 poses at 40^3 (measured, oracle/gen_golden.py)"
+        del volume
+
     # ---- CPU baseline beside it (rank 0, N == 1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -572,7 +610,7 @@ def own_arm(args):
             "breakdown_ms": {"init_fill": init_ms, "solve_kernel": solve_ms, "trace_kernel": trace_ms},
             "solver_stats": {k: stats[k] for k in ("tile_visits", "steps", "evals", "pushes", "cells_written")},
             "evals_per_cell": stats["evals"] / cells,
-            "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "batch": batch, "volume3d": vol, "costmap2d": cmap,
+            "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "batch": batch, "volume3d": vol, "costmap2d": cmap, "costvolume3d": cvol,
             "gpu_launches": 4 * K, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
