@@ -161,8 +161,10 @@ def pop_ranks_lifo2d(T: torch.Tensor, cost: torch.Tensor, seed, max_iters: int =
 
 
 def _pop_ranks_lifo2d_cuda(T, cost, seed_idx: int, max_iters: int) -> torch.Tensor:
-    """Device path of :func:`pop_ranks_lifo2d`: the per-cell step is one kernel of libfm_b200
-    (csrc/tiekeys.cuh) and one stable sort of its packed key per iteration."""
+    """Device path of :func:`pop_ranks_lifo2d`.  One sort of T up front gives the tie groups; every
+    iteration is then two small kernels of libfm_b200 (csrc/tiekeys.cuh): the per-cell key step and
+    the re-ranking inside each tie group (the global stable sort of the keys only permutes cells
+    within a group).  The convergence flag is polled every eighth iteration."""
     H, W = T.shape
     n = H * W
     dev = T.device
@@ -170,12 +172,49 @@ def _pop_ranks_lifo2d_cuda(T, cost, seed_idx: int, max_iters: int) -> torch.Tens
     fin = torch.isfinite(flat)
     order = torch.sort(flat, stable=True).indices
     ts = flat[order]
-    grp_sorted = torch.cumsum(torch.cat([torch.zeros(1, dtype=torch.int32, device=dev), (ts[1:] != ts[:-1]).to(torch.int32)]), 0)
+    new_grp = torch.cat([torch.ones(1, dtype=torch.bool, device=dev), ts[1:] != ts[:-1]])
+    grp_sorted = torch.cumsum(new_grp.to(torch.int32), 0) - 1
+    starts = torch.nonzero(new_grp).reshape(-1).to(torch.int32)                 # first sorted position of each group
+    sizes = torch.diff(torch.cat([starts, torch.tensor([n], dtype=torch.int32, device=dev)]))
     group = torch.empty(n, dtype=torch.int32, device=dev)
     group[order] = grp_sorted.to(torch.int32)
-    ar = torch.arange(n, dtype=torch.int32, device=dev)
+    gstart = starts[group.long()].contiguous()
+    gsize = torch.where(fin, sizes[group.long()], torch.ones_like(group)).to(torch.int32).contiguous()   # unreached cells: no re-ranking
+    members = order.to(torch.int32).contiguous()
     rank = torch.empty(n, dtype=torch.int32, device=dev)
-    rank[order] = ar
+    rank[order] = torch.arange(n, dtype=torch.int32, device=dev)
+    if int(gsize.max()) > 4096:           # a degenerate map: the quadratic in-group count would dominate
+        return _pop_ranks_lifo2d_sort(T, cost, seed_idx, max_iters, group, rank)
+    tau = rank.clone()
+    tau_new = torch.empty_like(tau)
+    rank_new = torch.empty_like(rank)
+    key = torch.empty(n, dtype=torch.int64, device=dev)
+    changed = torch.zeros(1, dtype=torch.int32, device=dev)
+    L = _capi.lib()
+    stream = torch.cuda.current_stream().cuda_stream
+    for it in range(max_iters):
+        _capi.check(L.fmb_tie_keys2d_f64(T.data_ptr(), cost.data_ptr(), rank.data_ptr(), tau.data_ptr(), group.data_ptr(),
+                                         H, W, seed_idx, tau_new.data_ptr(), key.data_ptr(), stream))
+        _capi.check(L.fmb_tie_rerank(key.data_ptr(), members.data_ptr(), gstart.data_ptr(), gsize.data_ptr(), rank.data_ptr(),
+                                     tau.data_ptr(), tau_new.data_ptr(), n, rank_new.data_ptr(), changed.data_ptr(), stream))
+        rank, rank_new = rank_new, rank
+        tau, tau_new = tau_new, tau
+        if (it & 7) == 7:                 # the flag covers the last eight steps: all quiet = fixed point
+            if int(changed.item()) == 0:
+                break
+            changed.zero_()
+    out = rank.clone()
+    out[~fin] = torch.iinfo(torch.int32).max
+    return out.reshape(H, W)
+
+
+def _pop_ranks_lifo2d_sort(T, cost, seed_idx: int, max_iters: int, group, rank) -> torch.Tensor:
+    """Fallback of the device path for maps with a huge tie group: one global stable sort per step."""
+    H, W = T.shape
+    n = H * W
+    dev = T.device
+    fin = torch.isfinite(T.reshape(-1))
+    ar = torch.arange(n, dtype=torch.int32, device=dev)
     tau = rank.clone()
     tau_new = torch.empty_like(tau)
     key = torch.empty(n, dtype=torch.int64, device=dev)
@@ -206,13 +245,14 @@ def truncate(T: torch.Tensor, cost: torch.Tensor, rank: torch.Tensor, k: int) ->
     out = torch.empty_like(T)
     scratch = torch.empty(T.numel(), dtype=torch.int32, device=T.device)      # compacted narrow-band cells
     counters = torch.zeros(2, dtype=torch.int32, device=T.device)
+    memo = torch.empty(T.numel() * (4 if T.dim() == 2 else 6), dtype=torch.float64, device=T.device)   # shared replay memo
     L = _capi.lib()
     stream = torch.cuda.current_stream().cuda_stream
     if T.dim() == 2:
         rc = L.fmb_truncate2d_f64(T.data_ptr(), cost.data_ptr(), rank.data_ptr(), T.shape[0], T.shape[1], int(k),
-                                  out.data_ptr(), scratch.data_ptr(), counters.data_ptr(), stream)
+                                  out.data_ptr(), scratch.data_ptr(), counters.data_ptr(), memo.data_ptr(), stream)
     else:
         rc = L.fmb_truncate3d_f64(T.data_ptr(), cost.data_ptr(), rank.data_ptr(), T.shape[0], T.shape[1], T.shape[2],
-                                  int(k), out.data_ptr(), scratch.data_ptr(), counters.data_ptr(), stream)
+                                  int(k), out.data_ptr(), scratch.data_ptr(), counters.data_ptr(), memo.data_ptr(), stream)
     _capi.check(rc)
     return out

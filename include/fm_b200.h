@@ -149,11 +149,13 @@ int fmb_trace3d_f64(const double *d_T, int64_t T_qstride, int ny, int nx, int nz
  * it so that the replay runs with full warps); d_counters: int32[2], zeroed by the caller; on return
  * [0] = number of narrow-band cells, [1] = replays that hit the internal depth/work cap (their
  * deepest contributions then fall back to the full-field value; damped by >= 2^-32).
+ * d_memo: scratch of 4 (2D) / 6 (3D) doubles per cell, contents ignored on entry: the tentative value a
+ * cell held after each of its neighbours popped, shared by all replay threads.
  */
 int fmb_truncate2d_f64(const double *d_F, const double *d_cost, const int32_t *d_rank, int rows, int cols,
-                       int32_t k, double *d_out, int32_t *d_list, int32_t *d_counters, void *stream);
+                       int32_t k, double *d_out, int32_t *d_list, int32_t *d_counters, double *d_memo, void *stream);
 int fmb_truncate3d_f64(const double *d_F, const double *d_cost, const int32_t *d_rank, int ny, int nx, int nz,
-                       int32_t k, double *d_out, int32_t *d_list, int32_t *d_counters, void *stream);
+                       int32_t k, double *d_out, int32_t *d_list, int32_t *d_counters, double *d_memo, void *stream);
 
 /* One refinement step of the reference's pop order among exactly equal T values (the reference
  * keeps its narrow band with bisect_left + insert, FastMarching.py:65-67,76-78: last inserted pops
@@ -163,6 +165,13 @@ int fmb_truncate3d_f64(const double *d_F, const double *d_cost, const int32_t *d
 int fmb_tie_keys2d_f64(const double *d_T, const double *d_cost, const int32_t *d_rank, const int32_t *d_tau,
                        const int32_t *d_group, int rows, int cols, int32_t seed_index,
                        int32_t *d_tau_new, int64_t *d_key, void *stream);
+/* The stable sort of those keys only permutes cells inside a tie group: new rank = first rank of the
+ * group + number of members sorting before the cell.  d_members lists the cells group by group
+ * (ascending T), d_gstart / d_gsize give every cell its group's slice (gsize 1 = keep the rank).
+ * *d_changed is set to 1 when any rank or insertion time moved (caller zeroes and polls it). */
+int fmb_tie_rerank(const int64_t *d_key, const int32_t *d_members, const int32_t *d_gstart, const int32_t *d_gsize,
+                   const int32_t *d_rank, const int32_t *d_tau, const int32_t *d_tau_new, int64_t total,
+                   int32_t *d_rank_new, int32_t *d_changed, void *stream);
 
 /* ---- 2D cost-map construction (the step right before the 2D solve) --------
  * Replaces Coupled_motion_planner.py:37-80 (surface_normal), :83-95 (image_filling), :97-109

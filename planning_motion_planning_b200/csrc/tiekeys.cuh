@@ -58,4 +58,34 @@ __global__ void tie_keys2d_kernel(const double *T, const double *cost, const int
     }
 }
 
+// Re-rank inside tie groups after a key step: the global stable sort of `key` (its top bits are the
+// tie group) only permutes cells WITHIN a group, so a cell's new rank is its group's first rank plus
+// the number of members that sort before it (smaller key, or equal key and smaller cell index --
+// what a stable sort of the cell-indexed key array does).  members[gstart .. gstart+gsize) lists the
+// cells of the group; singleton groups keep their rank.  *changed is raised when any rank or
+// insertion time moved, so the host polls one flag instead of comparing arrays.
+__global__ void tie_rerank_kernel(const long long *key, const int *members, const int *gstart, const int *gsize,
+                                  const int *rank, const int *tau, const int *tau_new, long long total, int *rank_new,
+                                  int *changed) {
+    bool moved = false;
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < total; c += (long long)gridDim.x * blockDim.x) {
+        const int n = gsize[c];
+        int r = rank[c];
+        if (n > 1) {
+            const int s = gstart[c];
+            const long long kc = key[c];
+            int before = 0;
+            for (int j = 0; j < n; ++j) {
+                const int m = members[s + j];
+                const long long km = key[m];
+                before += (km < kc || (km == kc && m < (int)c)) ? 1 : 0;
+            }
+            r = s + before;
+        }
+        moved |= r != rank[c] || tau_new[c] != tau[c];
+        rank_new[c] = r;
+    }
+    if (moved) *changed = 1;
+}
+
 }  // namespace fmb

@@ -13,18 +13,29 @@
 // t' = max{rank(n) <= t}, val(n, t') = F(n) if rank(n) <= t' else tent(n, t').  Times
 // strictly decrease along the recursion (the grid has no triangles, so two neighbours
 // of one cell are never adjacent), hence it terminates; it is evaluated per narrow-band
-// cell with a small explicit stack.  The recursion is a walk over a small DAG of
-// (cell, time) states; a per-thread memo table keeps it from being re-walked as a tree
-// (which is exponential in 3D).  Ranks come from a stable sort of F (host side).
+// cell with a small explicit stack.  The recursion is a walk over a DAG of (cell, time)
+// states.  A cell is re-relaxed only when one of its neighbours pops, so it has at most
+// one state per neighbour: a dense memo of NN values per cell (global memory, NaN = not
+// yet known) is shared by all threads -- a state is evaluated once instead of being
+// re-walked as a tree by every narrow-band cell that reaches it (exponential in 3D, and
+// chains along a uniform-cost front are dozens of states deep).  Concurrent evaluations
+// of one state write identical bits.  Ranks come from a stable sort of F (host side).
 #pragma once
 #include "eikonal2d.cuh"
 #include "eikonal3d.cuh"
 
 namespace fmb {
 
-constexpr int TRUNC_MAX_DEPTH = 64;
+constexpr int TRUNC_MAX_DEPTH = 256;      // frames per thread (88-104 B each, local memory)
 constexpr int TRUNC_MAX_EVALS = 1 << 16;   // work cap per narrow-band cell (safety net; never reached with the memo)
-constexpr int TRUNC_MEMO = 1024;            // memo entries per thread (power of two)
+
+#ifdef FMB_HOST_EMU
+// design-time counters, emulator build only: evaluations, deepest stack, fullest memo, recursive descents
+inline long long g_trunc_stats[4] = {0, 0, 0, 0};
+#define TRUNC_STAT(i, expr) (g_trunc_stats[i] = (expr))
+#else
+#define TRUNC_STAT(i, expr) ((void)0)
+#endif
 
 template <int D> struct Grid;
 template <> struct Grid<2> {
@@ -80,17 +91,18 @@ __device__ __forceinline__ real accepted_min(const Grid<D> &g, const int *rank, 
     return m;
 }
 
-// largest rank <= t among the neighbours of c, or -1
+// largest rank <= t among the neighbours of c, or -1; `which` = that neighbour's index
 template <int D>
-__device__ __forceinline__ int last_update_time(const Grid<D> &g, const int *rank, long long c, int t) {
-    int best = -1;
+__device__ __forceinline__ int last_update_time(const Grid<D> &g, const int *rank, long long c, int t, int *which = nullptr) {
+    int best = -1, bi = 0;
 #pragma unroll
     for (int i = 0; i < Grid<D>::NN; ++i) {
         const long long n = g.nbr(c, i);
         if (n < 0) continue;
         const int r = rank[n];
-        if (r <= t && r > best) best = r;
+        if (r <= t && r > best) { best = r; bi = i; }
     }
+    if (which) *which = bi;
     return best;
 }
 
@@ -110,80 +122,116 @@ __global__ void truncate_mark_kernel(Grid<D> g, const real *F, const real *cost,
     }
 }
 
-// pass 2: replay the last relaxation of every narrow-band cell (one thread per listed cell)
+// pass 2: replay the last relaxation of every narrow-band cell (one thread per listed cell).
+// memo: NN doubles per cell, all NaN on entry; slot c*NN + i = tent(c, rank of c's neighbour i).
+// A walk that runs out of stack (chains along a uniform-cost front are ~100 states deep at planner
+// scale) uses the final value as a stand-in for the state it cannot descend into; the states above
+// that point are "tainted": they are not memoised, and the cell is counted in *overflow.
 template <typename real, int D>
 __global__ void truncate_replay_kernel(Grid<D> g, const real *F, const real *cost, const int *rank, int k, real *out,
-                                       const int *list, const int *count, int *overflow) {
+                                       const int *list, const int *count, int *overflow, real *memo) {
     constexpr int NN = Grid<D>::NN;
     const real INF = num<real>::inf();
     const int n_list = *count;
-    struct Frame { long long c; int tp; int stage; real amin; real v[NN]; };
+    struct Frame { long long c; int tp; int stage; int slot; real amin; real u; real v[NN]; };
     for (int li = blockIdx.x * blockDim.x + threadIdx.x; li < n_list; li += gridDim.x * blockDim.x) {
         const long long c0 = list[li];
-        const int t0 = last_update_time<D>(g, rank, c0, k);
+        int w0;
+        const int t0 = last_update_time<D>(g, rank, c0, k, &w0);
         Frame st[TRUNC_MAX_DEPTH];
-        int sp = 0;
-        st[0].c = c0; st[0].tp = t0; st[0].stage = 0; st[0].amin = accepted_min<real, D>(g, rank, F, c0, t0);
         real result = INF;
-        bool have_result = false;
-        int budget = TRUNC_MAX_EVALS;
-        int memo_cell[TRUNC_MEMO], memo_tp[TRUNC_MEMO], memo_used = 0;
-        real memo_val[TRUNC_MEMO];
-        for (int i = 0; i < TRUNC_MEMO; ++i) memo_cell[i] = -1;
-        while (sp >= 0) {
-            Frame &f = st[sp];
-            if (have_result) { f.v[f.stage++] = result; have_result = false; }
-            bool descended = false;
-            while (f.stage < NN) {
-                const long long n = g.nbr(f.c, f.stage);
-                real val;
-                if (n < 0) val = INF;
-                else if (rank[n] <= f.tp) val = F[n];
-                else if (!(cost[n] < INF)) val = INF;
-                else {
-                    // Exact pruning.  A tentative value is >= the cell's final value F[n], so it cannot
-                    // matter when (a) it is not the minimum of its axis, or (b) it is at least one
-                    // cost above the smallest accepted neighbour (the upwind solvers then drop it):
-                    // in both cases any stand-in >= F[n] gives the same update.
-                    const int sib_i = f.stage ^ 1;
-                    const long long sib = g.nbr(f.c, sib_i);
-                    const bool sib_wins = (sib >= 0 && rank[sib] <= f.tp && F[sib] <= F[n]) ||
-                                          (sib_i < f.stage && f.v[sib_i] <= F[n]);
-                    const int tn = (sib_wins || !(F[n] - f.amin < cost[f.c])) ? -2 : last_update_time<D>(g, rank, n, f.tp);
-                    if (tn == -2) val = F[n];
-                    else if (tn < 0) val = INF;
-                    else if (sp + 1 >= TRUNC_MAX_DEPTH || budget <= 0) { val = F[n]; atomicAdd(overflow, 1); }
+        bool tainted_top = false;
+        {
+            int sp = 0, taint = -1;                 // frames 0..taint depend on a stand-in
+            bool top_dirty = false;
+            st[0].c = c0; st[0].tp = t0; st[0].stage = 0; st[0].slot = w0; st[0].amin = accepted_min<real, D>(g, rank, F, c0, t0);
+            bool have_result = false;
+            int budget = TRUNC_MAX_EVALS;
+            while (sp >= 0) {
+                Frame &f = st[sp];
+                if (have_result) {
+                    have_result = false;
+                    if (f.stage == NN + 1) {             // came back with this cell's previous tentative value
+                        result = result < f.u ? result : f.u;
+                        if (sp > taint) { if (sp > 0) __stcg(&memo[f.c * NN + f.slot], result); }
+                        else { taint = sp - 1; top_dirty |= sp == 0; }
+                        have_result = true;
+                        --sp;
+                        continue;
+                    }
+                    f.v[f.stage++] = result;
+                }
+                bool descended = false;
+                while (f.stage < NN) {
+                    const long long n = g.nbr(f.c, f.stage);
+                    real val;
+                    if (n < 0) val = INF;
+                    else if (rank[n] <= f.tp) val = F[n];
+                    else if (!(cost[n] < INF)) val = INF;
                     else {
-                        // memo lookup: tent(n, .) depends only on (n, tn)
-                        unsigned h = ((unsigned)n * 2654435761u + (unsigned)tn * 40503u) & (TRUNC_MEMO - 1);
-                        bool hit = false;
-                        for (int probe = 0; probe < 16; ++probe) {
-                            const unsigned e = (h + probe) & (TRUNC_MEMO - 1);
-                            if (memo_cell[e] < 0) break;
-                            if (memo_cell[e] == (int)n && memo_tp[e] == tn) { val = memo_val[e]; hit = true; break; }
+                        // Exact pruning.  A tentative value is >= the cell's final value F[n], so it cannot
+                        // matter when (a) it is not the minimum of its axis, or (b) it is at least one
+                        // cost above the smallest accepted neighbour (the upwind solvers then drop it):
+                        // in both cases any stand-in >= F[n] gives the same update.
+                        const int sib_i = f.stage ^ 1;
+                        const long long sib = g.nbr(f.c, sib_i);
+                        const bool sib_wins = (sib >= 0 && rank[sib] <= f.tp && F[sib] <= F[n]) ||
+                                              (sib_i < f.stage && f.v[sib_i] <= F[n]);
+                        int wn = 0;
+                        const int tn = (sib_wins || !(F[n] - f.amin < cost[f.c])) ? -2 : last_update_time<D>(g, rank, n, f.tp, &wn);
+                        if (tn == -2) val = F[n];
+                        else if (tn < 0) val = INF;
+                        else {
+                            const real known = __ldcg(&memo[n * NN + wn]);       // tent(n, tn), if already evaluated
+                            if (known == known) val = known;
+                            else if (sp + 1 >= TRUNC_MAX_DEPTH || budget <= 0) { val = F[n]; taint = sp; }
+                            else {
+                                ++sp;
+                                TRUNC_STAT(1, sp > g_trunc_stats[1] ? sp : g_trunc_stats[1]);
+                                TRUNC_STAT(3, g_trunc_stats[3] + 1);
+                                st[sp].c = n; st[sp].tp = tn; st[sp].stage = 0; st[sp].slot = wn;
+                                st[sp].amin = accepted_min<real, D>(g, rank, F, n, tn);
+                                descended = true;
+                                break;
+                            }
                         }
-                        if (hit) { f.v[f.stage++] = val; continue; }
-                        ++sp;
-                        st[sp].c = n; st[sp].tp = tn; st[sp].stage = 0; st[sp].amin = accepted_min<real, D>(g, rank, F, n, tn);
-                        descended = true;
-                        break;
+                    }
+                    f.v[f.stage++] = val;
+                }
+                if (descended) continue;
+                result = Grid<D>::template update<real>(f.v, cost[f.c]);
+                --budget;
+                TRUNC_STAT(0, g_trunc_stats[0] + 1);
+                // The reference keeps a new value only when it is lower (`if T < Tmap[child]`,
+                // FastMarching.py:70, FastMarching3D.py:86), and in floating point a later update can come
+                // out an ulp above an earlier one: the tentative value is the minimum over this cell's
+                // updates so far.  Nothing earlier can undercut the final value itself.
+                if (result > F[f.c]) {
+                    int wp = 0;
+                    const int tprev = last_update_time<D>(g, rank, f.c, f.tp - 1, &wp);
+                    if (tprev >= 0) {
+                        const real known = __ldcg(&memo[f.c * NN + wp]);
+                        if (known == known) result = known < result ? known : result;
+                        else if (sp + 1 >= TRUNC_MAX_DEPTH || budget <= 0) taint = sp;
+                        else {
+                            f.u = result; f.stage = NN + 1;
+                            ++sp;
+                            TRUNC_STAT(1, sp > g_trunc_stats[1] ? sp : g_trunc_stats[1]);
+                            TRUNC_STAT(3, g_trunc_stats[3] + 1);
+                            st[sp].c = f.c; st[sp].tp = tprev; st[sp].stage = 0; st[sp].slot = wp;
+                            st[sp].amin = accepted_min<real, D>(g, rank, F, f.c, tprev);
+                            continue;
+                        }
                     }
                 }
-                f.v[f.stage++] = val;
+                if (sp > taint) { if (sp > 0) __stcg(&memo[f.c * NN + f.slot], result); }
+                else { taint = sp - 1; top_dirty |= sp == 0; }
+                have_result = true;
+                --sp;
             }
-            if (descended) continue;
-            result = Grid<D>::template update<real>(f.v, cost[f.c]);
-            --budget;
-            if (sp > 0 && memo_used < (TRUNC_MEMO * 3) / 4) {      // remember tent(f.c, f.tp)
-                unsigned h = ((unsigned)f.c * 2654435761u + (unsigned)f.tp * 40503u) & (TRUNC_MEMO - 1);
-                for (int probe = 0; probe < 16; ++probe) {
-                    const unsigned e = (h + probe) & (TRUNC_MEMO - 1);
-                    if (memo_cell[e] < 0) { memo_cell[e] = (int)f.c; memo_tp[e] = f.tp; memo_val[e] = result; ++memo_used; break; }
-                }
-            }
-            have_result = true;
-            --sp;
+            tainted_top = top_dirty;
         }
+        if (tainted_top) atomicAdd(overflow, 1);
         out[c0] = result;
     }
 }
