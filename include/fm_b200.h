@@ -145,12 +145,12 @@ int fmb_trace3d_f64(const double *d_T, int64_t T_qstride, int ny, int nx, int nz
  * rest is +inf.  Given the full field d_F, the costs, and d_rank (int32 pop rank of
  * every cell: source 0, unreached INT32_MAX; a stable ascending sort of d_F), these
  * rebuild that partial field for truncation after k pops.  Dense arrays.
- * d_list: int32 scratch with room for one entry per cell (the narrow-band cells are compacted into
- * it so that the replay runs with full warps); d_counters: int32[2], zeroed by the caller; on return
- * [0] = number of narrow-band cells, [1] = replays that hit the internal depth/work cap (their
- * deepest contributions then fall back to the full-field value; damped by >= 2^-32).
+ * The kernel replays every relaxation of the first k pops in pop order, in parallel (csrc/truncate.cuh).
+ * d_list: int32 scratch with room for one entry per cell (receives the cell popped r-th for r <= k);
+ * d_counters: int32[2], zeroed by the caller; [0] is the ticket counter of the replay, on return
+ * [1] = dependency waits that hit the safety limit (0 in every test; non-zero means an inexact value).
  * d_memo: scratch of 4 (2D) / 6 (3D) doubles per cell, contents ignored on entry: the tentative value a
- * cell held after each of its neighbours popped, shared by all replay threads.
+ * cell held after each of its neighbours popped.
  */
 int fmb_truncate2d_f64(const double *d_F, const double *d_cost, const int32_t *d_rank, int rows, int cols,
                        int32_t k, double *d_out, int32_t *d_list, int32_t *d_counters, double *d_memo, void *stream);

@@ -9,33 +9,28 @@
 //     accepted neighbour was popped, from the neighbour values AS OF THAT MOMENT
 //     (accepted ones final, the others whatever tentative value they had then),
 //   * everything else: +inf.
-// "As of that moment" recurses: tent(c, t) = update(val(n, t') for n in N(c)) with
-// t' = max{rank(n) <= t}, val(n, t') = F(n) if rank(n) <= t' else tent(n, t').  Times
-// strictly decrease along the recursion (the grid has no triangles, so two neighbours
-// of one cell are never adjacent), hence it terminates; it is evaluated per narrow-band
-// cell with a small explicit stack.  The recursion is a walk over a DAG of (cell, time)
-// states.  A cell is re-relaxed only when one of its neighbours pops, so it has at most
-// one state per neighbour: a dense memo of NN values per cell (global memory, NaN = not
-// yet known) is shared by all threads -- a state is evaluated once instead of being
-// re-walked as a tree by every narrow-band cell that reaches it (exponential in 3D, and
-// chains along a uniform-cost front are dozens of states deep).  Concurrent evaluations
-// of one state write identical bits.  Ranks come from a stable sort of F (host side).
+// "As of that moment" chains backwards in time: tent(c, t) = update(val(n, t) for n in N(c)),
+// val(n, t) = F(n) if rank(n) <= t, else the tentative value n itself held at time t.  A cell is
+// re-relaxed only when one of its neighbours pops, so it has at most one tentative state per
+// neighbour; the reference keeps a new value only if it is lower (`if T < Tmap[child]`), so a state
+// is the minimum of the update and the cell's previous state.
+//
+// Instead of recursing from the narrow band (deep, serial chains along uniform-cost fronts), the
+// kernel replays EVERY relaxation the reference performed during its first k pops, in the
+// reference's own order, in parallel: ticket r*NN + j = "pop r relaxes its j-th neighbour".  Tickets
+// are handed out in order; a state waits (spin) for the few earlier states it reads -- they belong to
+// strictly earlier pops, i.e. to smaller tickets, which are held by running threads or finished, so
+// the wait cannot deadlock and the critical path is the longest dependency chain, not a walk.  The
+// states live in a dense memo of NN doubles per cell (slot c*NN + i = value of c after its neighbour i
+// popped; all-ones bits = not yet written).  The state of a narrow-band cell after its last update
+// <= k is its entry in the partial field.  Ranks come from a sort of F (host side).
 #pragma once
 #include "eikonal2d.cuh"
 #include "eikonal3d.cuh"
 
 namespace fmb {
 
-constexpr int TRUNC_MAX_DEPTH = 256;      // frames per thread (88-104 B each, local memory)
-constexpr int TRUNC_MAX_EVALS = 1 << 16;   // work cap per narrow-band cell (safety net; never reached with the memo)
-
-#ifdef FMB_HOST_EMU
-// design-time counters, emulator build only: evaluations, deepest stack, fullest memo, recursive descents
-inline long long g_trunc_stats[4] = {0, 0, 0, 0};
-#define TRUNC_STAT(i, expr) (g_trunc_stats[i] = (expr))
-#else
-#define TRUNC_STAT(i, expr) ((void)0)
-#endif
+constexpr int TRUNC_MAX_SPINS = 1 << 22;    // safety net of the dependency wait (never reached; counted in *overflow)
 
 template <int D> struct Grid;
 template <> struct Grid<2> {
@@ -79,18 +74,6 @@ template <> struct Grid<3> {
     }
 };
 
-// smallest final value among the neighbours of c accepted by time tp (the update's anchor)
-template <typename real, int D>
-__device__ __forceinline__ real accepted_min(const Grid<D> &g, const int *rank, const real *F, long long c, int tp) {
-    real m = num<real>::inf();
-#pragma unroll
-    for (int i = 0; i < Grid<D>::NN; ++i) {
-        const long long n = g.nbr(c, i);
-        if (n >= 0 && rank[n] <= tp) m = fmin(m, F[n]);
-    }
-    return m;
-}
-
 // largest rank <= t among the neighbours of c, or -1; `which` = that neighbour's index
 template <int D>
 __device__ __forceinline__ int last_update_time(const Grid<D> &g, const int *rank, long long c, int t, int *which = nullptr) {
@@ -106,133 +89,86 @@ __device__ __forceinline__ int last_update_time(const Grid<D> &g, const int *ran
     return best;
 }
 
-// pass 1: accepted cells and far cells are final here; narrow-band cells (free, not accepted, next
-// to an accepted cell) are collected into a dense list so that pass 2 runs with full warps.
+// pass 1: accepted cells keep their final value, everything else starts at +inf (narrow-band cells
+// are overwritten by pass 2); order[r] = the cell popped r-th, for r <= k.
 template <typename real, int D>
-__global__ void truncate_mark_kernel(Grid<D> g, const real *F, const real *cost, const int *rank, int k, real *out,
-                                     int *list, int *count) {
+__global__ void truncate_mark_kernel(Grid<D> g, const real *F, const int *rank, int k, real *out, int *order) {
     const real INF = num<real>::inf();
     const long long total = g.size();
-    for (long long c0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; c0 < total; c0 += (long long)gridDim.x * blockDim.x) {
-        if (rank[c0] <= k) { out[c0] = F[c0]; continue; }
-        out[c0] = INF;
-        if (!(cost[c0] < INF)) continue;
-        if (last_update_time<D>(g, rank, c0, k) < 0) continue;
-        list[atomicAdd(count, 1)] = (int)c0;
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < total; c += (long long)gridDim.x * blockDim.x) {
+        const int r = rank[c];
+        if (r <= k) { out[c] = F[c]; if (r >= 0) order[r] = (int)c; }
+        else out[c] = INF;
     }
 }
 
-// pass 2: replay the last relaxation of every narrow-band cell (one thread per listed cell).
-// memo: NN doubles per cell, all NaN on entry; slot c*NN + i = tent(c, rank of c's neighbour i).
-// A walk that runs out of stack (chains along a uniform-cost front are ~100 states deep at planner
-// scale) uses the final value as a stand-in for the state it cannot descend into; the states above
-// that point are "tainted": they are not memoised, and the cell is counted in *overflow.
+constexpr unsigned long long MEMO_UNKNOWN = 0xffffffffffffffffULL;
+
+template <typename real>
+__device__ __forceinline__ real memo_wait(const real *memo, long long slot, real fallback, int *overflow) {
+    const volatile unsigned long long *p = reinterpret_cast<const volatile unsigned long long *>(memo) + slot;
+    for (int spins = 0; spins < TRUNC_MAX_SPINS; ++spins) {
+        const unsigned long long b = *p;
+        if (b != MEMO_UNKNOWN) { __threadfence(); return (real)__longlong_as_double((long long)b); }
+        __nanosleep(40);
+    }
+    atomicAdd(overflow, 1);
+    return fallback;
+}
+
+// pass 2: every relaxation of the first k pops, in pop order (see the header of this file)
 template <typename real, int D>
-__global__ void truncate_replay_kernel(Grid<D> g, const real *F, const real *cost, const int *rank, int k, real *out,
-                                       const int *list, const int *count, int *overflow, real *memo) {
+__global__ void truncate_sweep_kernel(Grid<D> g, const real *F, const real *cost, const int *rank, const int *order, int k,
+                                      real *out, real *memo, int *ticket, int *overflow) {
     constexpr int NN = Grid<D>::NN;
     const real INF = num<real>::inf();
-    const int n_list = *count;
-    struct Frame { long long c; int tp; int stage; int slot; real amin; real u; real v[NN]; };
-    for (int li = blockIdx.x * blockDim.x + threadIdx.x; li < n_list; li += gridDim.x * blockDim.x) {
-        const long long c0 = list[li];
-        int w0;
-        const int t0 = last_update_time<D>(g, rank, c0, k, &w0);
-        Frame st[TRUNC_MAX_DEPTH];
-        real result = INF;
-        bool tainted_top = false;
-        {
-            int sp = 0, taint = -1;                 // frames 0..taint depend on a stand-in
-            bool top_dirty = false;
-            st[0].c = c0; st[0].tp = t0; st[0].stage = 0; st[0].slot = w0; st[0].amin = accepted_min<real, D>(g, rank, F, c0, t0);
-            bool have_result = false;
-            int budget = TRUNC_MAX_EVALS;
-            while (sp >= 0) {
-                Frame &f = st[sp];
-                if (have_result) {
-                    have_result = false;
-                    if (f.stage == NN + 1) {             // came back with this cell's previous tentative value
-                        result = result < f.u ? result : f.u;
-                        if (sp > taint) { if (sp > 0) __stcg(&memo[f.c * NN + f.slot], result); }
-                        else { taint = sp - 1; top_dirty |= sp == 0; }
-                        have_result = true;
-                        --sp;
-                        continue;
-                    }
-                    f.v[f.stage++] = result;
-                }
-                bool descended = false;
-                while (f.stage < NN) {
-                    const long long n = g.nbr(f.c, f.stage);
-                    real val;
-                    if (n < 0) val = INF;
-                    else if (rank[n] <= f.tp) val = F[n];
-                    else if (!(cost[n] < INF)) val = INF;
-                    else {
-                        // Exact pruning.  A tentative value is >= the cell's final value F[n], so it cannot
-                        // matter when (a) it is not the minimum of its axis, or (b) it is at least one
-                        // cost above the smallest accepted neighbour (the upwind solvers then drop it):
-                        // in both cases any stand-in >= F[n] gives the same update.
-                        const int sib_i = f.stage ^ 1;
-                        const long long sib = g.nbr(f.c, sib_i);
-                        const bool sib_wins = (sib >= 0 && rank[sib] <= f.tp && F[sib] <= F[n]) ||
-                                              (sib_i < f.stage && f.v[sib_i] <= F[n]);
-                        int wn = 0;
-                        const int tn = (sib_wins || !(F[n] - f.amin < cost[f.c])) ? -2 : last_update_time<D>(g, rank, n, f.tp, &wn);
-                        if (tn == -2) val = F[n];
-                        else if (tn < 0) val = INF;
+    const int lane = threadIdx.x & 31;
+    const long long n_tickets = ((long long)k + 1) * NN;
+    for (;;) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(ticket, 32);
+        base = __shfl_sync(FULL, base, 0);
+        if (base >= n_tickets) break;
+        const long long tk = (long long)base + lane;
+        if (tk < n_tickets) {
+            const int r = (int)(tk / NN), j = (int)(tk - (long long)r * NN);
+            const long long a = order[r];
+            const long long c = g.nbr(a, j);
+            if (c >= 0 && rank[c] > r && cost[c] < INF) {           // a free neighbour that is not accepted yet (:56, FastMarching3D.py:35)
+                real v[NN];
+                int newer = -1;                                      // a neighbour of c that pops in (r, k]: not c's last update
+#pragma unroll
+                for (int i = 0; i < NN; ++i) {
+                    const long long m = g.nbr(c, i);
+                    real val = INF;
+                    if (m >= 0) {
+                        const int rm = rank[m];
+                        if (rm <= r) val = F[m];
                         else {
-                            const real known = __ldcg(&memo[n * NN + wn]);       // tent(n, tn), if already evaluated
-                            if (known == known) val = known;
-                            else if (sp + 1 >= TRUNC_MAX_DEPTH || budget <= 0) { val = F[n]; taint = sp; }
-                            else {
-                                ++sp;
-                                TRUNC_STAT(1, sp > g_trunc_stats[1] ? sp : g_trunc_stats[1]);
-                                TRUNC_STAT(3, g_trunc_stats[3] + 1);
-                                st[sp].c = n; st[sp].tp = tn; st[sp].stage = 0; st[sp].slot = wn;
-                                st[sp].amin = accepted_min<real, D>(g, rank, F, n, tn);
-                                descended = true;
-                                break;
+                            if (rm <= k) newer = i;
+                            if (cost[m] < INF) {
+                                int wm = 0;
+                                const int tm = last_update_time<D>(g, rank, m, r, &wm);
+                                if (tm >= 0) val = memo_wait<real>(memo, m * NN + wm, F[m], overflow);
                             }
                         }
                     }
-                    f.v[f.stage++] = val;
+                    v[i] = val;
                 }
-                if (descended) continue;
-                result = Grid<D>::template update<real>(f.v, cost[f.c]);
-                --budget;
-                TRUNC_STAT(0, g_trunc_stats[0] + 1);
-                // The reference keeps a new value only when it is lower (`if T < Tmap[child]`,
-                // FastMarching.py:70, FastMarching3D.py:86), and in floating point a later update can come
-                // out an ulp above an earlier one: the tentative value is the minimum over this cell's
-                // updates so far.  Nothing earlier can undercut the final value itself.
-                if (result > F[f.c]) {
-                    int wp = 0;
-                    const int tprev = last_update_time<D>(g, rank, f.c, f.tp - 1, &wp);
-                    if (tprev >= 0) {
-                        const real known = __ldcg(&memo[f.c * NN + wp]);
-                        if (known == known) result = known < result ? known : result;
-                        else if (sp + 1 >= TRUNC_MAX_DEPTH || budget <= 0) taint = sp;
-                        else {
-                            f.u = result; f.stage = NN + 1;
-                            ++sp;
-                            TRUNC_STAT(1, sp > g_trunc_stats[1] ? sp : g_trunc_stats[1]);
-                            TRUNC_STAT(3, g_trunc_stats[3] + 1);
-                            st[sp].c = f.c; st[sp].tp = tprev; st[sp].stage = 0; st[sp].slot = wp;
-                            st[sp].amin = accepted_min<real, D>(g, rank, F, f.c, tprev);
-                            continue;
-                        }
-                    }
+                real u = Grid<D>::template update<real>(v, cost[c]);
+                int wp = 0;
+                const int tprev = last_update_time<D>(g, rank, c, r - 1, &wp);
+                if (tprev >= 0) {
+                    const real prev = memo_wait<real>(memo, c * NN + wp, u, overflow);
+                    u = prev < u ? prev : u;
                 }
-                if (sp > taint) { if (sp > 0) __stcg(&memo[f.c * NN + f.slot], result); }
-                else { taint = sp - 1; top_dirty |= sp == 0; }
-                have_result = true;
-                --sp;
+                if (newer < 0 && rank[c] > k) out[c] = u;            // c's state when the reference stops
+                __threadfence();
+                *(reinterpret_cast<volatile unsigned long long *>(memo) + (c * NN + (j ^ 1))) =
+                    (unsigned long long)__double_as_longlong((double)u);
             }
-            tainted_top = top_dirty;
         }
-        if (tainted_top) atomicAdd(overflow, 1);
-        out[c0] = result;
+        __syncwarp();
     }
 }
 

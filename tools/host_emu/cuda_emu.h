@@ -186,6 +186,7 @@ inline unsigned long long atomicMin(unsigned long long *p, unsigned long long v)
 }
 inline unsigned long long atomicExch(unsigned long long *p, unsigned long long v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
 inline long long __double_as_longlong(double v) { long long b; memcpy(&b, &v, 8); return b; }
+inline unsigned long long atomicCAS(unsigned long long *p, unsigned long long cmp, unsigned long long v) { __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST); return cmp; }
 inline int atomicCAS(int *p, int cmp, int v) { __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST); return cmp; }
 
 template <typename T> inline T __ldcg(const T *p) { return *(const volatile T *)p; }

@@ -109,21 +109,19 @@ void emu_trace3d_f64(const double *T, int ny, int nx, int nz, int npaths, const 
 int emu_truncate2d_f64(const double *F, const double *cost, const int *rank, int rows, int cols, int k, double *out) {
     fmb::Grid<2> g; g.rows = rows; g.cols = cols;
     std::vector<int> list((size_t)rows * cols); int counters[2] = {0, 0};
-    std::vector<double> memo((size_t)rows * cols * 4, std::nan(""));
-    emu::launch(4, 64, 0, [&] { fmb::truncate_mark_kernel<double, 2>(g, F, cost, rank, k, out, list.data(), counters); });
-    emu::launch(4, 64, 0, [&] { fmb::truncate_replay_kernel<double, 2>(g, F, cost, rank, k, out, list.data(), counters, counters + 1, memo.data()); });
+    std::vector<double> memo((size_t)rows * cols * 4); memset(memo.data(), 0xff, memo.size() * sizeof(double));   // as fmb_truncate2d_f64 does
+    emu::launch(4, 64, 0, [&] { fmb::truncate_mark_kernel<double, 2>(g, F, rank, k, out, list.data()); });
+    emu::launch(4, 64, 0, [&] { fmb::truncate_sweep_kernel<double, 2>(g, F, cost, rank, list.data(), k, out, memo.data(), counters, counters + 1); });
     return counters[1];
 }
 int emu_truncate3d_f64(const double *F, const double *cost, const int *rank, int ny, int nx, int nz, int k, double *out) {
     fmb::Grid<3> g; g.ny = ny; g.nx = nx; g.nz = nz;
     std::vector<int> list((size_t)ny * nx * nz); int counters[2] = {0, 0};
-    std::vector<double> memo((size_t)ny * nx * nz * 6, std::nan(""));
-    emu::launch(4, 64, 0, [&] { fmb::truncate_mark_kernel<double, 3>(g, F, cost, rank, k, out, list.data(), counters); });
-    emu::launch(4, 64, 0, [&] { fmb::truncate_replay_kernel<double, 3>(g, F, cost, rank, k, out, list.data(), counters, counters + 1, memo.data()); });
+    std::vector<double> memo((size_t)ny * nx * nz * 6); memset(memo.data(), 0xff, memo.size() * sizeof(double));
+    emu::launch(4, 64, 0, [&] { fmb::truncate_mark_kernel<double, 3>(g, F, rank, k, out, list.data()); });
+    emu::launch(4, 64, 0, [&] { fmb::truncate_sweep_kernel<double, 3>(g, F, cost, rank, list.data(), k, out, memo.data(), counters, counters + 1); });
     return counters[1];
 }
-
-void emu_trunc_stats(long long *out, int reset) { for (int i = 0; i < 4; ++i) { out[i] = fmb::g_trunc_stats[i]; if (reset) fmb::g_trunc_stats[i] = 0; } }
 
 void emu_div3(const double *x, double *out, long long n) { for (long long i = 0; i < n; ++i) out[i] = fmb::num<double>::div3(x[i]); }
 
