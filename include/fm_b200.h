@@ -165,13 +165,16 @@ int fmb_truncate3d_f64(const double *d_F, const double *d_cost, const int32_t *d
 int fmb_tie_keys2d_f64(const double *d_T, const double *d_cost, const int32_t *d_rank, const int32_t *d_tau,
                        const int32_t *d_group, int rows, int cols, int32_t seed_index,
                        int32_t *d_tau_new, int64_t *d_key, void *stream);
-/* The stable sort of those keys only permutes cells inside a tie group: new rank = first rank of the
- * group + number of members sorting before the cell.  d_members lists the cells group by group
- * (ascending T), d_gstart / d_gsize give every cell its group's slice (gsize 1 = keep the rank).
- * *d_changed is set to 1 when any rank or insertion time moved (caller zeroes and polls it). */
-int fmb_tie_rerank(const int64_t *d_key, const int32_t *d_members, const int32_t *d_gstart, const int32_t *d_gsize,
-                   const int32_t *d_rank, const int32_t *d_tau, const int32_t *d_tau_new, int64_t total,
-                   int32_t *d_rank_new, int32_t *d_changed, void *stream);
+/* The same order in ONE launch, without iteration: only strictly upwind neighbours (smaller T) take part
+ * in a cell's final update and they pop before the cell's tie group starts, so insertion times and
+ * in-group ranks are settled group by group in ascending T by a ticketed sweep with dependency waits.
+ * d_members lists the cells in ascending T (stable), d_gstart / d_gsize give every cell the slice of its
+ * tie group in that list (size 1 for unreached cells; groups larger than 4096 cells are the caller's cue to
+ * use the iterated form); outputs d_rank (unreached = INT32_MAX) and d_tau; d_key: int64 scratch per cell;
+ * d_scratch: 2*rows*cols + 2 int32, on return its last entry counts waits that hit the safety limit. */
+int fmb_tie_order2d_f64(const double *d_T, const double *d_cost, const int32_t *d_members, const int32_t *d_gstart,
+                        const int32_t *d_gsize, int rows, int cols, int32_t seed_index, int32_t *d_rank, int32_t *d_tau,
+                        int64_t *d_key, int32_t *d_scratch, void *stream);
 
 /* ---- 2D cost-map construction (the step right before the 2D solve) --------
  * Replaces Coupled_motion_planner.py:37-80 (surface_normal), :83-95 (image_filling), :97-109

@@ -58,34 +58,99 @@ __global__ void tie_keys2d_kernel(const double *T, const double *cost, const int
     }
 }
 
-// Re-rank inside tie groups after a key step: the global stable sort of `key` (its top bits are the
-// tie group) only permutes cells WITHIN a group, so a cell's new rank is its group's first rank plus
-// the number of members that sort before it (smaller key, or equal key and smaller cell index --
-// what a stable sort of the cell-indexed key array does).  members[gstart .. gstart+gsize) lists the
-// cells of the group; singleton groups keep their rank.  *changed is raised when any rank or
-// insertion time moved, so the host polls one flag instead of comparing arrays.
-__global__ void tie_rerank_kernel(const long long *key, const int *members, const int *gstart, const int *gsize,
-                                  const int *rank, const int *tau, const int *tau_new, long long total, int *rank_new,
-                                  int *changed) {
-    bool moved = false;
-    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < total; c += (long long)gridDim.x * blockDim.x) {
-        const int n = gsize[c];
-        int r = rank[c];
-        if (n > 1) {
-            const int s = gstart[c];
-            const long long kc = key[c];
-            int before = 0;
-            for (int j = 0; j < n; ++j) {
-                const int m = members[s + j];
-                const long long km = key[m];
-                before += (km < kc || (km == kc && m < (int)c)) ? 1 : 0;
-            }
-            r = s + before;
-        }
-        moved |= r != rank[c] || tau_new[c] != tau[c];
-        rank_new[c] = r;
+// ---- exact tie order in one ordered sweep ----------------------------------------------------------
+// Only STRICTLY upwind neighbours (smaller T) can take part in a cell's final update, and they all
+// pop before the cell's tie group starts, so insertion times and in-group ranks can be settled group
+// by group in ascending T with no iteration: ticket p = p-th cell of the T-sorted list.  A cell waits
+// for its upwind neighbours (earlier groups => smaller tickets, held by running threads or done),
+// computes its insertion time and child index exactly as tie_keys2d_kernel does, then waits for the
+// rest of its tie group and takes its place among them (key ascending, cell index on equal keys).
+// Groups must fit among the resident threads (the host falls back to the iterated sort otherwise).
+constexpr int TIE_MAX_SPINS = 1 << 22;
+__device__ __forceinline__ bool tie_wait_nonzero(const int *flag, int want_at_least) {
+    for (int s = 0; s < TIE_MAX_SPINS; ++s) {
+        if (ld_volatile(flag) >= want_at_least) { __threadfence(); return true; }
+        __nanosleep(40);                              // (busy polling was measured slower: it starves the producers)
     }
-    if (moved) *changed = 1;
+    return false;
+}
+__global__ void tie_sweep2d_kernel(const double *T, const double *cost, const int *members, const int *gstart, const int *gsize,
+                                   int rows, int cols, int seed_idx, int *rank, int *tau, long long *key, int *done,
+                                   int *gcount, int *ticket, int *failed) {
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    const long long BIG = 0x7fffffffLL;
+    const long long total = (long long)rows * cols;
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(ticket, 32);
+        base = __shfl_sync(FULL, base, 0);
+        if (base >= total) break;
+        const long long p = (long long)base + lane;
+        if (p < total) {
+            const int c = members[p];
+            const double t = T[c];
+            if (!(t < INF)) rank[c] = 0x7fffffff;
+            else {
+                long long best = BIG;
+                int cidx = 0;
+                if (c == seed_idx) best = -1;
+                else {
+                    const int y = c / cols, x = c - y * cols;
+                    const int nb[4] = {x > 0 ? c - 1 : -1, x < cols - 1 ? c + 1 : -1, y > 0 ? c - cols : -1, y < rows - 1 ? c + cols : -1};
+                    double tv[4]; long long rv[4], av[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        tv[i] = INF; rv[i] = BIG; av[i] = BIG;
+                        if (nb[i] >= 0) {
+                            const double v = T[nb[i]];
+                            if (v < t) {                              // strictly upwind: its rank and insertion time are final before mine
+                                if (!tie_wait_nonzero(&done[nb[i]], 1)) atomicAdd(failed, 1);
+                                tv[i] = v; rv[i] = ld_volatile(&rank[nb[i]]); av[i] = ld_volatile(&tau[nb[i]]);
+                            }
+                        }
+                    }
+                    const double c_cost = cost[c];
+                    const double limit = t * (1.0 + 1e-14);
+                    const int ci[4] = {4, 3, 2, 1};   // popped neighbour left/right/up/down => my child index in its updateNode
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const long long ti = rv[i];
+                        if (ti >= BIG || ti >= best) continue;
+                        const double l = av[0] <= ti ? tv[0] : INF, r = av[1] <= ti ? tv[1] : INF;
+                        const double u = av[2] <= ti ? tv[2] : INF, d = av[3] <= ti ? tv[3] : INF;
+                        const double a = l < r ? l : r, b = u < d ? u : d;
+                        const double m = a < b ? a : b, dd = a - b;
+                        double v;
+                        if (!(fabs(dd) <= c_cost)) v = m + c_cost;
+                        else v = 0.5 * (a + b + sqrt(2.0 * (c_cost * c_cost) - dd * dd));
+                        if (v <= limit) { best = ti; cidx = ci[i]; }
+                    }
+                }
+                tau[c] = (int)best;
+                int r = gstart[c];
+                const int n = gsize[c];
+                if (n > 1) {
+                    const long long kc = ((long long)(0xffffffffLL - (unsigned long long)(best + 1)) << 3) | (long long)(7 - cidx);
+                    *reinterpret_cast<volatile long long *>(&key[c]) = kc;
+                    __threadfence();
+                    atomicAdd(&gcount[r], 1);
+                    if (!tie_wait_nonzero(&gcount[r], n)) atomicAdd(failed, 1);
+                    int before = 0;
+                    for (int j = 0; j < n; ++j) {
+                        const int m = members[r + j];
+                        const long long km = *reinterpret_cast<const volatile long long *>(&key[m]);
+                        before += (km < kc || (km == kc && m < c)) ? 1 : 0;
+                    }
+                    r += before;
+                }
+                rank[c] = r;
+                __threadfence();
+                *reinterpret_cast<volatile int *>(&done[c]) = 1;
+            }
+        }
+        __syncwarp();
+    }
 }
 
 }  // namespace fmb

@@ -110,7 +110,7 @@ __device__ __forceinline__ real memo_wait(const real *memo, long long slot, real
     for (int spins = 0; spins < TRUNC_MAX_SPINS; ++spins) {
         const unsigned long long b = *p;
         if (b != MEMO_UNKNOWN) { __threadfence(); return (real)__longlong_as_double((long long)b); }
-        __nanosleep(40);
+        __nanosleep(40);                              // (busy polling was measured slower: it starves the producers)
     }
     atomicAdd(overflow, 1);
     return fallback;

@@ -158,3 +158,34 @@ def costvolume(Zs, resX, resY, resZ, sX, sY, sZ, xm, ym, rlim, rO, rm, gamma2D, 
     fn.argtypes = [C.c_void_p, dp, dp, dp]
     assert fn(C.byref(d), cmap.ctypes.data_as(dp), tunnel.ctypes.data_as(dp), terrain.ctypes.data_as(dp)) == 0
     return cmap.reshape(sX, sY, sZ), tunnel.reshape(sY, sX, sZ), terrain.reshape(sX, sY, sZ)
+
+
+def tie_groups(F):
+    """(members, gstart, gsize) of the T-sorted tie groups, as FastMarching/_compat.py builds them."""
+    flat = np.ascontiguousarray(F, dtype=np.float64).ravel()
+    order = np.argsort(flat, kind="stable")
+    ts = flat[order]
+    new = np.concatenate([[True], ts[1:] != ts[:-1]])
+    starts = np.nonzero(new)[0]
+    sizes = np.diff(np.concatenate([starts, [flat.size]]))
+    grp = np.cumsum(new) - 1
+    group = np.empty(flat.size, np.int64)
+    group[order] = grp
+    gstart = starts[group].astype(np.int32)
+    gsize = np.where(np.isfinite(flat), sizes[group], 1).astype(np.int32)
+    return order.astype(np.int32), gstart, gsize
+
+
+def tie_order2d(F, cost, seed):
+    """Emulated tie_sweep2d_kernel: int32 pop ranks incl. the LIFO order among equal values."""
+    F = np.ascontiguousarray(F, dtype=np.float64)
+    cost = np.ascontiguousarray(cost, dtype=np.float64)
+    rows, cols = F.shape
+    members, gstart, gsize = tie_groups(F)
+    rank, tau = np.empty(F.size, np.int32), np.empty(F.size, np.int32)
+    fn = lib().emu_tie_order2d
+    fn.argtypes = [dp, dp, ip, ip, ip, C.c_int, C.c_int, C.c_int, ip, ip]
+    failed = fn(F.ctypes.data_as(dp), cost.ctypes.data_as(dp), members.ctypes.data_as(ip), gstart.ctypes.data_as(ip),
+                gsize.ctypes.data_as(ip), rows, cols, int(seed[1]) * cols + int(seed[0]), rank.ctypes.data_as(ip), tau.ctypes.data_as(ip))
+    assert failed == 0
+    return rank.reshape(rows, cols)

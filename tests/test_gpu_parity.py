@@ -399,7 +399,18 @@ def test_tie_order_kernel_matches_torch_reference_and_oracle_order():
         T, order, _ = O.computeTmap(c, g, return_stats=True)
         r_cpu = _compat.pop_ranks_lifo2d(torch.from_numpy(T), torch.from_numpy(c), g)
         r_gpu = _compat.pop_ranks_lifo2d(torch.from_numpy(T).cuda(), torch.from_numpy(c).cuda(), g).cpu()
-        assert torch.equal(r_cpu, r_gpu)
+        assert torch.equal(r_cpu, r_gpu)                  # iterated torch form == one-pass device sweep
+        Td, cd = torch.from_numpy(T).cuda(), torch.from_numpy(c).cuda()
+        flat = Td.reshape(-1)
+        order0 = torch.sort(flat, stable=True).indices
+        ts = flat[order0]
+        grp = torch.cumsum(torch.cat([torch.zeros(1, dtype=torch.int32, device="cuda"), (ts[1:] != ts[:-1]).to(torch.int32)]), 0)
+        group = torch.empty(flat.numel(), dtype=torch.int32, device="cuda")
+        group[order0] = grp.to(torch.int32)
+        rank0 = torch.empty(flat.numel(), dtype=torch.int32, device="cuda")
+        rank0[order0] = torch.arange(flat.numel(), dtype=torch.int32, device="cuda")
+        r_it = _compat._pop_ranks_lifo2d_sort(Td, cd, g[1] * T.shape[1] + g[0], 96, group, rank0).cpu()
+        assert torch.equal(r_it, r_gpu)                   # and == the iterated device fallback (huge tie groups)
         mine = np.argsort(r_gpu.numpy().ravel(), kind="stable")[1:1 + len(order)]
         assert int((mine != order).sum()) <= max_bad
 

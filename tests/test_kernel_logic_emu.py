@@ -217,3 +217,21 @@ def test_tracers_fuzz_against_oracle_including_failure_modes():
             po, so = O.getPathGDM3D(T, np.array(init), np.array(goal, dtype=float), 0.5, return_status=True)
             assert s[k] == so and p[k].shape == po.shape
             assert len(po) == 0 or np.allclose(p[k], po, rtol=0, atol=1e-9, equal_nan=True)
+
+
+def test_tie_order_sweep_matches_reference_pop_order():
+    """csrc/tiekeys.cuh tie_sweep2d_kernel (one ordered sweep, no iteration) under the emulator against
+    the reference's true pop order on tie-heavy maps and on the planner's own cost map."""
+    uniform = np.pad(np.ones((60, 60)), 1, constant_values=np.inf)
+    g = np.load(f"{GOLDEN}/planner_calls.npz")
+    pc = np.ascontiguousarray(g["bi_cost"])
+    for c, s, max_bad in ((uniform, [30, 30], 0), (uniform, [12, 40], 0), (plateau_map(80, 1), [8, 8], 0), (plateau_map(80, 2), [8, 8], 0),
+                          (plateau_map(120, 5), [60, 8], 0), (rand_map((60, 60), 2), [9, 40], 0),
+                          (pc, [int(v) for v in g["bi_goal"]], 0),
+                          # one mirror pair tied to the last bit whose order hinges on an ulp-level coincidence of a
+                          # NON-final neighbour value (DESIGN.md 6): the plain sort misplaces 100+ cells here
+                          (pc, [int(v) for v in g["bi_start"]], 2)):
+        T, order, _ = O.computeTmap(c, s, return_stats=True)
+        r = emu.tie_order2d(T, c, s)
+        mine = np.argsort(r.ravel(), kind="stable")[1:1 + len(order)]
+        assert int((mine != order).sum()) <= max_bad

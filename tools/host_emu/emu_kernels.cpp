@@ -11,6 +11,7 @@
 #include "../../planning_motion_planning_b200/csrc/trace2d.cuh"
 #include "../../planning_motion_planning_b200/csrc/trace3d.cuh"
 #include "../../planning_motion_planning_b200/csrc/truncate.cuh"
+#include "../../planning_motion_planning_b200/csrc/tiekeys.cuh"
 #include "../../planning_motion_planning_b200/csrc/costmap2d.cuh"
 #include "../../planning_motion_planning_b200/csrc/costvolume.cuh"
 #include "../../include/fm_b200.h"
@@ -213,6 +214,19 @@ int emu_costvolume_f64(const fmb_costvolume_desc *d, double *cmap, double *tunne
     emu::launch(2, 64, 0, [&] { fmb::cv_scatter_kernel(A); });
     emu::launch(2, 64, 0, [&] { fmb::cv_compose_kernel(A); });
     return 0;
+}
+
+// csrc/tiekeys.cuh: exact LIFO pop order in one ordered sweep
+int emu_tie_order2d(const double *T, const double *cost, const int *members, const int *gstart, const int *gsize, int rows,
+                    int cols, int seed_idx, int *rank, int *tau) {
+    const size_t n = (size_t)rows * cols;
+    std::vector<long long> key(n);
+    std::vector<int> scratch(2 * n + 2, 0);
+    emu::launch(4, 64, 0, [&] {
+        fmb::tie_sweep2d_kernel(T, cost, members, gstart, gsize, rows, cols, seed_idx, rank, tau, key.data(), scratch.data(),
+                                scratch.data() + n, scratch.data() + 2 * n, scratch.data() + 2 * n + 1);
+    });
+    return scratch[2 * n + 1];
 }
 
 }  // extern "C"
