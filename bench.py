@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--batch-queries", type=int, default=4096, help="512^2 queries per GPU in the batched section")
     ap.add_argument("--no-3d", action="store_true", help="skip the 3D (arm-workspace volume) section")
     ap.add_argument("--no-costmap", action="store_true", help="skip the cost-map construction section")
+    ap.add_argument("--inflight", type=int, default=3, help="independent queries solved concurrently per GPU (own stream each)")
     ap.add_argument("--size3d", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -178,10 +179,11 @@ def cpu_port_run(c, goal, start, threads, sample_n):
 
 
 def reference_arm(args):
-    """Reference arm: the CPU implementation of the SAME step (one full-size solve + path per
-    query, N = --gpus independent queries per step, one host thread per query -- a heap FMM is
-    sequential, a single query cannot use more).  It is the C port of the reference (oracle):
-    the reference itself is pure Python (~2e4 cells/s) and has nothing to compile."""
+    """Reference arm: the CPU implementation of the SAME work (one full-size solve + path per
+    query) with the SAME concurrency the GPU arm is given: --gpus x --inflight independent queries at
+    a time, one host thread per query -- a heap FMM is sequential, a single query cannot use more.
+    It is the C port of the reference (oracle): the reference itself is pure Python (~2e4 cells/s,
+    one thread) and has nothing to compile."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -191,7 +193,7 @@ def reference_arm(args):
     cores = len(os.sched_getaffinity(0))
     n = args.size
     c = make_map(n, args.map)
-    nq = max(1, args.gpus)
+    nq = max(1, args.gpus) * max(1, args.inflight)
     threads = min(nq, cores)
     goals, starts = goals_for(c, nq)
 
@@ -222,7 +224,7 @@ def reference_arm(args):
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{n}x{n} fp64 planner-like costmap ({args.map}, seed 0): full-field solve + 1 path "
-                               f"per query per step, {nq} independent queries", "cpu_threads": threads},
+                               f"per query, {nq} independent queries at a time (--gpus x --inflight)", "cpu_threads": threads},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                          "throughput_all_cores": {"value": allc, "unit": UNIT, "cores": min(cores, 32),
                                                   "sample": f"{min(cores, 32)} threads x one {small}x{small} crop each"}},
@@ -265,29 +267,41 @@ def own_arm(args):
     init = torch.tensor([start], dtype=torch.float64, device=dev)
     end = torch.tensor([goal], dtype=torch.float64, device=dev)
 
-    # One step = one query = full-field solve + its path.  The path of step k is traced on a
-    # second stream while step k+1 already solves into the other field buffer (the tracer is one
-    # warp); every solve and every trace of the K steps lies inside the timed region.
-    T_buf = [T_d, torch.empty_like(T_d)]
-    s_tr = torch.cuda.Stream(device=dev)
-    ev_solved2 = [torch.cuda.Event(), torch.cuda.Event()]
-    ev_traced2 = [torch.cuda.Event(), torch.cuda.Event()]
+    # One step = one query = full-field solve + its path.  Queries are independent, and a single solve
+    # is bound by its chain of tile visits, not by throughput (in windowed order it uses a
+    # third of the SM slots), so `--inflight` queries run concurrently, each on its own stream with its
+    # own workspace and field buffers; the path of a query is traced on a second stream while the next
+    # query of that lane already solves.  Every solve and every trace of the K steps lies inside the
+    # timed region; `latency_ms_one_query` reports one query run alone.
+    NF = max(1, args.inflight)
+    T_bufs = [[T_d if (f == 0) else torch.empty_like(T_d), torch.empty_like(T_d)] for f in range(NF)]
+    s_solve = [torch.cuda.Stream(device=dev) for _ in range(NF)]
+    s_trace = [torch.cuda.Stream(device=dev) for _ in range(NF)]
+    ev_solved2 = [[torch.cuda.Event(), torch.cuda.Event()] for _ in range(NF)]
+    ev_traced2 = [[torch.cuda.Event(), torch.cuda.Event()] for _ in range(NF)]
 
     def run_resident(K_):
         cur = torch.cuda.current_stream()
-        for b in (0, 1):
-            ev_traced2[b].record(cur)
+        start = torch.cuda.Event()
+        start.record(cur)
         res = None
+        for f in range(NF):
+            s_solve[f].wait_event(start)
+            for b in (0, 1):
+                ev_traced2[f][b].record(s_solve[f])
         for k in range(K_):
-            b = k & 1
-            cur.wait_event(ev_traced2[b])               # the trace that last read this buffer is done
-            engine.solve2d(cost_d, seeds_d, out=T_buf[b], nq=1, sync=False)
-            ev_solved2[b].record(cur)
-            with torch.cuda.stream(s_tr):
-                s_tr.wait_event(ev_solved2[b])
-                res = engine.trace2d(T_buf[b], init, end, tau)
-                ev_traced2[b].record(s_tr)
-        cur.wait_stream(s_tr)
+            f, b = k % NF, (k // NF) & 1
+            with torch.cuda.stream(s_solve[f]):
+                s_solve[f].wait_event(ev_traced2[f][b])          # the trace that last read this buffer is done
+                engine.solve2d(cost_d, seeds_d, out=T_bufs[f][b], nq=1, sync=False)
+                ev_solved2[f][b].record(s_solve[f])
+            with torch.cuda.stream(s_trace[f]):
+                s_trace[f].wait_event(ev_solved2[f][b])
+                res = engine.trace2d(T_bufs[f][b], init, end, tau)
+                ev_traced2[f][b].record(s_trace[f])
+        for f in range(NF):
+            cur.wait_stream(s_solve[f])
+            cur.wait_stream(s_trace[f])
         return res
 
     def step_resident():
@@ -303,8 +317,11 @@ def own_arm(args):
     for _ in range(max(W, 3)):
         out, cnt, st = step_resident()
         stats = engine.finish(dev)
-    run_resident(2)
+    run_resident(2 * NF)
     torch.cuda.synchronize()
+    for f in range(NF):
+        with torch.cuda.stream(s_solve[f]):
+            engine.finish(dev)
     path_len = int(cnt[0])
     path_status = int(st[0])
 
@@ -319,7 +336,8 @@ def own_arm(args):
     barrier()
     clocks = sampler.stop()
     t_ms = ev0.elapsed_time(ev1)
-    stats = engine.finish(dev)
+    with torch.cuda.stream(s_solve[0]):
+        stats = engine.finish(dev)
     if world > 1:
         tt = torch.tensor([t_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -361,69 +379,84 @@ def own_arm(args):
     # the path and its length back.  Copies run on two side streams so that step k's field
     # download overlaps its own trace and step k+1's upload overlaps step k's solve (two device
     # input buffers); all of it is inside the timed region, which ends with a full synchronize.
-    T_h = torch.empty((1, n, n), dtype=torch.float64).pin_memory()
     cap = int(round(15000 / tau)) + 2
-    path_h = torch.empty((1, cap, 2), dtype=torch.float64).pin_memory()
-    cnt_h = torch.empty(1, dtype=torch.int32).pin_memory()
-    s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    T_hs = [torch.empty((1, n, n), dtype=torch.float64).pin_memory() for _ in range(NF)]
+    path_hs = [torch.empty((1, cap, 2), dtype=torch.float64).pin_memory() for _ in range(NF)]
+    cnt_hs = [torch.empty(1, dtype=torch.int32).pin_memory() for _ in range(NF)]
+    T_h, path_h, cnt_h = T_hs[0], path_hs[0], cnt_hs[0]
     main = torch.cuda.current_stream()
-    cbuf = [torch.empty_like(cost_d), torch.empty_like(cost_d)]
-    ev_in = [torch.cuda.Event(), torch.cuda.Event()]
-    ev_free = [torch.cuda.Event(), torch.cuda.Event()]
-    ev_solved = [torch.cuda.Event(), torch.cuda.Event()]
-    ev_T_out = [torch.cuda.Event(), torch.cuda.Event()]
-    ev_traced = [torch.cuda.Event(), torch.cuda.Event()]
+    s_ins = [torch.cuda.Stream(device=dev) for _ in range(NF)]
+    s_outs = [torch.cuda.Stream(device=dev) for _ in range(NF)]
+    cbufs = [[torch.empty_like(cost_d), torch.empty_like(cost_d)] for _ in range(NF)]
+    mk = lambda: [[torch.cuda.Event(), torch.cuda.Event()] for _ in range(NF)]      # noqa: E731
+    ev_in, ev_free, ev_solved, ev_T_out, ev_traced = mk(), mk(), mk(), mk(), mk()
 
-    def upload(k):
-        b = k & 1
-        with torch.cuda.stream(s_in):
-            s_in.wait_event(ev_free[b])                 # the solve that last read this buffer is done
-            cbuf[b].copy_(cost_h, non_blocking=True)
-            ev_in[b].record(s_in)
+    def upload(f, j):
+        b = j & 1
+        with torch.cuda.stream(s_ins[f]):
+            s_ins[f].wait_event(ev_free[f][b])          # the solve that last read this buffer is done
+            cbufs[f][b].copy_(cost_h, non_blocking=True)
+            ev_in[f][b].record(s_ins[f])
 
     def run_e2e(K_):
-        for b in (0, 1):
-            ev_free[b].record(main)
-            ev_T_out[b].record(main)
-            ev_traced[b].record(main)
-        upload(0)
+        start = torch.cuda.Event()
+        start.record(main)
+        for f in range(NF):
+            for st_ in (s_solve[f], s_ins[f]):
+                st_.wait_event(start)
+            for b in (0, 1):
+                ev_free[f][b].record(s_solve[f])
+                ev_T_out[f][b].record(s_solve[f])
+                ev_traced[f][b].record(s_solve[f])
+            if f < K_:
+                upload(f, 0)
         for k in range(K_):
-            b = k & 1
-            main.wait_event(ev_in[b])
-            main.wait_event(ev_T_out[b])                # download and trace of step k-2 finished with T_buf[b]
-            main.wait_event(ev_traced[b])
-            engine.solve2d(cbuf[b], seeds_d, out=T_buf[b], nq=1, sync=False)
-            ev_free[b].record(main)
-            ev_solved[b].record(main)
-            if k + 1 < K_:
-                upload(k + 1)
-            with torch.cuda.stream(s_out):
-                s_out.wait_event(ev_solved[b])
-                T_h.copy_(T_buf[b], non_blocking=True)
-                ev_T_out[b].record(s_out)
-            with torch.cuda.stream(s_tr):
-                s_tr.wait_event(ev_solved[b])
-                out, cnt, st = engine.trace2d(T_buf[b], init, end, tau)
-                path_h.copy_(out, non_blocking=True)
-                cnt_h.copy_(cnt, non_blocking=True)
-                ev_traced[b].record(s_tr)
+            f, j = k % NF, k // NF
+            b = j & 1
+            with torch.cuda.stream(s_solve[f]):
+                s_solve[f].wait_event(ev_in[f][b])
+                s_solve[f].wait_event(ev_T_out[f][b])   # download and trace of this lane's step j-2 are done with the buffer
+                s_solve[f].wait_event(ev_traced[f][b])
+                engine.solve2d(cbufs[f][b], seeds_d, out=T_bufs[f][b], nq=1, sync=False)
+                ev_free[f][b].record(s_solve[f])
+                ev_solved[f][b].record(s_solve[f])
+            if k + NF < K_:
+                upload(f, j + 1)
+            with torch.cuda.stream(s_outs[f]):
+                s_outs[f].wait_event(ev_solved[f][b])
+                T_hs[f].copy_(T_bufs[f][b], non_blocking=True)
+                ev_T_out[f][b].record(s_outs[f])
+            with torch.cuda.stream(s_trace[f]):
+                s_trace[f].wait_event(ev_solved[f][b])
+                out, cnt, st = engine.trace2d(T_bufs[f][b], init, end, tau)
+                path_hs[f].copy_(out, non_blocking=True)
+                cnt_hs[f].copy_(cnt, non_blocking=True)
+                ev_traced[f][b].record(s_trace[f])
         torch.cuda.synchronize()
 
-    run_e2e(2)
-    engine.finish(dev)
+    def finish_lanes():
+        st_all = None
+        for f in range(NF):
+            with torch.cuda.stream(s_solve[f]):
+                r = engine.finish(dev)
+            st_all = st_all or r
+        return st_all
+
+    run_e2e(2 * NF)
+    finish_lanes()
     barrier()
     t0 = time.perf_counter()
     run_e2e(K)
     barrier()
     e2e_s = time.perf_counter() - t0
-    engine.finish(dev)
+    finish_lanes()
     if world > 1:
         tt = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt[0])
     e2e = {"value": world * cells * K / e2e_s, "unit": UNIT, "ms_per_step": 1e3 * e2e_s / K,
            "h2d_bytes_per_step": int(cost_h.numel() * 8), "d2h_bytes_per_step": int(T_h.numel() * 8 + path_h.numel() * 8 + 4),
-           "pipelining": "uploads, downloads and the trace of step k run on side streams and overlap the solve of step k+1"}
+           "pipelining": f"{NF} queries in flight, each lane with its own upload / solve / download / trace streams and double buffers"}
 
     # ---- batched independent queries (config 4 style): Q goal queries on one 512^2 map per GPU
     batch = None
@@ -605,7 +638,8 @@ def own_arm(args):
             "config": {"workload": f"{n}x{n} fp64 planner-like costmap ({args.map}, seed 0): full-field solve + 1 path "
                                    f"per GPU per step", "l2_policy": "inputs larger than L2 (cost + T = %d MiB)" % (2 * cells * 8 >> 20),
                        "tau": tau, "path_rows": path_len, "path_status": path_status, "parallelism": f"{world} replicas, one query per GPU per step",
-                       "pipelining": "step k's path is traced on a second stream while step k+1 solves (two field buffers)"},
+                       "pipelining": f"{NF} independent queries in flight per GPU (own streams and buffers); a query's path is traced "
+                                     "while the next query of its lane solves"},
             "latency_ms_one_query": init_ms + solve_ms + trace_ms,
             "breakdown_ms": {"init_fill": init_ms, "solve_kernel": solve_ms, "trace_kernel": trace_ms},
             "solver_stats": {k: stats[k] for k in ("tile_visits", "steps", "evals", "pushes", "cells_written")},

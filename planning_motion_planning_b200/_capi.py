@@ -25,6 +25,7 @@ class FmbStats(C.Structure):
     def as_dict(self):
         d = {k: int(getattr(self, k)) for k in ("tile_visits", "steps", "evals", "pushes", "cells_written",
                                                 "cyc_wait", "cyc_load", "cyc_relax", "cyc_store")}
+        d["deferrals"] = int(self.reserved[0])
         d["solve_kernel_ms"] = float(self.solve_kernel_ms)
         d["init_kernel_ms"] = float(self.init_kernel_ms)
         return d

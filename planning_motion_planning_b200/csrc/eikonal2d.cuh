@@ -31,7 +31,27 @@ struct Problem2D {
     int best_first;          // 1: ring carries query ids, workers claim the lowest-priority queued tile
     int arm_rows;            // bit 0 / bit 1: the first / last tile row holds a halo row written from outside
                              // (domain decomposition): every visit of those tiles re-arms all their cells
+    // windowed order (one large map): a popped tile whose level (priority / delta) is more than
+    // `win_window` levels above the lowest queued level is put back at the tail instead of being run
+    int windowed, win_window;
+    int *lev_count;          // [WIN_LEVELS] queued tiles per level
+    int *win_hint;           // lowest level that may be non-empty
+    int *tile_level;         // [ntiles] level recorded when the tile was queued
+    double *win_inv_delta;   // 1 / (T units per level), set by the seed kernel
 };
+constexpr int WIN_LEVELS = 8192;
+__device__ __forceinline__ int win_level(unsigned long long pbits, double inv_delta) {
+    const double v = __longlong_as_double((long long)pbits) * inv_delta;
+    return v < (double)(WIN_LEVELS - 1) ? (int)v : WIN_LEVELS - 1;        // +inf / NaN land on the last level
+}
+template <typename real>
+__device__ __forceinline__ void win_count_push(const Problem2D<real> &P, int item) {
+    const int L = win_level(*reinterpret_cast<const volatile unsigned long long *>(&P.tile_prio[item]), *P.win_inv_delta);
+    *reinterpret_cast<volatile int *>(&P.tile_level[item]) = L;
+    atomicAdd(&P.lev_count[L], 1);
+    atomicMin(P.win_hint, L);
+    __threadfence();          // level and count are visible before the ring slot is
+}
 
 // FastMarching.py:17-29 getEikonal, written branch-for-branch on the values
 // a = min(left,right), b = min(up,down).  Products and sums are individually
@@ -77,12 +97,15 @@ __global__ void init_fill2d_kernel(Problem2D<real> P, int ring_slots) {
     const long long ntiles = (long long)P.nq * P.ntx * P.nty;
     for (long long i = tid; i < ntiles; i += nth) {
         P.tile_state[i] = ST_IDLE;
-        if (P.best_first) P.tile_prio[i] = 0x7ff0000000000000ULL;
+        if (P.best_first || P.windowed) P.tile_prio[i] = 0x7ff0000000000000ULL;
     }
     for (long long i = tid; i < ring_slots; i += nth) P.q.ring[i] = -1;
+    if (P.windowed)
+        for (long long i = tid; i < WIN_LEVELS; i += nth) P.lev_count[i] = 0;
     if (tid == 0) {
         QueueCtl z = {};
         *P.q.ctl = z;
+        if (P.windowed) *P.win_hint = WIN_LEVELS - 1;
     }
 }
 
@@ -97,6 +120,10 @@ __global__ void init_seed2d_kernel(Problem2D<real> P) {
     P.T[q * P.T_qstride + (long long)sy * P.T_pitch + sx] = (real)0;
     const int tx = sx / TW, ty = sy / TILE_H;
     const int base = q * P.ntx * P.nty;
+    if (P.windowed) {        // one level = the time to cross one tile at the source's cost
+        const real c0 = P.cost[q * P.cost_qstride + (long long)sy * P.cost_pitch + sx];
+        *P.win_inv_delta = (c0 > (real)0 && c0 < num<real>::inf()) ? 1.0 / ((double)TW * (double)c0) : 1.0 / (double)TW;
+    }
     int cand[5][2] = {{tx, ty}, {-1, -1}, {-1, -1}, {-1, -1}, {-1, -1}};
     if (sx % TW == 0 && tx > 0) { cand[1][0] = tx - 1; cand[1][1] = ty; }
     if (sx % TW == TW - 1 && tx < P.ntx - 1) { cand[2][0] = tx + 1; cand[2][1] = ty; }
@@ -106,7 +133,8 @@ __global__ void init_seed2d_kernel(Problem2D<real> P) {
         if (cand[k][0] < 0) continue;
         int item = base + cand[k][1] * P.ntx + cand[k][0];
         if (tile_activate(P.tile_state, P.q.ctl, item)) {
-            if (P.best_first) P.tile_prio[item] = 0ULL;
+            if (P.best_first || P.windowed) P.tile_prio[item] = 0ULL;
+            if (P.windowed) win_count_push<real>(P, item);
             q_push(P.q, P.best_first ? q : item);
             atomicAdd(&P.q.ctl->pushes, 1ULL);
         }
@@ -163,18 +191,44 @@ __global__ void __launch_bounds__(WARPS * 32) solve2d_kernel(Problem2D<real> P) 
     const int tiles_per_q = P.ntx * P.nty;
     const unsigned long long PRIO_INF = 0x7ff0000000000000ULL;
 
-    unsigned long long n_visits = 0, n_steps = 0, n_evals = 0, n_pushes = 0, n_written = 0;
+    unsigned long long n_visits = 0, n_steps = 0, n_evals = 0, n_pushes = 0, n_written = 0, n_defer = 0;
+    int streak = 0;
     long long c_wait = 0, c_load = 0, c_relax = 0, c_store = 0;
 
     for (;;) {
         const long long tc0 = clock64();
         int item;
-        {
+        for (;;) {
             int it = -1;
             if (lane == 0) it = q_pop_lane0(P.q);
             item = __shfl_sync(FULL, it, 0);
-            if (item < 0) break;
+            if (item < 0 || BEST || !P.windowed) break;
+            // windowed order: run the tile only if it is within win_window levels of the lowest queued
+            // level; otherwise put it back at the tail (the lowest queued level itself always runs)
+            int defer = 0;
+            if (lane == 0 && streak < 32) {            // a worker never defers more than 32 times in a row
+                __threadfence();
+                const int L = ld_volatile(&P.tile_level[item]);
+                atomicSub(&P.lev_count[L], 1);
+                const int h0 = ld_volatile(P.win_hint);
+                int h = h0;
+                const int stop_at = min(L - P.win_window, h0 + 64);          // bounded scan
+                while (h < stop_at && ld_volatile(&P.lev_count[h]) <= 0) ++h;
+                if (h != h0) atomicCAS(P.win_hint, h0, h);
+                if (h < L - P.win_window && h < stop_at) {                    // a queued tile sits more than a window below this one
+                    atomicAdd(&P.lev_count[L], 1);
+                    q_push(P.q, item);
+                    defer = 1;
+                }
+            }
+            else if (lane == 0) atomicSub(&P.lev_count[ld_volatile(&P.tile_level[item])], 1);
+            defer = __shfl_sync(FULL, defer, 0);
+            if (!defer) { streak = 0; break; }
+            ++streak;
+            n_defer += 1;
+            __nanosleep(streak < 4 ? 200u : streak < 12 ? 800u : 2000u);      // back off: the front is elsewhere
         }
+        if (item < 0) break;
         if (BEST) {
             // `item` is a query id: claim its lowest-priority queued tile (QUEUED -> RUNNING)
             const int base = item * tiles_per_q;
@@ -221,7 +275,11 @@ __global__ void __launch_bounds__(WARPS * 32) solve2d_kernel(Problem2D<real> P) 
         } else {
             // QUEUED -> RUNNING *before* sampling T: anything published after this point flips
             // the state to DIRTY and the tile is run again.
-            if (lane == 0) { atomicExch(&P.tile_state[item], ST_RUNNING); __threadfence(); }
+            if (lane == 0) {
+                atomicExch(&P.tile_state[item], ST_RUNNING);
+                if (P.windowed) atomicExch(&P.tile_prio[item], PRIO_INF);
+                __threadfence();
+            }
         }
         __syncwarp();
         const long long tc1 = clock64();
@@ -371,7 +429,7 @@ __global__ void __launch_bounds__(WARPS * 32) solve2d_kernel(Problem2D<real> P) 
                     mask |= (l > v ? bit >> 1 : 0u) | (r > v ? bit << 1 : 0u);   // only neighbours that can still improve
                     up_msg = u > v ? bit : 0u;
                     dn_msg = d > v ? bit : 0u;
-                    if (BEST) vmin = v < vmin ? v : vmin;
+                    if (BEST || P.windowed) vmin = v < vmin ? v : vmin;
                 }
             }
             unsigned from_below = __shfl_down_sync(FULL, up_msg, 1);   // row+1 improved and my cell above it is larger
@@ -417,7 +475,7 @@ __global__ void __launch_bounds__(WARPS * 32) solve2d_kernel(Problem2D<real> P) 
         if (__any_sync(FULL, nt) && ty > 0) act |= 4u;
         if (__any_sync(FULL, nb) && ty < P.nty - 1) act |= 8u;
         unsigned long long pbits = PRIO_INF;
-        if (BEST) {     // priority handed to the neighbours: the lowest value this visit produced
+        if (BEST || P.windowed) {     // priority handed to the neighbours: the lowest value this visit produced
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) { const real ov = __shfl_xor_sync(FULL, vmin, o); vmin = ov < vmin ? ov : vmin; }
             pbits = (unsigned long long)__double_as_longlong((double)vmin);
@@ -428,7 +486,7 @@ __global__ void __launch_bounds__(WARPS * 32) solve2d_kernel(Problem2D<real> P) 
         // instruction, so the common case costs one atomic round trip instead of five.
         const int nact = __popc(act);
         if (lane == 0 && nact) atomicAdd(&P.q.ctl->pending, nact);
-        if (BEST && lane < 4 && ((act >> lane) & 1u))
+        if ((BEST || P.windowed) && lane < 4 && ((act >> lane) & 1u))
             atomicMin(&P.tile_prio[item + (lane == 0 ? -1 : lane == 1 ? 1 : lane == 2 ? -P.ntx : P.ntx)], pbits);
         __threadfence();          // T stores (+ pending, priorities) are device-visible ...
         __syncwarp();             // ... before any state transition is published
@@ -450,7 +508,11 @@ __global__ void __launch_bounds__(WARPS * 32) solve2d_kernel(Problem2D<real> P) 
                         old = atomicCAS(st, ST_IDLE, ST_QUEUED);
                     }
                 }
-                if (newly || requeue) { q_push(P.q, BEST ? q : tgt); pushed = true; }
+                if (newly || requeue) {
+                    if (!BEST && P.windowed) win_count_push<real>(P, tgt);
+                    q_push(P.q, BEST ? q : tgt);
+                    pushed = true;
+                }
             }
         }
         const int n_new = __popc(__ballot_sync(FULL, newly));
@@ -478,6 +540,7 @@ __global__ void __launch_bounds__(WARPS * 32) solve2d_kernel(Problem2D<real> P) 
         atomicAdd(&P.q.ctl->evals, n_evals);
         atomicAdd(&P.q.ctl->pushes, n_pushes);
         atomicAdd(&P.q.ctl->cells_written, n_written);
+        if (n_defer) atomicAdd(&P.q.ctl->pad[0], n_defer);
     }
 }
 

@@ -47,4 +47,4 @@ for cfg in configs:
                       "cyc_load/visit": round(best["cyc_load"] / max(1, best["tile_visits"])),
                       "cyc_store/visit": round(best["cyc_store"] / max(1, best["tile_visits"])),
                       "phase%": {k: round(100 * best["cyc_" + k] / tot, 1) for k in ("wait", "load", "relax", "store")},
-                      "consistent": same}), flush=True)
+                      "deferrals": best.get("deferrals", 0), "consistent": same}), flush=True)

@@ -38,6 +38,11 @@ int run2d(const real *cost, long long cost_qstride, real *T, int rows, int cols,
     P.tile_prio = prio.data();
     P.best_first = getenv("FMB_BEST_FIRST") ? atoi(getenv("FMB_BEST_FIRST")) : 0;
     P.arm_rows = 0;
+    std::vector<int> lev_count(fmb::WIN_LEVELS), tile_level(ntiles);
+    int win_hint = 0; double win_inv_delta = 1.0;
+    P.windowed = (!P.best_first && nq == 1 && getenv("FMB_WINDOWED")) ? atoi(getenv("FMB_WINDOWED")) : 0;
+    P.win_window = getenv("FMB_WINDOW") ? atoi(getenv("FMB_WINDOW")) : 16;
+    P.lev_count = lev_count.data(); P.tile_level = tile_level.data(); P.win_hint = &win_hint; P.win_inv_delta = &win_inv_delta;
     emu::launch(2, 64, 0, [&] { fmb::init_fill2d_kernel<real>(P, (int)ring.size()); });
     emu::launch(1, 32 * ((nq + 31) / 32), 0, [&] { fmb::init_seed2d_kernel<real, TW>(P); });
     if (P.best_first) emu::launch(nblocks, WARPS * 32, fmb::Tile2D<real, TW>::WARP_BYTES * WARPS, [&] { fmb::solve2d_kernel<real, TW, WARPS, true>(P); });
@@ -140,7 +145,8 @@ int emu_resolve2d_f64(const double *cost, double *T, int rows, int cols, const i
     std::vector<unsigned long long> prio(ntiles);
     fmb::QueueCtl ctl;
     P.tile_state = state.data(); P.q.ctl = &ctl; P.q.ring = ring.data(); P.q.ring_mask = (unsigned)ring.size() - 1;
-    P.q.watchdog_cycles = 1LL << 40; P.step_cap = 1 << 20; P.tile_prio = prio.data(); P.best_first = 0; P.arm_rows = halo_rows;
+    P.q.watchdog_cycles = 1LL << 40; P.step_cap = 1 << 20; P.tile_prio = prio.data(); P.best_first = 0; P.arm_rows = halo_rows; P.windowed = 0; P.win_window = 0;
+    P.lev_count = nullptr; P.tile_level = nullptr; P.win_hint = nullptr; P.win_inv_delta = nullptr;
     emu::launch(2, 64, 0, [&] { fmb::init_resume2d_kernel<double>(P, (int)ring.size()); });
     if (activate & 7) emu::launch((unsigned)((ntiles + 63) / 64), 64, 0, [&] { fmb::activate_rows2d_kernel<double>(P, activate); });
     emu::launch(1, 32, 0, [&] { fmb::init_seed2d_kernel<double, TW>(P); });
