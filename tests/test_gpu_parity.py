@@ -170,6 +170,48 @@ def test_best_first_and_fifo_agree(eng, monkeypatch):
         assert rel_err(outs[0][q], ref) < TOL64 and rel_err(outs[1][q], ref) < TOL64
 
 
+@pytest.mark.parametrize("window", ["1", "2", "8"])
+def test_windowed_order_reaches_the_same_field(eng, window, monkeypatch):
+    """Windowed FIFO (deferral of tiles far above the lowest queued level; the default for one map of
+    >= 16384 tiles) forced on for smaller maps: same fixed point as the oracle, whatever the window."""
+    from oracle import oracle as O
+    from planning_motion_planning_b200 import synth
+    monkeypatch.setenv("FMB_WINDOWED", "1")
+    monkeypatch.setenv("FMB_WINDOW", window)
+    for c, g in ((rand_map((257, 300), 3), [290, 3]), (plateau_map(400, 2), [8, 8]), (synth.mars_costmap(768, 4), None)):
+        if g is None:
+            g = list(synth.free_cell_near(c, 100, 650))
+        T = _gpu2d(eng, c, [g])[0]
+        assert rel_err(T, O.computeTmap(c, g)) < TOL64
+    assert eng.last_stats()["deferrals"] >= 0
+
+
+def test_concurrent_solves_on_separate_streams(eng):
+    """Three independent queries in flight on their own streams (what bench.py does): each lane has its
+    own workspace, the results equal the one-at-a-time results bit for bit in their inf pattern and to
+    rounding in value (iteration order differs run to run)."""
+    import torch
+    from planning_motion_planning_b200 import synth
+    c = synth.mars_costmap(2048, 5)
+    cd = torch.from_numpy(c).cuda()
+    goals = [list(synth.free_cell_near(c, 300, 300)), list(synth.free_cell_near(c, 1700, 400)), list(synth.free_cell_near(c, 1000, 1800))]
+    serial = [eng.solve2d(cd, [g]).clone() for g in goals]
+    streams = [torch.cuda.Stream() for _ in goals]
+    outs = [torch.empty((1, 2048, 2048), dtype=torch.float64, device="cuda") for _ in goals]
+    torch.cuda.synchronize()
+    for rep in range(3):
+        for s, g, o in zip(streams, goals, outs):
+            with torch.cuda.stream(s):
+                eng.solve2d(cd, [g], out=o, sync=False)
+        for s in streams:
+            with torch.cuda.stream(s):
+                eng.finish()
+        for a, b in zip(serial, outs):
+            fin = torch.isfinite(a)
+            assert torch.equal(fin, torch.isfinite(b))
+            assert float(((a - b).abs() / a.clamp_min(1e-300))[fin].max()) < 1e-12
+
+
 def test_batch_api_single_rank(eng):
     from oracle import oracle as O
     from planning_motion_planning_b200 import batch, synth

@@ -235,3 +235,16 @@ def test_tie_order_sweep_matches_reference_pop_order():
         r = emu.tie_order2d(T, c, s)
         mine = np.argsort(r.ravel(), kind="stable")[1:1 + len(order)]
         assert int((mine != order).sum()) <= max_bad
+
+
+@pytest.mark.parametrize("window", ["1", "4"])
+def test_windowed_order_under_the_emulator(window, monkeypatch):
+    """solve2d_kernel with the windowed FIFO order (per-level counters, deferral) == oracle."""
+    monkeypatch.setenv("FMB_WINDOWED", "1")
+    monkeypatch.setenv("FMB_WINDOW", window)
+    for c, g in ((rand_map((130, 170), 5), [160, 5]), (plateau_map(160, 2), [8, 8])):
+        T, st = emu.solve2d(c, [g], nblocks=3)
+        ref = O.computeTmap(c, g)
+        fin = np.isfinite(ref)
+        assert np.array_equal(np.isfinite(T[0]), fin)
+        assert np.max(np.abs(T[0][fin] - ref[fin]) / np.maximum(ref[fin], 1e-300)) < 1e-12
