@@ -551,7 +551,7 @@ def own_arm(args):
             torch.cuda.synchronize()
             cts.append(e0.elapsed_time(e1))
         cms = float(np.median(cts))
-        cmap = {"workload": f"{n}x{n} crater DEM (seed 1, resolution {res_c}) -> planner cost map, 26 kernel launches",
+        cmap = {"workload": f"{n}x{n} crater DEM (seed 1, resolution {res_c}) -> planner cost map, 31 kernel launches",
                 "ms": cms, "cells_per_s": cells / (cms * 1e-3),
                 "roofline_frac": (2 * 8 * cells / (cms * 1e-3) / 1e9) / peak,
                 "algorithmic_bytes": "read DEM once + write cost once = 16 B per cell"}

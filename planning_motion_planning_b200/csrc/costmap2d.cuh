@@ -7,7 +7,7 @@
 // scipy.ndimage.distance_transform_edt and a 2500-tap scipy.signal.convolve2d.  Here:
 //   * every erosion / dilation by the reference's digital disk {di^2 + dj^2 <= r^2} is a threshold
 //     on an exact squared Euclidean distance (dilate: a set pixel within r; erode: no clear pixel
-//     within r), computed by a bounded vertical scan + a bounded horizontal scan -- bit-identical
+//     within r), computed by a vertical scan (64-row segment summaries) + a bounded horizontal scan -- bit-identical
 //     to cv2 including its border rule (outside counts as set for erode, clear for dilate);
 //   * image_filling (flood fill from pixel (0,0), then OR of the unreached zeros) is a
 //     union-find labelling of the zero pixels (row runs pre-linked by ballot, vertical links by
@@ -125,19 +125,6 @@ __global__ void cm_fill_apply_kernel(const unsigned char *im, int n, const int *
 }
 
 // ---- erosion / dilation by a disk, exact EDT -----------------------------------------------------
-// vertical distance to the nearest pixel equal to `fv` in the same column, looked for within `cap` rows
-__global__ void cm_vscan_bounded_kernel(const unsigned char *im, int fv, int n, int cap, int *g) {
-    CM_GRID_STRIDE(i, (long long)n * n) {
-        const int y = (int)(i / n);
-        int d = CM_FAR;
-        if (im[i] == fv) d = 0;
-        else
-            for (int k = 1; k <= cap; ++k) {
-                if ((y - k >= 0 && im[i - (long long)k * n] == fv) || (y + k < n && im[i + (long long)k * n] == fv)) { d = k; break; }
-            }
-        g[i] = d;
-    }
-}
 // out = 1 where a pixel equal to `fv` lies within Euclidean distance r (dilate: fv = 1, on_hit = 1),
 // out = 0 where one does (erode: fv = 0, on_hit = 0)
 __global__ void cm_hscan_threshold_kernel(const int *g, int n, int r, int on_hit, unsigned char *out) {

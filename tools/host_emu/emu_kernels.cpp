@@ -169,8 +169,13 @@ int emu_costmap2d_f64(const double *dem, const double *grid, int n, double resol
         emu::launch(G, T, 0, [&] { fmb::cm_link_kernel(im, n, lab.data()); });
         emu::launch(G, T, 0, [&] { fmb::cm_fill_apply_kernel(im, n, lab.data(), im); });
     };
+    std::vector<int> seg_first((size_t)((n + fmb::CM_SEG - 1) / fmb::CM_SEG) * n), seg_last(seg_first.size());
+    auto vscan = [&](const unsigned char *src, int fv) {
+        emu::launch(G, T, 0, [&] { fmb::cm_vseg_kernel(src, fv, n, seg_first.data(), seg_last.data()); });
+        emu::launch(G, T, 0, [&] { fmb::cm_vscan_full_kernel(src, fv, n, seg_first.data(), seg_last.data(), g.data()); });
+    };
     auto morph = [&](const unsigned char *src, unsigned char *dst, int r, bool dilate) {
-        emu::launch(G, T, 0, [&] { fmb::cm_vscan_bounded_kernel(src, dilate ? 1 : 0, n, r, g.data()); });
+        vscan(src, dilate ? 1 : 0);
         emu::launch(G, T, 0, [&] { fmb::cm_hscan_threshold_kernel(g.data(), n, r, dilate ? 1 : 0, dst); });
     };
     emu::launch(1, 32, 0, [&] { fmb::cm_init_ctl_kernel(&ctl); });
@@ -185,9 +190,7 @@ int emu_costmap2d_f64(const double *dem, const double *grid, int n, double resol
     emu::launch(1, 64, 0, [&] { fmb::cm_set_border_kernel(A.data(), n, 1); });
     if (obst) memcpy(obst, A.data(), nn);
     morph(A.data(), B.data(), r_expand, true);
-    std::vector<int> seg_first((size_t)((n + fmb::CM_SEG - 1) / fmb::CM_SEG) * n), seg_last(seg_first.size());
-    emu::launch(G, T, 0, [&] { fmb::cm_vseg_kernel(A.data(), 1, n, seg_first.data(), seg_last.data()); });
-    emu::launch(G, T, 0, [&] { fmb::cm_vscan_full_kernel(A.data(), 1, n, seg_first.data(), seg_last.data(), g.data()); });
+    vscan(A.data(), 1);
     emu::launch(G, T, 0, [&] { fmb::cm_hscan_exact_kernel(g.data(), n, lab.data(), &ctl); });
     emu::launch(G, T, 0, [&] { fmb::cm_band_min_kernel(B.data(), lab.data(), n, resolution, &ctl); });
     double *p = pre ? pre : pre_own.data();
