@@ -364,7 +364,7 @@ def own_arm(args):
     try:        # DRAM bytes of one launch of this kernel on this workload, from the committed ncu capture
         tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
         if n == 4096 and args.map == "mars":
-            ent = tj["solve2d_kernel<double,32,4,false>|4096x4096 mars seed0|fifo"]
+            ent = tj["solve2d_kernel<double,32,4,false>|4096x4096 mars seed0|" + ("fifo" if os.environ.get("FMB_WINDOWED") == "0" else "windowed")]
             traffic, traffic_src = ent["dram_bytes_read"] + ent["dram_bytes_write"], ent["source"]
     except Exception:
         pass
