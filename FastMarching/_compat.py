@@ -162,12 +162,12 @@ def pop_ranks_lifo2d(T: torch.Tensor, cost: torch.Tensor, seed, max_iters: int =
 
 def _pop_ranks_lifo2d_cuda(T, cost, seed_idx: int, max_iters: int) -> torch.Tensor:
     """Device path of :func:`pop_ranks_lifo2d`.  One sort of T gives the tie groups; the order inside
-    them is then settled by ONE kernel of libfm_b200 (csrc/tiekeys.cuh, tie_sweep2d_kernel): only
+    them is then settled by ONE kernel of libfm_b200 (csrc/tiekeys.cuh, tie_sweep_kernel<2|3>): only
     strictly upwind neighbours take part in a cell's final update and they pop before the cell's
     group starts, so the fixed point of the iteration above is reached group by group in ascending T
     without iterating.  Maps with a tie group of more than 4096 cells use the iterated form."""
-    H, W = T.shape
-    n = H * W
+    shape = tuple(T.shape)
+    n = T.numel()
     dev = T.device
     flat = T.reshape(-1)
     fin = torch.isfinite(flat)
@@ -178,7 +178,7 @@ def _pop_ranks_lifo2d_cuda(T, cost, seed_idx: int, max_iters: int) -> torch.Tens
     rank[order] = torch.arange(n, dtype=torch.int32, device=dev)
     if not bool((~new_grp & torch.isfinite(ts)).any()):          # no two reached cells share a value: the sort is the pop order
         rank[~fin] = torch.iinfo(torch.int32).max
-        return rank.reshape(H, W)
+        return rank.reshape(shape)
     grp_sorted = torch.cumsum(new_grp.to(torch.int32), 0) - 1
     starts = torch.nonzero(new_grp).reshape(-1).to(torch.int32)                 # first sorted position of each group
     sizes = torch.diff(torch.cat([starts, torch.tensor([n], dtype=torch.int32, device=dev)]))
@@ -188,17 +188,31 @@ def _pop_ranks_lifo2d_cuda(T, cost, seed_idx: int, max_iters: int) -> torch.Tens
     gsize = torch.where(fin, sizes[group.long()], torch.ones_like(group)).to(torch.int32).contiguous()   # unreached cells: no re-ranking
     members = order.to(torch.int32).contiguous()
     if int(gsize.max()) > 4096:           # a degenerate map: the quadratic in-group count would dominate
-        return _pop_ranks_lifo2d_sort(T, cost, seed_idx, max_iters, group, rank)
+        if len(shape) == 2:
+            return _pop_ranks_lifo2d_sort(T, cost, seed_idx, max_iters, group, rank)
+        rank[~fin] = torch.iinfo(torch.int32).max                 # 3D: the plain sort (ties in sorted order)
+        return rank.reshape(shape)
     tau = torch.empty_like(rank)
     key = torch.empty(n, dtype=torch.int64, device=dev)
     scratch = torch.empty(2 * n + 2, dtype=torch.int32, device=dev)
     L = _capi.lib()
-    _capi.check(L.fmb_tie_order2d_f64(T.data_ptr(), cost.data_ptr(), members.data_ptr(), gstart.data_ptr(), gsize.data_ptr(),
-                                      H, W, seed_idx, rank.data_ptr(), tau.data_ptr(), key.data_ptr(), scratch.data_ptr(),
-                                      torch.cuda.current_stream().cuda_stream))
+    fn = L.fmb_tie_order2d_f64 if len(shape) == 2 else L.fmb_tie_order3d_f64
+    _capi.check(fn(T.data_ptr(), cost.data_ptr(), members.data_ptr(), gstart.data_ptr(), gsize.data_ptr(), *shape, seed_idx,
+                   rank.data_ptr(), tau.data_ptr(), key.data_ptr(), scratch.data_ptr(), torch.cuda.current_stream().cuda_stream))
     if int(scratch[-1]) != 0:
         raise RuntimeError("tie-order sweep: a dependency wait hit its safety limit")
-    return rank.reshape(H, W)
+    return rank.reshape(shape)
+
+
+def pop_ranks_lifo3d(T: torch.Tensor, cost: torch.Tensor, seed) -> torch.Tensor:
+    """3D pop ranks incl. the reference's LIFO order among equal values (FastMarching3D.py:22-33 child
+    order, :77-95 bisect_left insertion): the same ordered sweep as in 2D on the device; CPU tensors
+    (no product path uses them) get the plain stable sort."""
+    if not T.is_cuda:
+        return pop_ranks(T)
+    ny, nx, nz = T.shape
+    seed_idx = (int(seed[1]) * nx + int(seed[0])) * nz + int(seed[2])
+    return _pop_ranks_lifo2d_cuda(T.contiguous(), cost.contiguous(), seed_idx, 96)
 
 
 def _pop_ranks_lifo2d_sort(T, cost, seed_idx: int, max_iters: int, group, rank) -> torch.Tensor:

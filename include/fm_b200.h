@@ -175,6 +175,11 @@ int fmb_tie_keys2d_f64(const double *d_T, const double *d_cost, const int32_t *d
 int fmb_tie_order2d_f64(const double *d_T, const double *d_cost, const int32_t *d_members, const int32_t *d_gstart,
                         const int32_t *d_gsize, int rows, int cols, int32_t seed_index, int32_t *d_rank, int32_t *d_tau,
                         int64_t *d_key, int32_t *d_scratch, void *stream);
+/* 3D form (FastMarching3D.py:22-33 child order z-1, z+1, x-1, x+1, y+1, y-1; :77-95 the same bisect_left
+ * insertion): d_T is [ny][nx][nz], seed_index = (y*nx + x)*nz + z. */
+int fmb_tie_order3d_f64(const double *d_T, const double *d_cost, const int32_t *d_members, const int32_t *d_gstart,
+                        const int32_t *d_gsize, int ny, int nx, int nz, int32_t seed_index, int32_t *d_rank, int32_t *d_tau,
+                        int64_t *d_key, int32_t *d_scratch, void *stream);
 
 /* ---- 2D cost-map construction (the step right before the 2D solve) --------
  * Replaces Coupled_motion_planner.py:37-80 (surface_normal), :83-95 (image_filling), :97-109

@@ -10,6 +10,7 @@
 // implementation there, which the tests compare against the reference's true pop order.
 #pragma once
 #include "fm_common.cuh"
+#include "truncate.cuh"      // Grid<D>: neighbours and the local update in 2D / 3D
 
 namespace fmb {
 
@@ -74,12 +75,21 @@ __device__ __forceinline__ bool tie_wait_nonzero(const int *flag, int want_at_le
     }
     return false;
 }
-__global__ void tie_sweep2d_kernel(const double *T, const double *cost, const int *members, const int *gstart, const int *gsize,
-                                   int rows, int cols, int seed_idx, int *rank, int *tau, long long *key, int *done,
-                                   int *gcount, int *ticket, int *failed) {
+// child index (1-based position in the reference's updateNode loop) of a cell as seen from its popped
+// neighbour i (Grid<D>::nbr order).  2D (FastMarching.py:46-54): children (0,-1), (0,+1), (-1,0), (+1,0);
+// 3D (FastMarching3D.py:22-33): z-1, z+1, x-1, x+1, y+1, y-1.
+template <int D> __device__ __forceinline__ int tie_child_index(int i);
+template <> __device__ __forceinline__ int tie_child_index<2>(int i) { const int ci[4] = {4, 3, 2, 1}; return ci[i]; }
+template <> __device__ __forceinline__ int tie_child_index<3>(int i) { const int ci[6] = {4, 3, 5, 6, 2, 1}; return ci[i]; }
+
+template <int D>
+__global__ void tie_sweep_kernel(Grid<D> g, const double *T, const double *cost, const int *members, const int *gstart,
+                                 const int *gsize, int seed_idx, int *rank, int *tau, long long *key, int *done,
+                                 int *gcount, int *ticket, int *failed) {
+    constexpr int NN = Grid<D>::NN;
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
     const long long BIG = 0x7fffffffLL;
-    const long long total = (long long)rows * cols;
+    const long long total = g.size();
     const int lane = threadIdx.x & 31;
     for (;;) {
         int base = 0;
@@ -96,35 +106,29 @@ __global__ void tie_sweep2d_kernel(const double *T, const double *cost, const in
                 int cidx = 0;
                 if (c == seed_idx) best = -1;
                 else {
-                    const int y = c / cols, x = c - y * cols;
-                    const int nb[4] = {x > 0 ? c - 1 : -1, x < cols - 1 ? c + 1 : -1, y > 0 ? c - cols : -1, y < rows - 1 ? c + cols : -1};
-                    double tv[4]; long long rv[4], av[4];
+                    double tv[NN]; long long rv[NN], av[NN];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
+                    for (int i = 0; i < NN; ++i) {
                         tv[i] = INF; rv[i] = BIG; av[i] = BIG;
-                        if (nb[i] >= 0) {
-                            const double v = T[nb[i]];
+                        const long long nb = g.nbr(c, i);
+                        if (nb >= 0) {
+                            const double v = T[nb];
                             if (v < t) {                              // strictly upwind: its rank and insertion time are final before mine
-                                if (!tie_wait_nonzero(&done[nb[i]], 1)) atomicAdd(failed, 1);
-                                tv[i] = v; rv[i] = ld_volatile(&rank[nb[i]]); av[i] = ld_volatile(&tau[nb[i]]);
+                                if (!tie_wait_nonzero(&done[nb], 1)) atomicAdd(failed, 1);
+                                tv[i] = v; rv[i] = ld_volatile(&rank[nb]); av[i] = ld_volatile(&tau[nb]);
                             }
                         }
                     }
                     const double c_cost = cost[c];
                     const double limit = t * (1.0 + 1e-14);
-                    const int ci[4] = {4, 3, 2, 1};   // popped neighbour left/right/up/down => my child index in its updateNode
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
+                    for (int i = 0; i < NN; ++i) {
                         const long long ti = rv[i];
                         if (ti >= BIG || ti >= best) continue;
-                        const double l = av[0] <= ti ? tv[0] : INF, r = av[1] <= ti ? tv[1] : INF;
-                        const double u = av[2] <= ti ? tv[2] : INF, d = av[3] <= ti ? tv[3] : INF;
-                        const double a = l < r ? l : r, b = u < d ? u : d;
-                        const double m = a < b ? a : b, dd = a - b;
-                        double v;
-                        if (!(fabs(dd) <= c_cost)) v = m + c_cost;
-                        else v = 0.5 * (a + b + sqrt(2.0 * (c_cost * c_cost) - dd * dd));
-                        if (v <= limit) { best = ti; cidx = ci[i]; }
+                        double v[NN];
+#pragma unroll
+                        for (int j = 0; j < NN; ++j) v[j] = av[j] <= ti ? tv[j] : INF;
+                        if (Grid<D>::template update<double>(v, c_cost) <= limit) { best = ti; cidx = tie_child_index<D>(i); }
                     }
                 }
                 tau[c] = (int)best;

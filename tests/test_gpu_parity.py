@@ -512,6 +512,26 @@ def test_dropin_bisolve_fuzz_join_and_patterns_exact():
     assert checked >= 16
 
 
+def test_dropin_3d_early_exit_on_tie_heavy_volumes():
+    """Uniform-cost volumes are full of exactly equal T values; which of them are accepted when the
+    start pops follows the reference's LIFO order (FastMarching3D.py:77-95): identical inf pattern."""
+    import FastMarching.FastMarching3D as FM3D
+    from oracle import oracle as O
+
+    def uniform_vol(n, val):
+        c = np.full((n, n, n), val)
+        c[0] = c[-1] = np.inf
+        c[:, 0] = c[:, -1] = np.inf
+        c[:, :, 0] = c[:, :, -1] = np.inf
+        return c
+    for c, g, s in ((uniform_vol(30, 20.0), [5, 6, 7], [22, 20, 18]), (uniform_vol(30, 20.0), [15, 15, 15], [22, 15, 15]),
+                    (uniform_vol(26, 1.0), [3, 12, 20], [20, 12, 3])):
+        T = FM3D.computeTmap(c, np.uint32(g), np.uint32(s))
+        ref = O.computeTmap3D(c, g, s)
+        assert np.array_equal(np.isfinite(T), np.isfinite(ref))
+        assert rel_err(T, ref) < TOL64
+
+
 def test_dropin_errors():
     import FastMarching.FastMarching as FM
     c = rand_map((40, 40), 0)

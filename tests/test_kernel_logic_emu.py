@@ -248,3 +248,22 @@ def test_windowed_order_under_the_emulator(window, monkeypatch):
         fin = np.isfinite(ref)
         assert np.array_equal(np.isfinite(T[0]), fin)
         assert np.max(np.abs(T[0][fin] - ref[fin]) / np.maximum(ref[fin], 1e-300)) < 1e-12
+
+
+def test_tie_order_sweep_3d_matches_reference_pop_order():
+    """tie_sweep_kernel<3> under the emulator: uniform-cost volumes (where the plain sort misplaces
+    most of the cells), the planner-like arm volume and a tie-free random volume."""
+    from planning_motion_planning_b200 import synth
+
+    def uniform_vol(n, val):
+        c = np.full((n, n, n), val)
+        c[0] = c[-1] = np.inf
+        c[:, 0] = c[:, -1] = np.inf
+        c[:, :, 0] = c[:, :, -1] = np.inf
+        return c
+    c3, g3, _ = synth.arm_volume((48, 48, 28), 1)
+    for c, g in ((uniform_vol(24, 20.0), [5, 6, 7]), (uniform_vol(22, 1.0), [11, 11, 11]), (c3, list(g3)), (rand_map((16, 16, 16), 1), [4, 5, 6])):
+        F, order, _ = O.computeTmap3D(c, g, [-1, -1, -1], return_stats=True)
+        r = emu.tie_order3d(F, c, g)
+        mine = np.argsort(r.ravel(), kind="stable")[1:1 + len(order)]
+        assert int((mine != order).sum()) == 0

@@ -72,6 +72,20 @@ int run3d(const real *cost, long long cost_qstride, real *T, int ny, int nx, int
 }
 }  // namespace
 
+// csrc/tiekeys.cuh: exact LIFO pop order in one ordered sweep (2D and 3D)
+template <int D>
+static int emu_tie_order(fmb::Grid<D> g, const double *T, const double *cost, const int *members, const int *gstart,
+                         const int *gsize, int seed_idx, int *rank, int *tau) {
+    const size_t n = (size_t)g.size();
+    std::vector<long long> key(n);
+    std::vector<int> scratch(2 * n + 2, 0);
+    emu::launch(4, 64, 0, [&] {
+        fmb::tie_sweep_kernel<D>(g, T, cost, members, gstart, gsize, seed_idx, rank, tau, key.data(), scratch.data(),
+                                 scratch.data() + n, scratch.data() + 2 * n, scratch.data() + 2 * n + 1);
+    });
+    return scratch[2 * n + 1];
+}
+
 extern "C" {
 
 int emu_solve2d_f64(const double *cost, long long cost_qstride, double *T, int rows, int cols, int nq, const int *seeds,
@@ -225,17 +239,15 @@ int emu_costvolume_f64(const fmb_costvolume_desc *d, double *cmap, double *tunne
     return 0;
 }
 
-// csrc/tiekeys.cuh: exact LIFO pop order in one ordered sweep
 int emu_tie_order2d(const double *T, const double *cost, const int *members, const int *gstart, const int *gsize, int rows,
                     int cols, int seed_idx, int *rank, int *tau) {
-    const size_t n = (size_t)rows * cols;
-    std::vector<long long> key(n);
-    std::vector<int> scratch(2 * n + 2, 0);
-    emu::launch(4, 64, 0, [&] {
-        fmb::tie_sweep2d_kernel(T, cost, members, gstart, gsize, rows, cols, seed_idx, rank, tau, key.data(), scratch.data(),
-                                scratch.data() + n, scratch.data() + 2 * n, scratch.data() + 2 * n + 1);
-    });
-    return scratch[2 * n + 1];
+    fmb::Grid<2> g; g.rows = rows; g.cols = cols;
+    return emu_tie_order<2>(g, T, cost, members, gstart, gsize, seed_idx, rank, tau);
+}
+int emu_tie_order3d(const double *T, const double *cost, const int *members, const int *gstart, const int *gsize, int ny,
+                    int nx, int nz, int seed_idx, int *rank, int *tau) {
+    fmb::Grid<3> g; g.ny = ny; g.nx = nx; g.nz = nz;
+    return emu_tie_order<3>(g, T, cost, members, gstart, gsize, seed_idx, rank, tau);
 }
 
 }  // extern "C"
