@@ -124,7 +124,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.005)
+            time.sleep(0.001)
 
     def start(self):
         if self.ok:
@@ -444,11 +444,19 @@ def own_arm(args):
 
     run_e2e(2 * NF)
     finish_lanes()
+    sampler2 = ClockSampler(local if os.environ.get("CUDA_VISIBLE_DEVICES") is None else 0)
     barrier()
+    sampler2.start()
     t0 = time.perf_counter()
     run_e2e(K)
     barrier()
     e2e_s = time.perf_counter() - t0
+    clocks2 = sampler2.stop()
+    if clocks2["samples"]:            # both timed regions feed the clock record
+        allm = sampler.samples + sampler2.samples
+        clocks = {"sm_mhz": float(np.median(allm)), "sm_max_mhz": clocks["sm_max_mhz"] or clocks2["sm_max_mhz"],
+                  "reasons": sorted(set(clocks["reasons"]) | set(clocks2["reasons"])), "samples": len(allm),
+                  "samples_resident_region": clocks["samples"], "samples_e2e_region": clocks2["samples"]}
     finish_lanes()
     if world > 1:
         tt = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
