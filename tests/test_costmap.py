@@ -61,3 +61,25 @@ def test_all_obstacle_map_raises_like_the_reference():
     with pytest.raises(ValueError), np.errstate(all="ignore"):
         CO.costmap2d(Z, res, n * res)
     assert emu.costmap2d(Z, res, n * res)[4] == 0
+
+
+@pytest.mark.parametrize("n,res,seed", [(40, 0.1, 1), (70, 0.08, 2), (33, 0.12, 4), (65, 0.1, 5), (97, 0.06, 3)])
+def test_emulated_kernels_on_awkward_sizes(n, res, seed):
+    """Maps smaller than the 50x50 blur window, sizes that are not multiples of the 32-pixel run chunks
+    or the 64-row scan segments, nearly all-obstacle maps; (97, 0.06, 3) is one the reference dies on."""
+    Z = synth.crater_dem(n, res, seed, craters=1, rocks=3)
+    Z = Z + np.random.default_rng(seed).normal(0, 0.08 * res, Z.shape)
+    Z -= Z.min()
+    cost, raw, obst, pre, npos = emu.costmap2d(Z, res, n * res)
+    try:
+        with np.errstate(all="ignore"):
+            c, st = CO.costmap2d(Z, res, n * res, stages=True)
+    except ValueError:
+        assert npos == 0
+        return
+    assert npos > 0
+    assert np.array_equal(raw, st["raw"]) and np.array_equal(obst, st["obst"].astype(np.uint8))
+    assert np.array_equal(pre, st["pre_blur"].T)
+    fin = np.isfinite(c)
+    assert np.array_equal(np.isfinite(cost.T), fin)
+    assert np.max(np.abs(cost.T[fin] - c[fin]) / c[fin]) < 1e-12
