@@ -80,18 +80,9 @@ def biComputeTmap(costMap, goal, start):
     TG, TS = T[0], T[1]
     rG = _c.pop_ranks_lifo2d(TG, cd, _c.node2(goal, swap))
     rS = _c.pop_ranks_lifo2d(TS, cd, _c.node2(start, swap))
-    both = torch.isfinite(TG) & torch.isfinite(TS)
-    if not bool(both.any()):
+    k, j = _c.bi_join(rG, rS)
+    if k is None:
         raise NameError("name 'nodeJoin' is not defined")
-    big = torch.iinfo(torch.int32).max
-    m = torch.where(both, torch.maximum(rG, rS), torch.full_like(rG, big))
-    k = int(m.min())
-    cand = (m == k).reshape(-1)
-    flatG = rG.reshape(-1)
-    idx = torch.nonzero(cand).reshape(-1)
-    # G's popped node is tested first (:150-155)
-    pick = idx[flatG[idx] == k]
-    j = int(pick[0]) if pick.numel() else int(idx[0])
     cols = TG.shape[1]
     jy, jx = divmod(j, cols)
     TGt = _c.truncate(TG, cd, rG, k)

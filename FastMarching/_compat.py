@@ -263,3 +263,14 @@ def truncate(T: torch.Tensor, cost: torch.Tensor, rank: torch.Tensor, k: int) ->
                                   int(k), out.data_ptr(), scratch.data_ptr(), counters.data_ptr(), memo.data_ptr(), stream)
     _capi.check(rc)
     return out
+
+
+def bi_join(rankG: torch.Tensor, rankS: torch.Tensor):
+    """(k, flat index of the join cell) of the two fronts, or (None, None) when they never meet
+    (FastMarching.py:141-161): libfm_b200's fmb_bi_join on the int32 pop ranks."""
+    out = torch.empty(4, dtype=torch.int32, device=rankG.device)
+    _capi.check(_capi.lib().fmb_bi_join(rankG.contiguous().data_ptr(), rankS.contiguous().data_ptr(), rankG.numel(),
+                                        out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    k, j = (int(v) for v in out[:2].tolist())
+    big = torch.iinfo(torch.int32).max
+    return (None, None) if k == big else (k, j)

@@ -181,6 +181,14 @@ int fmb_tie_order3d_f64(const double *d_T, const double *d_cost, const int32_t *
                         const int32_t *d_gsize, int ny, int nx, int nz, int32_t seed_index, int32_t *d_rank, int32_t *d_tau,
                         int64_t *d_key, int32_t *d_scratch, void *stream);
 
+/* Where the two fronts of biComputeTmap meet (FastMarching.py:141-155): k = min over cells of
+ * max(rankG, rankS) = the round in which the reference's alternating loop breaks, and the join node
+ * (the cell G popped in round k if it attains the minimum -- G is tested first, :150-152 -- else S's).
+ * d_rankG / d_rankS: int32 pop ranks of the two full fields (unreached = INT32_MAX).
+ * d_out: int32[4], 8-byte aligned; on return [0] = k, [1] = flat index of the join cell (both INT32_MAX
+ * when the fronts never meet: the reference raises NameError, :161); [2..3] scratch. */
+int fmb_bi_join(const int32_t *d_rankG, const int32_t *d_rankS, int64_t total, int32_t *d_out, void *stream);
+
 /* ---- 2D cost-map construction (the step right before the 2D solve) --------
  * Replaces Coupled_motion_planner.py:37-80 (surface_normal), :83-95 (image_filling), :97-109
  * (structural_disk) and the inline pipeline of main() :1144-1216: slope obstacles from the DEM,

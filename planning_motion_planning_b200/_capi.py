@@ -59,6 +59,7 @@ SIGNATURES = {
     "fmb_tie_keys2d_f64": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "fmb_tie_order2d_f64": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "fmb_tie_order3d_f64": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "fmb_bi_join": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "fmb_workspace_bytes_costmap2d": (_sz, [_i32]),
     "fmb_costmap2d_f64": (C.c_int, [_vp, _vp, _i32, _dbl, _dbl, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "fmb_costmap2d_finish": (C.c_int, [_vp, _sz, _vp, C.POINTER(C.c_int32)]),

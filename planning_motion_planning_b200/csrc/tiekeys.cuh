@@ -157,4 +157,33 @@ __global__ void tie_sweep_kernel(Grid<D> g, const double *T, const double *cost,
     }
 }
 
+// ---- where the two fronts of biComputeTmap meet (FastMarching.py:141-155) ------------------------
+// Both fronts pop one node per round; the loop stops in the first round k in which G's node is already
+// closed in S (tested first, :150-152) or S's node is closed in G (:153-155).  With pop ranks that is
+// k = min over cells of max(rankG, rankS); the join node is the cell popped by G in round k if it
+// attains the minimum, else the one popped by S.  out[0] = k, out[1] = join cell (both INT_MAX when the
+// fronts never meet); pass 1 reduces k, pass 2 picks the cell (G's pop wins, then the smaller index).
+__global__ void bi_join_k_kernel(const int *rankG, const int *rankS, long long total, int *out) {
+    int best = 0x7fffffff;
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < total; c += (long long)gridDim.x * blockDim.x) {
+        const int a = rankG[c], b = rankS[c];
+        const int m = a > b ? a : b;
+        best = m < best ? m : best;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const int v = __shfl_xor_sync(FULL, best, o); best = v < best ? v : best; }
+    if ((threadIdx.x & 31) == 0 && best != 0x7fffffff) atomicMin(&out[0], best);
+}
+__global__ void bi_join_cell_kernel(const int *rankG, const int *rankS, long long total, int *out, unsigned long long *pick) {
+    const int k = out[0];
+    if (k == 0x7fffffff) return;
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < total; c += (long long)gridDim.x * blockDim.x) {
+        const int a = rankG[c], b = rankS[c];
+        if ((a > b ? a : b) == k) atomicMin(pick, ((unsigned long long)(a == k ? 0 : 1) << 40) | (unsigned long long)c);
+    }
+}
+__global__ void bi_join_finish_kernel(int *out, const unsigned long long *pick) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[1] = out[0] == 0x7fffffff ? 0x7fffffff : (int)(*pick & 0xffffffffffULL);
+}
+
 }  // namespace fmb

@@ -201,3 +201,14 @@ def _tie_order(F, cost, seed_idx):
                 gsize.ctypes.data_as(ip), *F.shape, seed_idx, rank.ctypes.data_as(ip), tau.ctypes.data_as(ip))
     assert failed == 0
     return rank.reshape(F.shape)
+
+
+def bi_join(rankG, rankS):
+    """Emulated fmb_bi_join: (k, flat join index) or (None, None)."""
+    rG = np.ascontiguousarray(rankG, dtype=np.int32).ravel()
+    rS = np.ascontiguousarray(rankS, dtype=np.int32).ravel()
+    out = np.zeros(2, np.int32)
+    fn = lib().emu_bi_join
+    fn.argtypes = [ip, ip, C.c_longlong, ip]
+    fn(rG.ctypes.data_as(ip), rS.ctypes.data_as(ip), rG.size, out.ctypes.data_as(ip))
+    return (None, None) if out[0] == 2**31 - 1 else (int(out[0]), int(out[1]))

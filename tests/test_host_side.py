@@ -143,6 +143,7 @@ def test_bisolve_emulation_fuzz_is_bitwise_equal_to_the_heap_loop():
         pick = [i for i in cand if rG[i] == k]
         jj = pick[0] if pick else cand[0]
         W = c.shape[1]
+        assert emu.bi_join(np.where(np.isfinite(FG).ravel(), rG, 2**31 - 1), np.where(np.isfinite(FS).ravel(), rS, 2**31 - 1)) == (k, int(jj))
         oG, _ = emu.truncate(FG, c, k, rG.astype(np.int32))
         oS, _ = emu.truncate(FS, c, k, rS.astype(np.int32))
         assert [jj % W, jj // W] == list(j), (it, kind)

@@ -250,4 +250,14 @@ int emu_tie_order3d(const double *T, const double *cost, const int *members, con
     return emu_tie_order<3>(g, T, cost, members, gstart, gsize, seed_idx, rank, tau);
 }
 
+// csrc/tiekeys.cuh: join of the two fronts (same kernel sequence as fmb_bi_join)
+int emu_bi_join(const int *rankG, const int *rankS, long long total, int *out2) {
+    alignas(8) int out[4] = {0x7fffffff, 0x7fffffff, -1, -1};
+    emu::launch(2, 64, 0, [&] { fmb::bi_join_k_kernel(rankG, rankS, total, out); });
+    emu::launch(2, 64, 0, [&] { fmb::bi_join_cell_kernel(rankG, rankS, total, out, (unsigned long long *)(out + 2)); });
+    emu::launch(1, 32, 0, [&] { fmb::bi_join_finish_kernel(out, (const unsigned long long *)(out + 2)); });
+    out2[0] = out[0]; out2[1] = out[1];
+    return 0;
+}
+
 }  // extern "C"
