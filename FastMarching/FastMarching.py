@@ -78,17 +78,19 @@ def biComputeTmap(costMap, goal, start):
     reference (:161)."""
     T, cd, swap = _solve_fields(costMap, [goal, start])
     TG, TS = T[0], T[1]
-    rG = _c.pop_ranks_lifo2d(TG, cd, _c.node2(goal, swap))
-    rS = _c.pop_ranks_lifo2d(TS, cd, _c.node2(start, swap))
+    # the two fronts are independent until they are joined: ranks (and later the truncations) of G and S
+    # run side by side on two streams
+    rG, rS = _c.both_fronts(lambda: _c.pop_ranks_lifo2d(TG, cd, _c.node2(goal, swap)),
+                            lambda: _c.pop_ranks_lifo2d(TS, cd, _c.node2(start, swap)))
     k, j = _c.bi_join(rG, rS)
     if k is None:
         raise NameError("name 'nodeJoin' is not defined")
     cols = TG.shape[1]
     jy, jx = divmod(j, cols)
-    TGt = _c.truncate(TG, cd, rG, k)
-    TSt = _c.truncate(TS, cd, rS, k)
+    TGt, TSt = _c.both_fronts(lambda: _c.truncate(TG, cd, rG, k), lambda: _c.truncate(TS, cd, rS, k))
     node = (jy, jx) if swap else (jx, jy)
-    return _to_numpy_field(TGt, swap), _to_numpy_field(TSt, swap), np.uint32(node)
+    outG, outS = _to_numpy_field(TGt, swap), _to_numpy_field(TSt, swap)      # synchronous copies: the side-stream tensors stay alive until here
+    return outG, outS, np.uint32(node)
 
 
 def getPathGDM(totalCostMap, initWaypoint, endWaypoint, tau):

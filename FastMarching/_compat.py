@@ -274,3 +274,29 @@ def bi_join(rankG: torch.Tensor, rankS: torch.Tensor):
     k, j = (int(v) for v in out[:2].tolist())
     big = torch.iinfo(torch.int32).max
     return (None, None) if k == big else (k, j)
+
+
+_SIDE = {}
+
+
+def both_fronts(fn_g, fn_s):
+    """Run the G-front and the S-front piece of biComputeTmap concurrently: each on its own CUDA
+    stream and host thread (the rank computation has host syncs; they release the GIL), joined back
+    into the current stream.  Returns (result_g, result_s)."""
+    from concurrent.futures import ThreadPoolExecutor
+    cur = torch.cuda.current_stream()
+    dev = torch.cuda.current_device()
+    if dev not in _SIDE:
+        _SIDE[dev] = (torch.cuda.Stream(), torch.cuda.Stream(), ThreadPoolExecutor(max_workers=2))
+    sa, sb, pool = _SIDE[dev]
+
+    def run(stream, fn):
+        torch.cuda.set_device(dev)
+        with torch.cuda.stream(stream):
+            stream.wait_stream(cur)
+            return fn()
+    fa, fb = pool.submit(run, sa, fn_g), pool.submit(run, sb, fn_s)
+    ra, rb = fa.result(), fb.result()
+    cur.wait_stream(sa)
+    cur.wait_stream(sb)
+    return ra, rb
