@@ -66,7 +66,7 @@ def computeTmap(costMap, goal, start):
     s = _c.node2(start, swap)
     rows, cols = T0.shape
     if 0 <= s[0] < cols and 0 <= s[1] < rows and bool(torch.isfinite(T0[s[1], s[0]])):
-        rank = _c.pop_ranks_lifo2d(T0, cd, _c.node2(goal, swap))
+        rank = _c.pop_ranks_lifo2d(T0, cd, _c.node2(goal, swap), transposed=swap)
         T0 = _c.truncate(T0, cd, rank, int(rank[s[1], s[0]]))
     return _to_numpy_field(T0, swap)
 
@@ -80,8 +80,8 @@ def biComputeTmap(costMap, goal, start):
     TG, TS = T[0], T[1]
     # the two fronts are independent until they are joined: ranks (and later the truncations) of G and S
     # run side by side on two streams
-    rG, rS = _c.both_fronts(lambda: _c.pop_ranks_lifo2d(TG, cd, _c.node2(goal, swap)),
-                            lambda: _c.pop_ranks_lifo2d(TS, cd, _c.node2(start, swap)))
+    rG, rS = _c.both_fronts(lambda: _c.pop_ranks_lifo2d(TG, cd, _c.node2(goal, swap), transposed=swap),
+                            lambda: _c.pop_ranks_lifo2d(TS, cd, _c.node2(start, swap), transposed=swap))
     k, j = _c.bi_join(rG, rS)
     if k is None:
         raise NameError("name 'nodeJoin' is not defined")

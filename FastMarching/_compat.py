@@ -88,7 +88,7 @@ def _lex_order(T, k2, k3):
     return order[torch.sort(T.reshape(-1)[order], stable=True).indices]
 
 
-def pop_ranks_lifo2d(T: torch.Tensor, cost: torch.Tensor, seed, max_iters: int = 96) -> torch.Tensor:
+def pop_ranks_lifo2d(T: torch.Tensor, cost: torch.Tensor, seed, max_iters: int = 96, transposed: bool = False) -> torch.Tensor:
     """Pop ranks of the reference's 2D front INCLUDING its order among exactly equal values.
 
     The reference keeps the narrow band sorted with bisect_left + insert (FastMarching.py:65-67,
@@ -98,6 +98,8 @@ def pop_ranks_lifo2d(T: torch.Tensor, cost: torch.Tensor, seed, max_iters: int =
     call in child order (:46-54).  So the pop order is the ascending order of
     (T, -insertion time, -child index), where insertion times depend on the ranks themselves:
     iterate to the fixed point.  Maps without exact ties return after the plain sort.
+    ``transposed``: T is the transpose of the caller's map (an F-ordered input solved as its C-ordered
+    transpose, see as_c_field); the child order is not symmetric in x and y, so it is mapped back.
     Measured against the reference's true pop order (oracle): 0 misplaced cells on every uniform,
     plateau and random map tried (the plain sort misplaces thousands on tie-heavy maps)."""
     H, W = T.shape
@@ -105,7 +107,7 @@ def pop_ranks_lifo2d(T: torch.Tensor, cost: torch.Tensor, seed, max_iters: int =
     flat = T.reshape(-1)
     seed_idx = int(seed[1]) * W + int(seed[0])
     if T.is_cuda:
-        return _pop_ranks_lifo2d_cuda(T.contiguous(), cost.contiguous(), seed_idx, max_iters)
+        return _pop_ranks_lifo2d_cuda(T.contiguous(), cost.contiguous(), seed_idx, max_iters, transposed)
     nfin = int(fin.sum())
     if nfin == int(torch.unique(flat[fin.reshape(-1)]).numel()):
         return pop_ranks(T)                                       # no ties: the sort is already exact
@@ -130,7 +132,7 @@ def pop_ranks_lifo2d(T: torch.Tensor, cost: torch.Tensor, seed, max_iters: int =
         tau_new = torch.full_like(r, _BIG)
         cidx = torch.zeros_like(r)
         inf_t = torch.full_like(T, INF)
-        for R, ci in ((RL, 4), (RR, 3), (RU, 2), (RD, 1)):        # child index w.r.t. the popped neighbour
+        for R, ci in (((RL, 2), (RR, 1), (RU, 4), (RD, 3)) if transposed else ((RL, 4), (RR, 3), (RU, 2), (RD, 1))):   # child index w.r.t. the popped neighbour
             lt = torch.where(AL <= R, TL, inf_t)
             rt = torch.where(AR <= R, TR, inf_t)
             ut = torch.where(AU <= R, TU, inf_t)
@@ -160,7 +162,7 @@ def pop_ranks_lifo2d(T: torch.Tensor, cost: torch.Tensor, seed, max_iters: int =
     return out
 
 
-def _pop_ranks_lifo2d_cuda(T, cost, seed_idx: int, max_iters: int) -> torch.Tensor:
+def _pop_ranks_lifo2d_cuda(T, cost, seed_idx: int, max_iters: int, transposed: bool = False) -> torch.Tensor:
     """Device path of :func:`pop_ranks_lifo2d`.  One sort of T gives the tie groups; the order inside
     them is then settled by ONE kernel of libfm_b200 (csrc/tiekeys.cuh, tie_sweep_kernel<2|3>): only
     strictly upwind neighbours take part in a cell's final update and they pop before the cell's
@@ -189,16 +191,20 @@ def _pop_ranks_lifo2d_cuda(T, cost, seed_idx: int, max_iters: int) -> torch.Tens
     members = order.to(torch.int32).contiguous()
     if int(gsize.max()) > 4096:           # a degenerate map: the quadratic in-group count would dominate
         if len(shape) == 2:
-            return _pop_ranks_lifo2d_sort(T, cost, seed_idx, max_iters, group, rank)
+            return _pop_ranks_lifo2d_sort(T, cost, seed_idx, max_iters, group, rank, transposed)
         rank[~fin] = torch.iinfo(torch.int32).max                 # 3D: the plain sort (ties in sorted order)
         return rank.reshape(shape)
     tau = torch.empty_like(rank)
     key = torch.empty(n, dtype=torch.int64, device=dev)
     scratch = torch.empty(2 * n + 2, dtype=torch.int32, device=dev)
     L = _capi.lib()
-    fn = L.fmb_tie_order2d_f64 if len(shape) == 2 else L.fmb_tie_order3d_f64
-    _capi.check(fn(T.data_ptr(), cost.data_ptr(), members.data_ptr(), gstart.data_ptr(), gsize.data_ptr(), *shape, seed_idx,
-                   rank.data_ptr(), tau.data_ptr(), key.data_ptr(), scratch.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    tail = (rank.data_ptr(), tau.data_ptr(), key.data_ptr(), scratch.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    if len(shape) == 2:
+        _capi.check(L.fmb_tie_order2d_f64(T.data_ptr(), cost.data_ptr(), members.data_ptr(), gstart.data_ptr(), gsize.data_ptr(),
+                                          *shape, seed_idx, int(bool(transposed)), *tail))
+    else:
+        _capi.check(L.fmb_tie_order3d_f64(T.data_ptr(), cost.data_ptr(), members.data_ptr(), gstart.data_ptr(), gsize.data_ptr(),
+                                          *shape, seed_idx, *tail))
     if int(scratch[-1]) != 0:
         raise RuntimeError("tie-order sweep: a dependency wait hit its safety limit")
     return rank.reshape(shape)
@@ -215,7 +221,7 @@ def pop_ranks_lifo3d(T: torch.Tensor, cost: torch.Tensor, seed) -> torch.Tensor:
     return _pop_ranks_lifo2d_cuda(T.contiguous(), cost.contiguous(), seed_idx, 96)
 
 
-def _pop_ranks_lifo2d_sort(T, cost, seed_idx: int, max_iters: int, group, rank) -> torch.Tensor:
+def _pop_ranks_lifo2d_sort(T, cost, seed_idx: int, max_iters: int, group, rank, transposed: bool = False) -> torch.Tensor:
     """Fallback of the device path for maps with a huge tie group: one global stable sort per step."""
     H, W = T.shape
     n = H * W
@@ -229,7 +235,7 @@ def _pop_ranks_lifo2d_sort(T, cost, seed_idx: int, max_iters: int, group, rank) 
     stream = torch.cuda.current_stream().cuda_stream
     for it in range(max_iters):
         _capi.check(L.fmb_tie_keys2d_f64(T.data_ptr(), cost.data_ptr(), rank.data_ptr(), tau.data_ptr(), group.data_ptr(),
-                                         H, W, seed_idx, tau_new.data_ptr(), key.data_ptr(), stream))
+                                         H, W, seed_idx, int(bool(transposed)), tau_new.data_ptr(), key.data_ptr(), stream))
         order = torch.sort(key, stable=True).indices
         new_rank = torch.empty_like(rank)
         new_rank[order] = ar

@@ -163,7 +163,7 @@ int fmb_truncate3d_f64(const double *d_F, const double *d_cost, const int32_t *d
  * every cell (dense rank of its T value); outputs the new insertion times and a packed 64-bit key
  * whose ascending stable sort gives the next ranks.  Iterated to a fixed point by the caller. */
 int fmb_tie_keys2d_f64(const double *d_T, const double *d_cost, const int32_t *d_rank, const int32_t *d_tau,
-                       const int32_t *d_group, int rows, int cols, int32_t seed_index,
+                       const int32_t *d_group, int rows, int cols, int32_t seed_index, int32_t transposed,
                        int32_t *d_tau_new, int64_t *d_key, void *stream);
 /* The same order in ONE launch, without iteration: only strictly upwind neighbours (smaller T) take part
  * in a cell's final update and they pop before the cell's tie group starts, so insertion times and
@@ -171,10 +171,12 @@ int fmb_tie_keys2d_f64(const double *d_T, const double *d_cost, const int32_t *d
  * d_members lists the cells in ascending T (stable), d_gstart / d_gsize give every cell the slice of its
  * tie group in that list (size 1 for unreached cells; groups larger than 4096 cells are the caller's cue to
  * use the iterated form); outputs d_rank (unreached = INT32_MAX) and d_tau; d_key: int64 scratch per cell;
- * d_scratch: 2*rows*cols + 2 int32, on return its last entry counts waits that hit the safety limit. */
+ * d_scratch: 2*rows*cols + 2 int32, on return its last entry counts waits that hit the safety limit.
+ * transposed != 0: d_T is the transpose of the caller's map (an F-ordered input solved as its C-ordered
+ * transpose); the child order of updateNode (FastMarching.py:46-54) is not symmetric in x and y. */
 int fmb_tie_order2d_f64(const double *d_T, const double *d_cost, const int32_t *d_members, const int32_t *d_gstart,
-                        const int32_t *d_gsize, int rows, int cols, int32_t seed_index, int32_t *d_rank, int32_t *d_tau,
-                        int64_t *d_key, int32_t *d_scratch, void *stream);
+                        const int32_t *d_gsize, int rows, int cols, int32_t seed_index, int32_t transposed, int32_t *d_rank,
+                        int32_t *d_tau, int64_t *d_key, int32_t *d_scratch, void *stream);
 /* 3D form (FastMarching3D.py:22-33 child order z-1, z+1, x-1, x+1, y+1, y-1; :77-95 the same bisect_left
  * insertion): d_T is [ny][nx][nz], seed_index = (y*nx + x)*nz + z. */
 int fmb_tie_order3d_f64(const double *d_T, const double *d_cost, const int32_t *d_members, const int32_t *d_gstart,

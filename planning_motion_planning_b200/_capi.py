@@ -56,8 +56,8 @@ SIGNATURES = {
     "fmb_trace3d_f64": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _dbl, _i32, _vp, _i64, _vp, _vp, _vp]),
     "fmb_truncate2d_f64": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "fmb_truncate3d_f64": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
-    "fmb_tie_keys2d_f64": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
-    "fmb_tie_order2d_f64": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "fmb_tie_keys2d_f64": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "fmb_tie_order2d_f64": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "fmb_tie_order3d_f64": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "fmb_bi_join": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "fmb_workspace_bytes_costmap2d": (_sz, [_i32]),

@@ -15,7 +15,7 @@
 namespace fmb {
 
 __global__ void tie_keys2d_kernel(const double *T, const double *cost, const int *rank, const int *tau, const int *group,
-                                  int rows, int cols, int seed_idx, int *tau_new, long long *key) {
+                                  int rows, int cols, int seed_idx, int transposed, int *tau_new, long long *key) {
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
     const long long BIG = 0x7fffffffLL;
     const long long total = (long long)rows * cols;
@@ -39,7 +39,9 @@ __global__ void tie_keys2d_kernel(const double *T, const double *cost, const int
         const double c_cost = cost[c];
         const double limit = t * (1.0 + 1e-14);               // the solver's field is a fixed point to a few ulp
         long long best = BIG; int cidx = 0;
-        const int ci[4] = {4, 3, 2, 1};          // popped neighbour left/right/up/down => my child index in its updateNode
+        // popped neighbour left/right/up/down => my child index in its updateNode; when the map is the
+        // transpose of the caller's (F-ordered input), left/right are the caller's up/down
+        const int ci[4] = {transposed ? 2 : 4, transposed ? 1 : 3, transposed ? 4 : 2, transposed ? 3 : 1};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const long long ti = rv[i];
@@ -78,13 +80,18 @@ __device__ __forceinline__ bool tie_wait_nonzero(const int *flag, int want_at_le
 // child index (1-based position in the reference's updateNode loop) of a cell as seen from its popped
 // neighbour i (Grid<D>::nbr order).  2D (FastMarching.py:46-54): children (0,-1), (0,+1), (-1,0), (+1,0);
 // 3D (FastMarching3D.py:22-33): z-1, z+1, x-1, x+1, y+1, y-1.
-template <int D> __device__ __forceinline__ int tie_child_index(int i);
-template <> __device__ __forceinline__ int tie_child_index<2>(int i) { const int ci[4] = {4, 3, 2, 1}; return ci[i]; }
-template <> __device__ __forceinline__ int tie_child_index<3>(int i) { const int ci[6] = {4, 3, 5, 6, 2, 1}; return ci[i]; }
+// `transposed` (2D only): the field is the transpose of the caller's map (an F-ordered input solved as its
+// C-ordered transpose), so this grid's x-neighbours are the caller's y-neighbours.
+template <int D> __device__ __forceinline__ int tie_child_index(int i, int transposed);
+template <> __device__ __forceinline__ int tie_child_index<2>(int i, int transposed) {
+    const int ci[4] = {4, 3, 2, 1}, ct[4] = {2, 1, 4, 3};
+    return transposed ? ct[i] : ci[i];
+}
+template <> __device__ __forceinline__ int tie_child_index<3>(int i, int) { const int ci[6] = {4, 3, 5, 6, 2, 1}; return ci[i]; }
 
 template <int D>
 __global__ void tie_sweep_kernel(Grid<D> g, const double *T, const double *cost, const int *members, const int *gstart,
-                                 const int *gsize, int seed_idx, int *rank, int *tau, long long *key, int *done,
+                                 const int *gsize, int seed_idx, int transposed, int *rank, int *tau, long long *key, int *done,
                                  int *gcount, int *ticket, int *failed) {
     constexpr int NN = Grid<D>::NN;
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
@@ -128,7 +135,7 @@ __global__ void tie_sweep_kernel(Grid<D> g, const double *T, const double *cost,
                         double v[NN];
 #pragma unroll
                         for (int j = 0; j < NN; ++j) v[j] = av[j] <= ti ? tv[j] : INF;
-                        if (Grid<D>::template update<double>(v, c_cost) <= limit) { best = ti; cidx = tie_child_index<D>(i); }
+                        if (Grid<D>::template update<double>(v, c_cost) <= limit) { best = ti; cidx = tie_child_index<D>(i, transposed); }
                     }
                 }
                 tau[c] = (int)best;

@@ -176,9 +176,9 @@ def tie_groups(F):
     return order.astype(np.int32), gstart, gsize
 
 
-def tie_order2d(F, cost, seed):
+def tie_order2d(F, cost, seed, transposed=False):
     """Emulated tie_sweep_kernel<2>: int32 pop ranks incl. the LIFO order among equal values."""
-    return _tie_order(F, cost, int(seed[1]) * F.shape[1] + int(seed[0]))
+    return _tie_order(F, cost, int(seed[1]) * F.shape[1] + int(seed[0]), transposed)
 
 
 def tie_order3d(F, cost, seed):
@@ -186,19 +186,21 @@ def tie_order3d(F, cost, seed):
     return _tie_order(F, cost, (int(seed[1]) * F.shape[1] + int(seed[0])) * F.shape[2] + int(seed[2]))
 
 
-def _tie_order(F, cost, seed_idx):
+def _tie_order(F, cost, seed_idx, transposed=False):
     F = np.ascontiguousarray(F, dtype=np.float64)
     cost = np.ascontiguousarray(cost, dtype=np.float64)
     members, gstart, gsize = tie_groups(F)
     rank, tau = np.empty(F.size, np.int32), np.empty(F.size, np.int32)
     if F.ndim == 2:
         fn = lib().emu_tie_order2d
-        fn.argtypes = [dp, dp, ip, ip, ip, C.c_int, C.c_int, C.c_int, ip, ip]
+        fn.argtypes = [dp, dp, ip, ip, ip, C.c_int, C.c_int, C.c_int, C.c_int, ip, ip]
+        extra = (int(bool(transposed)),)
     else:
+        extra = ()
         fn = lib().emu_tie_order3d
         fn.argtypes = [dp, dp, ip, ip, ip, C.c_int, C.c_int, C.c_int, C.c_int, ip, ip]
     failed = fn(F.ctypes.data_as(dp), cost.ctypes.data_as(dp), members.ctypes.data_as(ip), gstart.ctypes.data_as(ip),
-                gsize.ctypes.data_as(ip), *F.shape, seed_idx, rank.ctypes.data_as(ip), tau.ctypes.data_as(ip))
+                gsize.ctypes.data_as(ip), *F.shape, seed_idx, *extra, rank.ctypes.data_as(ip), tau.ctypes.data_as(ip))
     assert failed == 0
     return rank.reshape(F.shape)
 

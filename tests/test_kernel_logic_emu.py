@@ -267,3 +267,22 @@ def test_tie_order_sweep_3d_matches_reference_pop_order():
         r = emu.tie_order3d(F, c, g)
         mine = np.argsort(r.ravel(), kind="stable")[1:1 + len(order)]
         assert int((mine != order).sum()) == 0
+
+
+def test_tie_order_of_a_transposed_field_follows_the_callers_orientation():
+    """An F-ordered input is solved as its C-ordered transpose; the child order of updateNode
+    (FastMarching.py:46-54) is not symmetric in x and y, so the tie order must be mapped back."""
+    import torch
+    from FastMarching import _compat
+    uniform = np.pad(np.full((60, 60), 3.0), 1, constant_values=np.inf)
+    uniform[30, 8:25] = np.inf
+    for c, s in ((uniform, [18, 40]), (plateau_map(96, 7), [70, 66])):
+        T, order, _ = O.computeTmap(c, s, return_stats=True)
+        ct, Tt, st = np.ascontiguousarray(c.T), np.ascontiguousarray(T.T), s[::-1]
+        H, W = c.shape
+        for ranks in (emu.tie_order2d(Tt, ct, st, transposed=True),
+                      _compat.pop_ranks_lifo2d(torch.from_numpy(Tt), torch.from_numpy(ct), st, transposed=True).numpy()):
+            mt = np.argsort(ranks.ravel(), kind="stable")[1:1 + len(order)]
+            assert int((((mt % H) * W + mt // H) != order).sum()) == 0
+        wrong = np.argsort(emu.tie_order2d(Tt, ct, st).ravel(), kind="stable")[1:1 + len(order)]
+        assert int((((wrong % H) * W + wrong // H) != order).sum()) > 100          # the flag matters

@@ -75,12 +75,12 @@ int run3d(const real *cost, long long cost_qstride, real *T, int ny, int nx, int
 // csrc/tiekeys.cuh: exact LIFO pop order in one ordered sweep (2D and 3D)
 template <int D>
 static int emu_tie_order(fmb::Grid<D> g, const double *T, const double *cost, const int *members, const int *gstart,
-                         const int *gsize, int seed_idx, int *rank, int *tau) {
+                         const int *gsize, int seed_idx, int transposed, int *rank, int *tau) {
     const size_t n = (size_t)g.size();
     std::vector<long long> key(n);
     std::vector<int> scratch(2 * n + 2, 0);
     emu::launch(4, 64, 0, [&] {
-        fmb::tie_sweep_kernel<D>(g, T, cost, members, gstart, gsize, seed_idx, rank, tau, key.data(), scratch.data(),
+        fmb::tie_sweep_kernel<D>(g, T, cost, members, gstart, gsize, seed_idx, transposed, rank, tau, key.data(), scratch.data(),
                                  scratch.data() + n, scratch.data() + 2 * n, scratch.data() + 2 * n + 1);
     });
     return scratch[2 * n + 1];
@@ -240,14 +240,14 @@ int emu_costvolume_f64(const fmb_costvolume_desc *d, double *cmap, double *tunne
 }
 
 int emu_tie_order2d(const double *T, const double *cost, const int *members, const int *gstart, const int *gsize, int rows,
-                    int cols, int seed_idx, int *rank, int *tau) {
+                    int cols, int seed_idx, int transposed, int *rank, int *tau) {
     fmb::Grid<2> g; g.rows = rows; g.cols = cols;
-    return emu_tie_order<2>(g, T, cost, members, gstart, gsize, seed_idx, rank, tau);
+    return emu_tie_order<2>(g, T, cost, members, gstart, gsize, seed_idx, transposed, rank, tau);
 }
 int emu_tie_order3d(const double *T, const double *cost, const int *members, const int *gstart, const int *gsize, int ny,
                     int nx, int nz, int seed_idx, int *rank, int *tau) {
     fmb::Grid<3> g; g.ny = ny; g.nx = nx; g.nz = nz;
-    return emu_tie_order<3>(g, T, cost, members, gstart, gsize, seed_idx, rank, tau);
+    return emu_tie_order<3>(g, T, cost, members, gstart, gsize, seed_idx, 0, rank, tau);
 }
 
 // csrc/tiekeys.cuh: join of the two fronts (same kernel sequence as fmb_bi_join)
