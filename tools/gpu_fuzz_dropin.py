@@ -12,6 +12,7 @@ from oracle import oracle as O
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
 bad = checked = 0
+paths_checked = [0]
 worst = 0.0
 t0 = time.time()
 for it in range(N):
@@ -63,9 +64,33 @@ for it in range(N):
             for a, b in ((TG, oTG), (TS, oTS)):
                 f = np.isfinite(b)
                 e = max(e, float(np.max(np.abs(np.asarray(a)[f] - b[f]) / np.maximum(b[f], 1.0))))
+            # single-front early exit (intended semantics of the reference's broken computeTmap)
+            T1, o1 = FM.computeTmap(c, g, s), O.computeTmap(np.ascontiguousarray(c), g, s)
+            ok = ok and np.array_equal(np.isfinite(T1), np.isfinite(o1))
+            f = np.isfinite(o1)
+            e = max(e, float(np.max(np.abs(np.asarray(T1)[f] - o1[f]) / np.maximum(o1[f], 1.0))))
+            # the two half paths from the join node over the partial fields, incl. the failure modes
+            for Tm, oTm, endp in ((TG, oTG, g), (TS, oTS, s)):
+                try:
+                    po, so = O.getPathGDM(oTm, np.array(oj, dtype=np.float64), endp, 0.5, return_status=True)
+                except Exception as ex:      # noqa: BLE001
+                    po, so = None, type(ex).__name__
+                try:
+                    pg = FM.getPathGDM(Tm, j, endp, 0.5)
+                    sg = 0
+                except Exception as ex:      # noqa: BLE001
+                    pg, sg = None, type(ex).__name__
+                if isinstance(so, int) and so in (2, 3, 4):
+                    ok = ok and sg == {2: "ValueError", 3: "IndexError", 4: "OverflowError"}[so]
+                elif pg is None or po is None or pg.shape != po.shape:
+                    ok = False
+                else:
+                    pe = float(np.max(np.abs(pg - po))) if len(po) else 0.0
+                    ok = ok and pe < 1e-3
+                    paths_checked[0] += 1
     checked += 1
     worst = max(worst, e)
     if not ok or e > 1e-9:
         bad += 1
         print("MISMATCH case", it, "kind", kind, "shape", c.shape, "goal", g, "start", s, "ok", ok, "err", e, flush=True)
-print(f"cases {checked} bad {bad} worst rel err {worst:.2e} in {time.time() - t0:.1f} s")
+print(f"cases {checked} bad {bad} worst rel err {worst:.2e} paths compared {paths_checked[0]} in {time.time() - t0:.1f} s")
