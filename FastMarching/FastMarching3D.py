@@ -33,9 +33,10 @@ def computeTmap(costMap, goal, start):
     s = [int(np.int64(v)) for v in start]
     if 0 <= s[0] < nx and 0 <= s[1] < ny and 0 <= s[2] < nz and bool(torch.isfinite(T[s[1], s[0], s[2]])):
         # Only the order INSIDE the tie group of `start` decides which cells are accepted when it pops:
-        # the plain sort is exact unless another cell carries exactly T[start]; then the reference's LIFO
+        # the plain sort is exact unless another cell carries T[start] (to the tolerance of the device field); then the reference's LIFO
         # order among equal values is reproduced by the ordered sweep (csrc/tiekeys.cuh).
-        if int((T == T[s[1], s[0], s[2]]).sum()) > 1:
+        Ts = T[s[1], s[0], s[2]]
+        if int(((T - Ts).abs() <= _c.TIE_TOL_3D * Ts).sum()) > 1:
             rank = _c.pop_ranks_lifo3d(T, cd, g)
         else:
             rank = _c.pop_ranks(T)

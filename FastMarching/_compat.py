@@ -70,6 +70,12 @@ def pop_ranks(T: torch.Tensor) -> torch.Tensor:
 
 
 _BIG = torch.iinfo(torch.int64).max
+# Relative gap below which two values count as tied.  Zero = exact equality: a tolerance was tried (the device
+# field is within 3 ulp of the reference's in 2D, so a pair the reference ties exactly can differ by an ulp
+# here) but on plateau maps the reference itself holds many DISTINCT values one or two ulp apart, and merging
+# those misorders far more cells (154 vs 1 on the case that motivated it).
+TIE_TOL_2D = 0.0
+TIE_TOL_3D = 0.0
 
 
 def _shift(a, dy, dx, fill):
@@ -175,10 +181,13 @@ def _pop_ranks_lifo2d_cuda(T, cost, seed_idx: int, max_iters: int, transposed: b
     fin = torch.isfinite(flat)
     order = torch.sort(flat, stable=True).indices
     ts = flat[order]
-    new_grp = torch.cat([torch.ones(1, dtype=torch.bool, device=dev), ts[1:] != ts[:-1]])
+    # tie groups (TIE_TOL_* = 0: exact equality, see the note at their definition)
+    tol = TIE_TOL_2D if len(shape) == 2 else TIE_TOL_3D
+    new_grp = torch.cat([torch.ones(1, dtype=torch.bool, device=dev), (ts[1:] - ts[:-1]) > tol * ts[1:]])
+    new_grp = new_grp | ~torch.isfinite(ts)
     rank = torch.empty(n, dtype=torch.int32, device=dev)
     rank[order] = torch.arange(n, dtype=torch.int32, device=dev)
-    if not bool((~new_grp & torch.isfinite(ts)).any()):          # no two reached cells share a value: the sort is the pop order
+    if not bool((~new_grp).any()):                               # no two reached cells share a value: the sort is the pop order
         rank[~fin] = torch.iinfo(torch.int32).max
         return rank.reshape(shape)
     grp_sorted = torch.cumsum(new_grp.to(torch.int32), 0) - 1

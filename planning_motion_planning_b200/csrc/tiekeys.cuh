@@ -120,7 +120,10 @@ __global__ void tie_sweep_kernel(Grid<D> g, const double *T, const double *cost,
                         const long long nb = g.nbr(c, i);
                         if (nb >= 0) {
                             const double v = T[nb];
-                            if (v < t) {                              // strictly upwind: its rank and insertion time are final before mine
+                            // strictly upwind: its rank and insertion time are final before mine.  A neighbour of my own
+                            // tie group is never upwind (groups may be formed with a tolerance of a few ulp, and waiting
+                            // for a member of my own group would deadlock on the group barrier below)
+                            if (v < t && gstart[nb] != gstart[c]) {
                                 if (!tie_wait_nonzero(&done[nb], 1)) atomicAdd(failed, 1);
                                 tv[i] = v; rv[i] = ld_volatile(&rank[nb]); av[i] = ld_volatile(&tau[nb]);
                             }

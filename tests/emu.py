@@ -160,12 +160,17 @@ def costvolume(Zs, resX, resY, resZ, sX, sY, sZ, xm, ym, rlim, rO, rm, gamma2D, 
     return cmap.reshape(sX, sY, sZ), tunnel.reshape(sY, sX, sZ), terrain.reshape(sX, sY, sZ)
 
 
-def tie_groups(F):
-    """(members, gstart, gsize) of the T-sorted tie groups, as FastMarching/_compat.py builds them."""
+def tie_groups(F, tol=None):
+    """(members, gstart, gsize) of the T-sorted tie groups, as FastMarching/_compat.py builds them
+    (values closer than `tol`, relative, are tied; default = the 2D / 3D tolerance of _compat)."""
+    from FastMarching import _compat
+    if tol is None:
+        tol = _compat.TIE_TOL_2D if np.ndim(F) == 2 else _compat.TIE_TOL_3D
     flat = np.ascontiguousarray(F, dtype=np.float64).ravel()
     order = np.argsort(flat, kind="stable")
     ts = flat[order]
-    new = np.concatenate([[True], ts[1:] != ts[:-1]])
+    with np.errstate(invalid="ignore"):
+        new = np.concatenate([[True], (ts[1:] - ts[:-1]) > tol * ts[1:]]) | ~np.isfinite(ts)
     starts = np.nonzero(new)[0]
     sizes = np.diff(np.concatenate([starts, [flat.size]]))
     grp = np.cumsum(new) - 1

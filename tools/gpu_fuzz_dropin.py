@@ -59,6 +59,9 @@ for it in range(N):
             continue
         TG, TS, j = FM.biComputeTmap(c, g, s)
         ok = np.array_equal(j, oj) and np.array_equal(np.isfinite(TG), np.isfinite(oTG)) and np.array_equal(np.isfinite(TS), np.isfinite(oTS))
+        if not ok:
+            print("   2D: join", list(j), "reference", list(oj), "; pattern differs in", int((np.isfinite(TG) != np.isfinite(oTG)).sum()), "+",
+                  int((np.isfinite(TS) != np.isfinite(oTS)).sum()), "cells of", oTG.size, "; distinct cost values", np.unique(c[np.isfinite(c)]).size)
         e = 0.0
         if ok:
             for a, b in ((TG, oTG), (TS, oTS)):
@@ -66,8 +69,11 @@ for it in range(N):
                 e = max(e, float(np.max(np.abs(np.asarray(a)[f] - b[f]) / np.maximum(b[f], 1.0))))
             # single-front early exit (intended semantics of the reference's broken computeTmap)
             T1, o1 = FM.computeTmap(c, g, s), O.computeTmap(np.ascontiguousarray(c), g, s)
-            ok = ok and np.array_equal(np.isfinite(T1), np.isfinite(o1))
-            f = np.isfinite(o1)
+            if not np.array_equal(np.isfinite(T1), np.isfinite(o1)):
+                ok = False
+                print("   2D single front: pattern differs in", int((np.isfinite(T1) != np.isfinite(o1)).sum()), "cells of", o1.size,
+                      "; distinct cost values", np.unique(c[np.isfinite(c)]).size)
+            f = np.isfinite(o1) & np.isfinite(T1)
             e = max(e, float(np.max(np.abs(np.asarray(T1)[f] - o1[f]) / np.maximum(o1[f], 1.0))))
             # the two half paths from the join node over the partial fields, incl. the failure modes
             for Tm, oTm, endp in ((TG, oTG, g), (TS, oTS, s)):
