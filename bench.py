@@ -635,7 +635,8 @@ def own_arm(args):
                "sample": f"the full {n}x{n} solve + path, once, single thread (C restatement of the reference FMM; "
                          f"the reference itself is single-threaded CPython at ~2e4 cells/s)",
                "seconds": dt, "host_cores_available": len(os.sched_getaffinity(0)),
-               "parity": {"field_max_rel_err": rel, "same_inf_pattern": same_inf, "path_rows": [len(gp), len(pref)],
+               "parity": {"field_max_rel_err": rel, "same_inf_pattern": same_inf,
+                          "field_cells_bitwise_equal": float(np.mean(Tg[fin] == Tref[fin])), "path_rows": [len(gp), len(pref)],
                           "path_max_abs_dev_cells": pdev}}
 
     if rank == 0:

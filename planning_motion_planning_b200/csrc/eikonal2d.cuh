@@ -423,7 +423,12 @@ __global__ void __launch_bounds__(WARPS * 32) solve2d_kernel(Problem2D<real> P) 
                 real *p = rowT + k;
                 const real l = p[-1], r = p[1], u = p[-PT], d = p[PT], cur = p[0];
                 const real v = eikonal_update<real>(l < r ? l : r, u < d ? u : d, rowC[k]);
-                if (v < cur) {
+                // Lower values always win.  A value up to a few ulp HIGHER also replaces the stored one: a cell
+                // keeps the minimum over its history of updates, rounding is not monotone, and without this a
+                // cell can stay an ulp below update(final neighbours) -- the reference's field is an exact fixed
+                // point of the update, and exact ties between mirror-image cells depend on it.  Upwind
+                // dependencies are acyclic, so once a cell's inputs are final it is written once and rests.
+                if (v < cur || (v > cur && num<real>::sub(v, cur) <= cur * (real)8e-16)) {
                     *p = v;
                     dirty |= bit;
                     mask |= (l > v ? bit >> 1 : 0u) | (r > v ? bit << 1 : 0u);   // only neighbours that can still improve

@@ -318,7 +318,10 @@ __global__ void __launch_bounds__(WARPS * 32) solve3d_kernel(Problem3D<real> P) 
                 const real zm = p[-1], zp = p[1], xm = p[-PZ], xp = p[PZ], ym = p[-PS], yp = p[PS], cur = p[0];
                 // FastMarching3D.py:44-57: per-axis minimum, Tarray = [Tx, Ty, Tz]
                 const real v = solve3d_update<real>(xm < xp ? xm : xp, ym < yp ? ym : yp, zm < zp ? zm : zp, colC[k]);
-                if (v < cur) {
+                // lower values always win; a value a few ulp higher also replaces the stored one, so that the field
+                // ends as an exact fixed point of the update instead of the minimum over a history of roundings
+                // (see eikonal2d.cuh)
+                if (v < cur || (v > cur && num<real>::sub(v, cur) <= cur * (real)8e-16)) {
                     *p = v;
                     dirty |= bit;
                     mask |= (zm > v ? bit >> 1 : 0u) | (zp > v ? bit << 1 : 0u);

@@ -286,3 +286,14 @@ def test_tie_order_of_a_transposed_field_follows_the_callers_orientation():
             assert int((((mt % H) * W + mt // H) != order).sum()) == 0
         wrong = np.argsort(emu.tie_order2d(Tt, ct, st).ravel(), kind="stable")[1:1 + len(order)]
         assert int((((wrong % H) * W + wrong // H) != order).sum()) > 100          # the flag matters
+
+
+def test_emulated_field_carries_the_references_bits():
+    """With the 'a few ulp higher also replaces' rule the emulated kernel's field is an exact fixed point of
+    the update: bit-identical to the reference on uniform, plateau and random maps."""
+    uniform = np.pad(np.full((110, 110), 7.0), 1, constant_values=np.inf)
+    uniform[40, 20:60] = np.inf
+    for c, g in ((uniform, [17, 18]), (plateau_map(128, 7), [96, 90]), (rand_map((150, 170), 3), [20, 30])):
+        T, _ = emu.solve2d(c, [g], nblocks=3)
+        ref = O.computeTmap(c, g)
+        assert np.array_equal(T[0], ref)
