@@ -428,7 +428,7 @@ __global__ void __launch_bounds__(WARPS * 32) solve2d_kernel(Problem2D<real> P) 
                 // cell can stay an ulp below update(final neighbours) -- the reference's field is an exact fixed
                 // point of the update, and exact ties between mirror-image cells depend on it.  Upwind
                 // dependencies are acyclic, so once a cell's inputs are final it is written once and rests.
-                if (v < cur || (v > cur && num<real>::sub(v, cur) <= cur * (real)8e-16)) {
+                if (v != cur && v <= num<real>::mul(cur, (real)(1.0 + 8.0 / 4503599627370496.0))) {      // lower, or at most ~4 ulp higher
                     *p = v;
                     dirty |= bit;
                     mask |= (l > v ? bit >> 1 : 0u) | (r > v ? bit << 1 : 0u);   // only neighbours that can still improve

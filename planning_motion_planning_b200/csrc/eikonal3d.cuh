@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(WARPS * 32) solve3d_kernel(Problem3D<real> P) 
                 // lower values always win; a value a few ulp higher also replaces the stored one, so that the field
                 // ends as an exact fixed point of the update instead of the minimum over a history of roundings
                 // (see eikonal2d.cuh)
-                if (v < cur || (v > cur && num<real>::sub(v, cur) <= cur * (real)8e-16)) {
+                if (v != cur && v <= num<real>::mul(cur, (real)(1.0 + 8.0 / 4503599627370496.0))) {      // lower, or at most ~4 ulp higher
                     *p = v;
                     dirty |= bit;
                     mask |= (zm > v ? bit >> 1 : 0u) | (zp > v ? bit << 1 : 0u);
