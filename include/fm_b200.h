@@ -72,6 +72,26 @@ typedef struct fmb_stats {
     uint64_t reserved[1];
 } fmb_stats;
 
+/* Tunables of the solvers: process-wide, read by every solve call (no getenv() on the call path; the FMB_*
+ * environment variables only give the INITIAL values, read once at first use).  0 / -1 = automatic. */
+typedef struct fmb_options {
+    int32_t engine2d;     /* 0 auto, 1 warp-per-tile visits (round 1), 2 CTA-per-tile visits */
+    int32_t cta_cells;    /* cells per thread of the CTA engine: 0 auto, 1, 2 or 4 */
+    int32_t tile_w2d;     /* tile width of the warp engine: 16 or 32 */
+    int32_t tile_z3d;     /* 3D tile depth: 16 or 32 */
+    int32_t best_first;   /* per-query best-first order: -1 auto, 0 off, 1 on */
+    int32_t windowed;     /* windowed FIFO order of one large map: -1 auto, 0 off, 1 on */
+    int32_t window;       /* window in levels (0 = default) */
+    int32_t worker_div;   /* tiles per worker used to size the grid (0 = automatic) */
+    int32_t max_blocks;   /* cap on the persistent grid (0 = none) */
+    int32_t watchdog_ms;  /* device watchdog, time without progress */
+    int32_t step_cap;     /* in-tile iteration cap */
+    int32_t engine3d;     /* 0 auto, 1 warp-per-tile, 2 CTA-per-tile */
+    int32_t reserved[4];
+} fmb_options;
+void fmb_get_options(fmb_options *out);
+int fmb_set_options(const fmb_options *in);
+
 int fmb_version(void);
 const char *fmb_last_error(void);
 /* number of SMs of the current device (grid sizing / reporting) */

@@ -31,6 +31,13 @@ class FmbStats(C.Structure):
         return d
 
 
+class FmbOptions(C.Structure):
+    """fmb_options of include/fm_b200.h (process-wide solver tunables)."""
+    _fields_ = [(k, C.c_int32) for k in ("engine2d", "cta_cells", "tile_w2d", "tile_z3d", "best_first", "windowed",
+                                         "window", "worker_div", "max_blocks", "watchdog_ms", "step_cap", "engine3d")]
+    _fields_ += [("reserved", C.c_int32 * 4)]
+
+
 class FmbError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"libfm_b200 error {code}: {msg}")
@@ -44,6 +51,8 @@ SIGNATURES = {
     "fmb_version": (C.c_int, []),
     "fmb_last_error": (C.c_char_p, []),
     "fmb_sm_count": (C.c_int, []),
+    "fmb_get_options": (None, [C.POINTER(FmbOptions)]),
+    "fmb_set_options": (C.c_int, [C.POINTER(FmbOptions)]),
     "fmb_workspace_bytes_2d": (_sz, [_i32, _i32, _i32]),
     "fmb_solve2d_f64": (C.c_int, [_vp, _i64, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
     "fmb_solve2d_f32": (C.c_int, [_vp, _i64, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
@@ -90,6 +99,25 @@ def lib():
             fn.argtypes = args
         _LIB = L
     return _LIB
+
+
+def get_options() -> dict:
+    o = FmbOptions()
+    lib().fmb_get_options(C.byref(o))
+    return {k: int(getattr(o, k)) for k, _ in FmbOptions._fields_ if k != "reserved"}
+
+
+def set_options(**kw) -> dict:
+    """Update solver tunables (see fmb_options); returns the previous values."""
+    o = FmbOptions()
+    lib().fmb_get_options(C.byref(o))
+    prev = {k: int(getattr(o, k)) for k, _ in FmbOptions._fields_ if k != "reserved"}
+    for k, v in kw.items():
+        if k not in prev:
+            raise KeyError(k)
+        setattr(o, k, int(v))
+    check(lib().fmb_set_options(C.byref(o)))
+    return prev
 
 
 def check(rc: int):

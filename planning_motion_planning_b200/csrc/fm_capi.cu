@@ -8,7 +8,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "eikonal2d.cuh"
+#include "eikonal2d_cta.cuh"
 #include "eikonal3d.cuh"
 #include "trace2d.cuh"
 #include "trace3d.cuh"
@@ -27,23 +30,73 @@ int cuda_fail(cudaError_t e, const char *where) {
 }
 #define CK(call, where) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(e_, where); } while (0)
 
-// per-host-thread CUDA events bracketing the most recent solve (timing evidence for bench.py)
-struct Timing { cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr; bool armed = false; };
-thread_local Timing g_tm;
-bool timing_begin(cudaStream_t st) {
-    if (!g_tm.e0) {
-        if (cudaEventCreate(&g_tm.e0) != cudaSuccess || cudaEventCreate(&g_tm.e1) != cudaSuccess ||
-            cudaEventCreate(&g_tm.e2) != cudaSuccess) { g_tm.e0 = nullptr; cudaGetLastError(); return false; }
+// CUDA events bracketing the most recent solve of every (host thread, device, stream): timing evidence for
+// bench.py.  Events belong to the device that was current when they were created, so they are kept per
+// device; one host thread may drive several streams, so they are also kept per stream (at most TM_SLOTS
+// streams per device and thread, oldest evicted).  Timing can never fail a solve: every error is swallowed.
+struct Timing { cudaStream_t st = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr; bool armed = false; unsigned long long age = 0; };
+constexpr int TM_DEVS = 16, TM_SLOTS = 16;
+thread_local Timing g_tm[TM_DEVS][TM_SLOTS];
+thread_local unsigned long long g_tm_clock = 0;
+Timing *timing_slot(cudaStream_t st, bool create) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= TM_DEVS) { cudaGetLastError(); return nullptr; }
+    Timing *row = g_tm[dev], *victim = &row[0];
+    for (int i = 0; i < TM_SLOTS; ++i) {
+        if (row[i].e0 && row[i].st == st) { row[i].age = ++g_tm_clock; return &row[i]; }
+        if (row[i].age < victim->age) victim = &row[i];
     }
-    g_tm.armed = false;
-    return cudaEventRecord(g_tm.e0, st) == cudaSuccess;
+    if (!create) return nullptr;
+    if (!victim->e0) {
+        if (cudaEventCreate(&victim->e0) != cudaSuccess || cudaEventCreate(&victim->e1) != cudaSuccess ||
+            cudaEventCreate(&victim->e2) != cudaSuccess) { victim->e0 = nullptr; cudaGetLastError(); return nullptr; }
+    }
+    victim->st = st; victim->armed = false; victim->age = ++g_tm_clock;
+    return victim;
 }
-void timing_mid(cudaStream_t st) { if (g_tm.e0) cudaEventRecord(g_tm.e1, st); }
-void timing_end(cudaStream_t st) { if (g_tm.e0 && cudaEventRecord(g_tm.e2, st) == cudaSuccess) g_tm.armed = true; }
+void timing_begin(cudaStream_t st) {
+    Timing *t = timing_slot(st, true);
+    if (t) { t->armed = false; if (cudaEventRecord(t->e0, st) != cudaSuccess) cudaGetLastError(); }
+}
+void timing_mid(cudaStream_t st) {
+    Timing *t = timing_slot(st, false);
+    if (t && cudaEventRecord(t->e1, st) != cudaSuccess) cudaGetLastError();
+}
+void timing_end(cudaStream_t st) {
+    Timing *t = timing_slot(st, false);
+    if (t) { if (cudaEventRecord(t->e2, st) == cudaSuccess) t->armed = true; else cudaGetLastError(); }
+}
 
+// ---- tunables: one process-wide options struct (fmb_get_options / fmb_set_options); the FMB_*
+// environment variables only give its INITIAL values, read once
+std::mutex g_opt_mu;
+fmb_options g_opt;
+bool g_opt_init = false;
 int env_int(const char *name, int dflt) {
     const char *v = getenv(name);
     return (v && *v) ? atoi(v) : dflt;
+}
+void opt_defaults_locked() {
+    if (g_opt_init) return;
+    memset(&g_opt, 0, sizeof(g_opt));
+    g_opt.engine2d = env_int("FMB_ENGINE2D", 0);
+    g_opt.cta_cells = env_int("FMB_CTA_CELLS", 0);
+    g_opt.tile_w2d = env_int("FMB_TW2D", 32);
+    g_opt.tile_z3d = env_int("FMB_TZ3D", 16);
+    g_opt.best_first = env_int("FMB_BEST_FIRST", -1);
+    g_opt.windowed = env_int("FMB_WINDOWED", -1);
+    g_opt.window = env_int("FMB_WINDOW", 0);
+    g_opt.worker_div = env_int("FMB_WORKER_DIV", 0);
+    g_opt.max_blocks = env_int("FMB_MAX_BLOCKS", 0);
+    g_opt.watchdog_ms = env_int("FMB_WATCHDOG_MS", 20000);
+    g_opt.step_cap = env_int("FMB_STEP_CAP", 1 << 20);
+    g_opt.engine3d = env_int("FMB_ENGINE3D", 0);
+    g_opt_init = true;
+}
+fmb_options opt() {
+    std::lock_guard<std::mutex> lk(g_opt_mu);
+    opt_defaults_locked();
+    return g_opt;
 }
 
 int sm_count() {
@@ -91,6 +144,18 @@ long long tiles2d(int rows, int cols, int tw) {
     return (long long)((cols + tw - 1) / tw) * ((rows + fmb::TILE_H - 1) / fmb::TILE_H);
 }
 
+template <typename real, int TW>
+void launch_init2d(const fmb::Problem2D<real> &P, const WsLayout &L, cudaStream_t st, int resume_activate, long long fill_blocks) {
+    if (resume_activate < 0) {
+        fmb::init_fill2d_kernel<real><<<(unsigned)fill_blocks, 256, 0, st>>>(P, (int)L.ring_slots);
+    } else {
+        fmb::init_resume2d_kernel<real><<<64, 256, 0, st>>>(P, (int)L.ring_slots);
+        if (resume_activate & 7)
+            fmb::activate_rows2d_kernel<real><<<(P.ntx * P.nty + 127) / 128, 128, 0, st>>>(P, resume_activate);
+    }
+    fmb::init_seed2d_kernel<real, TW><<<(P.nq + 127) / 128, 128, 0, st>>>(P);     // out-of-range seed = no seed
+}
+
 template <typename real, int TW, bool BEST>
 int launch_solve2d(fmb::Problem2D<real> P, const WsLayout &L, cudaStream_t st, int resume_activate = -1) {
     using TL = fmb::Tile2D<real, TW>;
@@ -107,30 +172,58 @@ int launch_solve2d(fmb::Problem2D<real> P, const WsLayout &L, cudaStream_t st, i
     // Windowed order: the solve is bound by the chain of tile visits, not by throughput -- one warp per
     // 28 tiles finishes as fast as the whole machine with a sixth of the work (4096^2: 22.4 ms, 13.6
     // evaluations per cell instead of 90), which leaves the other SM slots to concurrent solves.
-    const int div = env_int("FMB_WORKER_DIV", P.windowed ? 28 : (P.nq == 1 ? 2 : 1));
+    const fmb_options O = opt();
+    const int div = O.worker_div > 0 ? O.worker_div : (P.windowed ? 28 : (P.nq == 1 ? 2 : 1));
     const long long need = (ntiles + (long long)WARPS * div - 1) / ((long long)WARPS * div);
     if (blocks > need) blocks = need;
     if (blocks < 1) blocks = 1;
-    const int cap_blocks = env_int("FMB_MAX_BLOCKS", 0);
-    if (cap_blocks > 0 && blocks > cap_blocks) blocks = cap_blocks;
+    if (O.max_blocks > 0 && blocks > O.max_blocks) blocks = O.max_blocks;
 
     const long long cells = (long long)P.rows * P.cols * P.nq;
     long long fill_blocks = (cells + 256 * 8 - 1) / (256 * 8);
     if (fill_blocks > (long long)sm_count() * 16) fill_blocks = (long long)sm_count() * 16;
     if (fill_blocks < 1) fill_blocks = 1;
+    cudaGetLastError();          // a stale error of the caller must not be reported as ours
     timing_begin(st);
-    if (resume_activate < 0) {
-        fmb::init_fill2d_kernel<real><<<(unsigned)fill_blocks, 256, 0, st>>>(P, (int)L.ring_slots);
-    } else {
-        fmb::init_resume2d_kernel<real><<<64, 256, 0, st>>>(P, (int)L.ring_slots);
-        if (resume_activate & 7)
-            fmb::activate_rows2d_kernel<real><<<(P.ntx * P.nty + 127) / 128, 128, 0, st>>>(P, resume_activate);
-    }
-    fmb::init_seed2d_kernel<real, TW><<<(P.nq + 127) / 128, 128, 0, st>>>(P);     // out-of-range seed = no seed
+    launch_init2d<real, TW>(P, L, st, resume_activate, fill_blocks);
     timing_mid(st);
     kern<<<(unsigned)blocks, WARPS * 32, smem, st>>>(P);
+    cudaError_t le = cudaGetLastError();
     timing_end(st);
-    CK(cudaGetLastError(), "launch solve2d");
+    CK(le, "launch solve2d");
+    return FMB_OK;
+}
+
+// CTA-per-tile engine (eikonal2d_cta.cuh): 1024 / R threads per tile visit, 32 x 32 tiles
+template <typename real, int R, bool BEST>
+int launch_solve2d_cta(fmb::Problem2D<real> P, const WsLayout &L, cudaStream_t st, int resume_activate = -1) {
+    using TL = fmb::CtaTile2D<real>;
+    constexpr int NT = 1024 / R;
+    const size_t smem = TL::BYTES;
+    auto kern = fmb::solve2d_cta_kernel<real, R, BEST>;
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem), "occupancy(solve2d_cta)");
+    if (per_sm < 1) return fail(FMB_E_CUDA, "solve2d_cta kernel does not fit on an SM%s");
+    const long long ntiles = (long long)P.nq * P.ntx * P.nty;
+    long long blocks = (long long)per_sm * sm_count();
+    const fmb_options O = opt();
+    const int div = O.worker_div > 0 ? O.worker_div : (P.nq == 1 ? 2 : 1);
+    const long long need = (ntiles + div - 1) / div;
+    if (blocks > need) blocks = need;
+    if (blocks < 1) blocks = 1;
+    if (O.max_blocks > 0 && blocks > O.max_blocks) blocks = O.max_blocks;
+    const long long cells = (long long)P.rows * P.cols * P.nq;
+    long long fill_blocks = (cells + 256 * 8 - 1) / (256 * 8);
+    if (fill_blocks > (long long)sm_count() * 16) fill_blocks = (long long)sm_count() * 16;
+    if (fill_blocks < 1) fill_blocks = 1;
+    cudaGetLastError();
+    timing_begin(st);
+    launch_init2d<real, 32>(P, L, st, resume_activate, fill_blocks);
+    timing_mid(st);
+    kern<<<(unsigned)blocks, NT, smem, st>>>(P);
+    cudaError_t le = cudaGetLastError();
+    timing_end(st);
+    CK(le, "launch solve2d_cta");
     return FMB_OK;
 }
 
@@ -141,8 +234,11 @@ int solve2d(const real *d_cost, int64_t cost_pitch, int64_t cost_qstride, real *
     if (!d_cost || !d_T || !d_seeds || !d_ws) return fail(FMB_E_INVALID, "null pointer argument%s");
     if (rows < 1 || cols < 1 || nq < 1) return fail(FMB_E_INVALID, "rows, cols and nq must be positive%s");
     if (cost_pitch < cols || T_pitch < cols) return fail(FMB_E_INVALID, "pitch smaller than cols%s");
-    int tw = env_int("FMB_TW2D", 32);
-    if (tw != 16 && tw != 32) return fail(FMB_E_INVALID, "FMB_TW2D must be 16 or 32%s");
+    const fmb_options O = opt();
+    // engine: CTA-per-tile (32-wide tiles) unless the warp-per-tile engine of round 1 is asked for
+    const int engine = O.engine2d > 0 ? O.engine2d : 2;
+    int tw = engine == 2 ? 32 : O.tile_w2d;
+    if (tw != 16 && tw != 32) return fail(FMB_E_INVALID, "tile_w2d must be 16 or 32%s");
     const long long ntiles = tiles2d(rows, cols, tw) * nq;
     if (ntiles >= (1LL << 30)) return fail(FMB_E_INVALID, "too many tiles for one launch%s");
     if (ws_bytes < fmb_workspace_bytes_2d(rows, cols, nq)) return fail(FMB_E_WORKSPACE, "workspace too small%s");
@@ -158,23 +254,35 @@ int solve2d(const real *d_cost, int64_t cost_pitch, int64_t cost_qstride, real *
     P.q.ctl = (fmb::QueueCtl *)(ws + L.ctl_off);
     P.q.ring = (int *)(ws + L.ring_off);
     P.q.ring_mask = L.ring_slots - 1;
-    P.q.watchdog_cycles = (long long)env_int("FMB_WATCHDOG_MS", 20000) * 2000000LL;   // ~2 GHz
-    P.step_cap = env_int("FMB_STEP_CAP", 1 << 20);
+    P.q.watchdog_cycles = (long long)(O.watchdog_ms > 0 ? O.watchdog_ms : 20000) * 2000000LL;   // ~2 GHz
+    P.step_cap = O.step_cap > 0 ? O.step_cap : 1 << 20;
     P.tile_prio = (unsigned long long *)(ws + L.prio_off);
     // best-first per query pays off when many queries share the GPU and a query's tile table is
     // small enough to scan per claim; one large map is faster in plain FIFO order
     const long long tiles_per_q = ntiles / nq;
-    P.best_first = env_int("FMB_BEST_FIRST", (nq >= 8 && tiles_per_q <= 1024) ? 1 : 0);     // claim = scan of the query's tile table
+    P.best_first = O.best_first >= 0 ? O.best_first : ((nq >= 8 && tiles_per_q <= 1024) ? 1 : 0);     // claim = scan of the query's tile table
     P.arm_rows = arm_rows;
     if (resume_activate >= 0) P.best_first = 0;
     // windowed FIFO (deferral of tiles far ahead of the lowest queued level): one large map only
-    P.windowed = (!P.best_first && resume_activate < 0 && nq == 1) ? env_int("FMB_WINDOWED", ntiles >= 16384 ? 1 : 0) : 0;
-    P.win_window = env_int("FMB_WINDOW", 2);
+    P.windowed = (!P.best_first && resume_activate < 0 && nq == 1) ? (O.windowed >= 0 ? O.windowed : (ntiles >= 16384 ? 1 : 0)) : 0;
+    P.win_window = O.window > 0 ? O.window : 2;
     P.win_inv_delta = (double *)(ws + L.win_off);
     P.win_hint = (int *)(ws + L.win_off + 8);
     P.lev_count = (int *)(ws + L.win_off + 256);
     P.tile_level = (int *)(ws + L.level_off);
     cudaStream_t st = (cudaStream_t)stream;
+    if (engine == 2) {
+        const int R = O.cta_cells > 0 ? O.cta_cells : 2;
+        if (R != 1 && R != 2 && R != 4) return fail(FMB_E_INVALID, "cta_cells must be 1, 2 or 4%s");
+        if (P.best_first) {
+            if (R == 1) return launch_solve2d_cta<real, 1, true>(P, L, st);
+            if (R == 2) return launch_solve2d_cta<real, 2, true>(P, L, st);
+            return launch_solve2d_cta<real, 4, true>(P, L, st);
+        }
+        if (R == 1) return launch_solve2d_cta<real, 1, false>(P, L, st, resume_activate);
+        if (R == 2) return launch_solve2d_cta<real, 2, false>(P, L, st, resume_activate);
+        return launch_solve2d_cta<real, 4, false>(P, L, st, resume_activate);
+    }
     if (P.best_first) {
         if (tw == 16) return launch_solve2d<real, 16, true>(P, L, st);
         return launch_solve2d<real, 32, true>(P, L, st);
@@ -190,6 +298,17 @@ extern "C" {
 int fmb_version(void) { return 100; }
 const char *fmb_last_error(void) { return g_err; }
 int fmb_sm_count(void) { return sm_count(); }
+void fmb_get_options(fmb_options *out) { if (out) *out = opt(); }
+int fmb_set_options(const fmb_options *in) {
+    if (!in) return fail(FMB_E_INVALID, "null options%s");
+    if (in->cta_cells != 0 && in->cta_cells != 1 && in->cta_cells != 2 && in->cta_cells != 4) return fail(FMB_E_INVALID, "cta_cells must be 0, 1, 2 or 4%s");
+    if (in->tile_w2d != 16 && in->tile_w2d != 32) return fail(FMB_E_INVALID, "tile_w2d must be 16 or 32%s");
+    if (in->tile_z3d != 16 && in->tile_z3d != 32) return fail(FMB_E_INVALID, "tile_z3d must be 16 or 32%s");
+    std::lock_guard<std::mutex> lk(g_opt_mu);
+    opt_defaults_locked();
+    g_opt = *in;
+    return FMB_OK;
+}
 
 size_t fmb_workspace_bytes_2d(int rows, int cols, int nq) {
     if (rows < 1 || cols < 1 || nq < 1) return 0;
@@ -227,9 +346,10 @@ int fmb_finish(void *d_ws, size_t ws_bytes, void *stream, fmb_stats *stats) {
         stats->pushes = h.pushes; stats->cells_written = h.cells_written;
         stats->reserved[0] = h.pad[0];     /* deferrals of the windowed order */
         stats->cyc_wait = h.cyc_wait; stats->cyc_load = h.cyc_load; stats->cyc_relax = h.cyc_relax; stats->cyc_store = h.cyc_store;
-        if (g_tm.armed) {
+        Timing *tm = timing_slot((cudaStream_t)stream, false);
+        if (tm && tm->armed) {
             float a = 0.f, b = 0.f;
-            if (cudaEventElapsedTime(&a, g_tm.e0, g_tm.e1) == cudaSuccess && cudaEventElapsedTime(&b, g_tm.e1, g_tm.e2) == cudaSuccess) {
+            if (cudaEventElapsedTime(&a, tm->e0, tm->e1) == cudaSuccess && cudaEventElapsedTime(&b, tm->e1, tm->e2) == cudaSuccess) {
                 stats->init_kernel_ms = a; stats->solve_kernel_ms = b;
             } else cudaGetLastError();
         }

@@ -26,6 +26,8 @@ def lib():
         L = C.CDLL(_SO)
         L.emu_solve2d_f64.argtypes = [dp, C.c_longlong, dp, C.c_int, C.c_int, C.c_int, ip, C.c_int, C.c_int, up]
         L.emu_solve2d_f32.argtypes = [fp, C.c_longlong, fp, C.c_int, C.c_int, C.c_int, ip, C.c_int, C.c_int, up]
+        L.emu_solve2d_cta_f64.argtypes = [dp, C.c_longlong, dp, C.c_int, C.c_int, C.c_int, ip, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, up]
+        L.emu_solve2d_cta_f32.argtypes = [fp, C.c_longlong, fp, C.c_int, C.c_int, C.c_int, ip, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, up]
         L.emu_solve3d_f64.argtypes = [dp, C.c_longlong, dp, C.c_int, C.c_int, C.c_int, C.c_int, ip, C.c_int, C.c_int, up]
         L.emu_solve3d_f32.argtypes = [fp, C.c_longlong, fp, C.c_int, C.c_int, C.c_int, C.c_int, ip, C.c_int, C.c_int, up]
         L.emu_trace2d_f64.argtypes = [dp, C.c_int, C.c_int, C.c_int, ip, dp, dp, C.c_double, C.c_int, dp, C.c_longlong, ip, ip]
@@ -47,6 +49,23 @@ def solve2d(cost, seeds, tw=32, nblocks=2, shared=True):
     rc = fn(cost.ctypes.data_as(P), 0 if shared else rows * cols, T.ctypes.data_as(P), rows, cols, nq,
             seeds.ctypes.data_as(ip), tw, nblocks, st.ctypes.data_as(up))
     assert rc == 0, f"emulated solve2d failed rc={rc}"
+    return T, dict(visits=int(st[0]), steps=int(st[1]), evals=int(st[2]), pushes=int(st[3]), written=int(st[4]))
+
+
+def solve2d_cta(cost, seeds, R=2, nblocks=2, shared=True, best_first=0, windowed=0, window=2):
+    """CTA-per-tile engine (csrc/eikonal2d_cta.cuh) under the emulator."""
+    dt = cost.dtype
+    cost = np.ascontiguousarray(cost)
+    seeds = np.ascontiguousarray(seeds, dtype=np.int32).reshape(-1, 2)
+    nq = len(seeds)
+    rows, cols = cost.shape[-2:]
+    T = np.empty((nq, rows, cols), dtype=dt)
+    st = np.zeros(8, dtype=np.uint64)
+    P = dp if dt == np.float64 else fp
+    fn = lib().emu_solve2d_cta_f64 if dt == np.float64 else lib().emu_solve2d_cta_f32
+    rc = fn(cost.ctypes.data_as(P), 0 if shared else rows * cols, T.ctypes.data_as(P), rows, cols, nq,
+            seeds.ctypes.data_as(ip), R, nblocks, best_first, windowed, window, st.ctypes.data_as(up))
+    assert rc == 0, f"emulated solve2d_cta failed rc={rc}"
     return T, dict(visits=int(st[0]), steps=int(st[1]), evals=int(st[2]), pushes=int(st[3]), written=int(st[4]))
 
 

@@ -35,7 +35,7 @@ namespace emu {
 
 struct dim3_ { unsigned x = 1, y = 1, z = 1; };
 
-enum Coll { C_NONE = 0, C_SHFL, C_SHFL_UP, C_SHFL_DOWN, C_SHFL_XOR, C_BALLOT, C_ANY, C_SYNC };
+enum Coll { C_NONE = 0, C_SHFL, C_SHFL_UP, C_SHFL_DOWN, C_SHFL_XOR, C_BALLOT, C_ANY, C_SYNC, C_BLOCK };   // C_BLOCK: __syncthreads[_or]
 
 struct Warp;
 struct Lane {
@@ -51,6 +51,7 @@ struct Lane {
 struct Warp {
     Lane lanes[32];
     unsigned char *smem = nullptr;     // block shared memory (shared by the warps of a block)
+    int block = 0;                     // block index (block-wide barriers)
 };
 
 struct Machine {
@@ -79,6 +80,7 @@ inline void lane_entry() {
     yield_to_sched();
 }
 
+inline bool block_resolve(Warp *w);
 inline void resolve(Warp *w) {
     int kind = C_NONE;
     for (auto &l : w->lanes) {
@@ -87,6 +89,7 @@ inline void resolve(Warp *w) {
         if (l.coll != kind) { fprintf(stderr, "EMU: divergent collectives in a warp (%d vs %d)\n", kind, l.coll); abort(); }
     }
     for (auto &l : w->lanes) if (l.done) { fprintf(stderr, "EMU: collective with exited lanes\n"); abort(); }
+    if (kind == C_BLOCK) { block_resolve(w); return; }
     unsigned ballot = 0;
     for (int i = 0; i < 32; ++i) if (w->lanes[i].payload) ballot |= 1u << i;
     for (int i = 0; i < 32; ++i) {
@@ -104,6 +107,26 @@ inline void resolve(Warp *w) {
     for (auto &l : w->lanes) l.waiting = false;
 }
 
+// __syncthreads / __syncthreads_or: released when every lane of every warp of the block waits on it
+// (whole warps that already exited are ignored, like on the device)
+inline bool block_resolve(Warp *w) {
+    Machine &m = M();
+    uint64_t any = 0;
+    for (Warp *o : m.warps) {
+        if (o->block != w->block) continue;
+        for (auto &l : o->lanes) {
+            if (l.done) continue;
+            if (!l.waiting || l.coll != C_BLOCK) return false;
+            any |= l.payload;
+        }
+    }
+    for (Warp *o : m.warps) {
+        if (o->block != w->block) continue;
+        for (auto &l : o->lanes) if (!l.done) { l.result = any; l.waiting = false; }
+    }
+    return true;
+}
+
 // run `body` as a kernel of grid x block threads (block.x multiple of 32)
 inline void launch(unsigned grid, unsigned block, size_t smem_bytes, std::function<void()> body) {
     Machine &m = M();
@@ -114,7 +137,7 @@ inline void launch(unsigned grid, unsigned block, size_t smem_bytes, std::functi
         unsigned char *sm = (unsigned char *)aligned_alloc(64, ((smem_bytes + 63) / 64) * 64 + 64);
         smems.push_back(sm);
         for (unsigned wi = 0; wi < wpb; ++wi) {
-            Warp *w = new Warp(); w->smem = sm;
+            Warp *w = new Warp(); w->smem = sm; w->block = (int)b;
             for (int i = 0; i < 32; ++i) {
                 Lane &l = w->lanes[i];
                 l.warp = w; l.lane_id = i; l.tid.x = wi * 32 + i; l.bid.x = b;
@@ -169,6 +192,8 @@ template <typename T> inline T __shfl_xor_sync(unsigned, T v, int m) { return em
 inline unsigned __ballot_sync(unsigned, bool p) { return (unsigned)emu::collective(emu::C_BALLOT, p ? 1 : 0, 0); }
 inline bool __any_sync(unsigned, bool p) { return emu::collective(emu::C_ANY, p ? 1 : 0, 0) != 0; }
 inline void __syncwarp() { emu::collective(emu::C_SYNC, 0, 0); }
+inline void __syncthreads() { emu::collective(emu::C_BLOCK, 0, 0); }
+inline int __syncthreads_or(int p) { return emu::collective(emu::C_BLOCK, p ? 1 : 0, 0) != 0; }
 inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline void __nanosleep(unsigned) { emu::M().yielded_sleep = true; emu::M().clock += 100; emu::yield_to_sched(); }
 inline long long clock64() { return (long long)(emu::M().clock += 1); }

@@ -7,6 +7,7 @@
 #include "cuda_emu.h"
 
 #include "../../planning_motion_planning_b200/csrc/eikonal2d.cuh"
+#include "../../planning_motion_planning_b200/csrc/eikonal2d_cta.cuh"
 #include "../../planning_motion_planning_b200/csrc/eikonal3d.cuh"
 #include "../../planning_motion_planning_b200/csrc/trace2d.cuh"
 #include "../../planning_motion_planning_b200/csrc/trace3d.cuh"
@@ -47,6 +48,40 @@ int run2d(const real *cost, long long cost_qstride, real *T, int rows, int cols,
     emu::launch(1, 32 * ((nq + 31) / 32), 0, [&] { fmb::init_seed2d_kernel<real, TW>(P); });
     if (P.best_first) emu::launch(nblocks, WARPS * 32, fmb::Tile2D<real, TW>::WARP_BYTES * WARPS, [&] { fmb::solve2d_kernel<real, TW, WARPS, true>(P); });
     else emu::launch(nblocks, WARPS * 32, fmb::Tile2D<real, TW>::WARP_BYTES * WARPS, [&] { fmb::solve2d_kernel<real, TW, WARPS, false>(P); });
+    if (stats) { stats[0] = ctl.visits; stats[1] = ctl.steps; stats[2] = ctl.evals; stats[3] = ctl.pushes; stats[4] = ctl.cells_written; }
+    return ctl.abort ? ctl.abort : (ctl.pending != 0 ? -1 : 0);
+}
+
+// CTA-per-tile engine (eikonal2d_cta.cuh): same set-up, 1024 / R threads per block
+template <typename real, int R>
+int run2d_cta(const real *cost, long long cost_qstride, real *T, int rows, int cols, int nq, const int *seeds, int nblocks,
+              int best_first, int windowed, int window, unsigned long long *stats) {
+    constexpr int TW = 32;
+    fmb::Problem2D<real> P;
+    P.cost = cost; P.cost_pitch = cols; P.cost_qstride = cost_qstride;
+    P.T = T; P.T_pitch = cols; P.T_qstride = (long long)rows * cols;
+    P.rows = rows; P.cols = cols; P.nq = nq;
+    P.ntx = (cols + TW - 1) / TW; P.nty = (rows + fmb::TILE_H - 1) / fmb::TILE_H;
+    P.seeds = seeds;
+    const long long ntiles = (long long)nq * P.ntx * P.nty;
+    std::vector<int> state(ntiles), ring(pow2_at_least(ntiles));
+    fmb::QueueCtl ctl;
+    P.tile_state = state.data(); P.q.ctl = &ctl; P.q.ring = ring.data(); P.q.ring_mask = (unsigned)ring.size() - 1;
+    P.q.watchdog_cycles = 1LL << 40; P.step_cap = 1 << 20;
+    std::vector<unsigned long long> prio(ntiles);
+    P.tile_prio = prio.data();
+    P.best_first = best_first;
+    P.arm_rows = 0;
+    std::vector<int> lev_count(fmb::WIN_LEVELS), tile_level(ntiles);
+    int win_hint = 0; double win_inv_delta = 1.0;
+    P.windowed = (!best_first && nq == 1) ? windowed : 0;
+    P.win_window = window;
+    P.lev_count = lev_count.data(); P.tile_level = tile_level.data(); P.win_hint = &win_hint; P.win_inv_delta = &win_inv_delta;
+    emu::launch(2, 64, 0, [&] { fmb::init_fill2d_kernel<real>(P, (int)ring.size()); });
+    emu::launch(1, 32 * ((nq + 31) / 32), 0, [&] { fmb::init_seed2d_kernel<real, TW>(P); });
+    const size_t smem = fmb::CtaTile2D<real>::BYTES;
+    if (best_first) emu::launch(nblocks, 1024 / R, smem, [&] { fmb::solve2d_cta_kernel<real, R, true>(P); });
+    else emu::launch(nblocks, 1024 / R, smem, [&] { fmb::solve2d_cta_kernel<real, R, false>(P); });
     if (stats) { stats[0] = ctl.visits; stats[1] = ctl.steps; stats[2] = ctl.evals; stats[3] = ctl.pushes; stats[4] = ctl.cells_written; }
     return ctl.abort ? ctl.abort : (ctl.pending != 0 ? -1 : 0);
 }
@@ -97,6 +132,18 @@ int emu_solve2d_f32(const float *cost, long long cost_qstride, float *T, int row
                     int tw, int nblocks, unsigned long long *stats) {
     if (tw == 16) return run2d<float, 16>(cost, cost_qstride, T, rows, cols, nq, seeds, nblocks, stats);
     return run2d<float, 32>(cost, cost_qstride, T, rows, cols, nq, seeds, nblocks, stats);
+}
+int emu_solve2d_cta_f64(const double *cost, long long cost_qstride, double *T, int rows, int cols, int nq, const int *seeds,
+                        int R, int nblocks, int best_first, int windowed, int window, unsigned long long *stats) {
+    if (R == 1) return run2d_cta<double, 1>(cost, cost_qstride, T, rows, cols, nq, seeds, nblocks, best_first, windowed, window, stats);
+    if (R == 4) return run2d_cta<double, 4>(cost, cost_qstride, T, rows, cols, nq, seeds, nblocks, best_first, windowed, window, stats);
+    return run2d_cta<double, 2>(cost, cost_qstride, T, rows, cols, nq, seeds, nblocks, best_first, windowed, window, stats);
+}
+int emu_solve2d_cta_f32(const float *cost, long long cost_qstride, float *T, int rows, int cols, int nq, const int *seeds,
+                        int R, int nblocks, int best_first, int windowed, int window, unsigned long long *stats) {
+    if (R == 1) return run2d_cta<float, 1>(cost, cost_qstride, T, rows, cols, nq, seeds, nblocks, best_first, windowed, window, stats);
+    if (R == 4) return run2d_cta<float, 4>(cost, cost_qstride, T, rows, cols, nq, seeds, nblocks, best_first, windowed, window, stats);
+    return run2d_cta<float, 2>(cost, cost_qstride, T, rows, cols, nq, seeds, nblocks, best_first, windowed, window, stats);
 }
 int emu_solve3d_f64(const double *cost, long long cost_qstride, double *T, int ny, int nx, int nz, int nq,
                     const int *seeds, int tz, int nblocks, unsigned long long *stats) {
