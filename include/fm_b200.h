@@ -70,27 +70,37 @@ typedef struct fmb_stats {
     double init_kernel_ms;  /* device time of the init (fill + seed) launches that preceded it */
     uint64_t cyc_wait, cyc_load, cyc_relax, cyc_store; /* warp-cycles per phase, summed over worker warps (2D) */
     uint64_t reserved[1];
+    uint64_t cyc_check;     /* sweep engine: cycles of the check passes (part of cyc_relax), thread 0 of every CTA */
+    uint64_t noop_visits;   /* sweep engine: visits whose first check pass found the tile already at its fixed point */
+    uint64_t rounds;        /* sweep engine: rounds of four sweeps */
 } fmb_stats;
 
 /* Tunables of the solvers: process-wide, read by every solve call (no getenv() on the call path; the FMB_*
  * environment variables only give the INITIAL values, read once at first use).  0 / -1 = automatic. */
 typedef struct fmb_options {
-    int32_t engine2d;     /* 0 auto, 1 warp-per-tile visits (round 1), 2 CTA-per-tile visits */
+    int32_t engine2d;     /* 0 auto, 1 warp-per-tile visits (round 1), 2 CTA-per-tile Jacobi visits, 3 four-warp sweep visits */
     int32_t cta_cells;    /* cells per thread of the CTA engine: 0 auto, 1, 2 or 4 */
     int32_t tile_w2d;     /* tile width of the warp engine: 16 or 32 */
     int32_t tile_z3d;     /* 3D tile depth: 16 or 32 */
     int32_t best_first;   /* per-query best-first order: -1 auto, 0 off, 1 on */
     int32_t windowed;     /* windowed FIFO order of one large map: -1 auto, 0 off, 1 on */
-    int32_t window;       /* window in levels (0 = default) */
+    int32_t window;       /* window in levels (-1 = default) */
     int32_t worker_div;   /* tiles per worker used to size the grid (0 = automatic) */
     int32_t max_blocks;   /* cap on the persistent grid (0 = none) */
     int32_t watchdog_ms;  /* device watchdog, time without progress */
     int32_t step_cap;     /* in-tile iteration cap */
     int32_t engine3d;     /* 0 auto, 1 warp-per-tile, 2 CTA-per-tile */
-    int32_t reserved[4];
+    int32_t level_div;    /* windowed order: levels per tile crossing at the source's cost (0 = default) */
+    int32_t win_running;  /* windowed order: running tiles hold their level (-1 auto, 0 off, 1 on) */
+    int32_t check_passes; /* sweep engine: Jacobi check passes tried before another round of sweeps (0 = default) */
+    int32_t reserved[1];
 } fmb_options;
 void fmb_get_options(fmb_options *out);
 int fmb_set_options(const fmb_options *in);
+
+/* Self-test: counts (into *d_bad, zeroed by the caller) the inputs of d_x[0..n) inside the range of the library's
+ * branch-free fp64 square root whose result differs in any bit from sqrt.rn.f64.  Must stay 0. */
+int fmb_debug_sqrt_check(const double *d_x, int64_t n, uint64_t *d_bad, void *stream);
 
 int fmb_version(void);
 const char *fmb_last_error(void);

@@ -20,11 +20,12 @@ class FmbStats(C.Structure):
     _fields_ = [("tile_visits", C.c_uint64), ("steps", C.c_uint64), ("evals", C.c_uint64),
                 ("pushes", C.c_uint64), ("cells_written", C.c_uint64), ("solve_kernel_ms", C.c_double),
                 ("init_kernel_ms", C.c_double), ("cyc_wait", C.c_uint64), ("cyc_load", C.c_uint64),
-                ("cyc_relax", C.c_uint64), ("cyc_store", C.c_uint64), ("reserved", C.c_uint64 * 1)]
+                ("cyc_relax", C.c_uint64), ("cyc_store", C.c_uint64), ("reserved", C.c_uint64 * 1),
+                ("cyc_check", C.c_uint64), ("noop_visits", C.c_uint64), ("rounds", C.c_uint64)]
 
     def as_dict(self):
         d = {k: int(getattr(self, k)) for k in ("tile_visits", "steps", "evals", "pushes", "cells_written",
-                                                "cyc_wait", "cyc_load", "cyc_relax", "cyc_store")}
+                                                "cyc_wait", "cyc_load", "cyc_relax", "cyc_store", "cyc_check", "noop_visits", "rounds")}
         d["deferrals"] = int(self.reserved[0])
         d["solve_kernel_ms"] = float(self.solve_kernel_ms)
         d["init_kernel_ms"] = float(self.init_kernel_ms)
@@ -34,8 +35,9 @@ class FmbStats(C.Structure):
 class FmbOptions(C.Structure):
     """fmb_options of include/fm_b200.h (process-wide solver tunables)."""
     _fields_ = [(k, C.c_int32) for k in ("engine2d", "cta_cells", "tile_w2d", "tile_z3d", "best_first", "windowed",
-                                         "window", "worker_div", "max_blocks", "watchdog_ms", "step_cap", "engine3d")]
-    _fields_ += [("reserved", C.c_int32 * 4)]
+                                         "window", "worker_div", "max_blocks", "watchdog_ms", "step_cap", "engine3d",
+                                         "level_div", "win_running", "check_passes")]
+    _fields_ += [("reserved", C.c_int32 * 1)]
 
 
 class FmbError(RuntimeError):
@@ -51,6 +53,7 @@ SIGNATURES = {
     "fmb_version": (C.c_int, []),
     "fmb_last_error": (C.c_char_p, []),
     "fmb_sm_count": (C.c_int, []),
+    "fmb_debug_sqrt_check": (C.c_int, [_vp, _i64, _vp, _vp]),
     "fmb_get_options": (None, [C.POINTER(FmbOptions)]),
     "fmb_set_options": (C.c_int, [C.POINTER(FmbOptions)]),
     "fmb_workspace_bytes_2d": (_sz, [_i32, _i32, _i32]),

@@ -38,6 +38,12 @@ struct Problem2D {
     int *win_hint;           // lowest level that may be non-empty
     int *tile_level;         // [ntiles] level recorded when the tile was queued
     double *win_inv_delta;   // 1 / (T units per level), set by the seed kernel
+    unsigned long long *run_prio;   // [ntiles] priority a tile had when its current / last visit started (windowed == 2)
+    int precheck;            // sweep engine: 1 = a visit opens with one check pass (recognises no-op visits)
+    int check_passes;        // sweep engine: Jacobi check passes tried before another round of sweeps (>= 1)
+    int win_div;             // levels per tile crossing at the source's cost (1 in the warp engine)
+    int win_running;         // 1: a tile keeps its level count while it RUNS (released when it finishes), so the
+                             //    window is measured from the lowest queued-or-running level
 };
 constexpr int WIN_LEVELS = 8192;
 __device__ __forceinline__ int win_level(unsigned long long pbits, double inv_delta) {
@@ -69,6 +75,28 @@ __device__ __forceinline__ real eikonal_update(real a, real b, real c) {
     return N::mul((real)0.5, N::add(N::add(a, b), N::sqrt(disc)));
 }
 
+// The same update without divergent branches (both branches evaluated, one selected): the sweep engine runs it
+// inside a one-warp dependent chain where a divergent branch costs more than the spare arithmetic, and ptxas
+// can interleave independent evaluations only when there is no branch between them.  Same operations in the
+// same order on the selected path, hence the same bits.  The square root sees 1.0 instead of the discriminant
+// of the one-sided case (negative / NaN / inf).  Precondition: finite costs lie in [COST_MIN, COST_MAX] (the
+// range in which the discriminant stays inside the branch-free square root's domain); the sweep engine checks
+// it on every tile it visits and fails the solve loudly otherwise (DEV_COSTRANGE).
+template <typename real> struct cost_range;
+template <> struct cost_range<double> { static constexpr double lo = 1e-140, hi = 1e140; };
+template <> struct cost_range<float> { static constexpr float lo = 1e-15f, hi = 1e15f; };
+template <typename real>
+__device__ __forceinline__ real eikonal_update_sel(real a, real b, real c) {
+    using N = num<real>;
+    const real m = a < b ? a : b;
+    const real d = N::sub(a, b);
+    const bool two_sided = fabs(d) <= c && c < N::inf();
+    const real one = N::add(m, c);
+    const real disc = N::sub(N::mul((real)2, N::mul(c, c)), N::mul(d, d));
+    const real two = N::mul((real)0.5, N::add(N::add(a, b), sqrt_rn_fast(two_sided ? disc : (real)1)));
+    return two_sided ? two : one;
+}
+
 template <typename real, int TW>
 struct Tile2D {
     static constexpr int PT = TW + 2;                         // smem row pitch (even, PT-1 odd: conflict-free skews)
@@ -98,14 +126,15 @@ __global__ void init_fill2d_kernel(Problem2D<real> P, int ring_slots) {
     for (long long i = tid; i < ntiles; i += nth) {
         P.tile_state[i] = ST_IDLE;
         if (P.best_first || P.windowed) P.tile_prio[i] = 0x7ff0000000000000ULL;
+        if (P.windowed == 2) P.run_prio[i] = 0x7ff0000000000000ULL;
     }
     for (long long i = tid; i < ring_slots; i += nth) P.q.ring[i] = -1;
-    if (P.windowed)
+    if (P.windowed == 1)
         for (long long i = tid; i < WIN_LEVELS; i += nth) P.lev_count[i] = 0;
     if (tid == 0) {
         QueueCtl z = {};
         *P.q.ctl = z;
-        if (P.windowed) *P.win_hint = WIN_LEVELS - 1;
+        if (P.windowed == 1) *P.win_hint = WIN_LEVELS - 1;
     }
 }
 
@@ -120,9 +149,10 @@ __global__ void init_seed2d_kernel(Problem2D<real> P) {
     P.T[q * P.T_qstride + (long long)sy * P.T_pitch + sx] = (real)0;
     const int tx = sx / TW, ty = sy / TILE_H;
     const int base = q * P.ntx * P.nty;
-    if (P.windowed) {        // one level = the time to cross one tile at the source's cost
+    if (P.windowed == 1) {        // one level = the time to cross one tile at the source's cost
         const real c0 = P.cost[q * P.cost_qstride + (long long)sy * P.cost_pitch + sx];
-        *P.win_inv_delta = (c0 > (real)0 && c0 < num<real>::inf()) ? 1.0 / ((double)TW * (double)c0) : 1.0 / (double)TW;
+        const double div = P.win_div > 0 ? (double)P.win_div : 1.0;
+        *P.win_inv_delta = (c0 > (real)0 && c0 < num<real>::inf()) ? div / ((double)TW * (double)c0) : div / (double)TW;
     }
     int cand[5][2] = {{tx, ty}, {-1, -1}, {-1, -1}, {-1, -1}, {-1, -1}};
     if (sx % TW == 0 && tx > 0) { cand[1][0] = tx - 1; cand[1][1] = ty; }
@@ -134,7 +164,7 @@ __global__ void init_seed2d_kernel(Problem2D<real> P) {
         int item = base + cand[k][1] * P.ntx + cand[k][0];
         if (tile_activate(P.tile_state, P.q.ctl, item)) {
             if (P.best_first || P.windowed) P.tile_prio[item] = 0ULL;
-            if (P.windowed) win_count_push<real>(P, item);
+            if (P.windowed == 1) win_count_push<real>(P, item);
             q_push(P.q, P.best_first ? q : item);
             atomicAdd(&P.q.ctl->pushes, 1ULL);
         }
@@ -514,7 +544,7 @@ __global__ void __launch_bounds__(WARPS * 32) solve2d_kernel(Problem2D<real> P) 
                     }
                 }
                 if (newly || requeue) {
-                    if (!BEST && P.windowed) win_count_push<real>(P, tgt);
+                    if (!BEST && P.windowed == 1) win_count_push<real>(P, tgt);
                     q_push(P.q, BEST ? q : tgt);
                     pushed = true;
                 }

@@ -85,12 +85,15 @@ void opt_defaults_locked() {
     g_opt.tile_z3d = env_int("FMB_TZ3D", 16);
     g_opt.best_first = env_int("FMB_BEST_FIRST", -1);
     g_opt.windowed = env_int("FMB_WINDOWED", -1);
-    g_opt.window = env_int("FMB_WINDOW", 0);
+    g_opt.window = env_int("FMB_WINDOW", -1);
     g_opt.worker_div = env_int("FMB_WORKER_DIV", 0);
     g_opt.max_blocks = env_int("FMB_MAX_BLOCKS", 0);
     g_opt.watchdog_ms = env_int("FMB_WATCHDOG_MS", 20000);
     g_opt.step_cap = env_int("FMB_STEP_CAP", 1 << 20);
     g_opt.engine3d = env_int("FMB_ENGINE3D", 0);
+    g_opt.level_div = env_int("FMB_LEVEL_DIV", 0);
+    g_opt.win_running = env_int("FMB_WIN_RUNNING", -1);
+    g_opt.check_passes = env_int("FMB_CHECK_PASSES", 0);
     g_opt_init = true;
 }
 fmb_options opt() {
@@ -119,7 +122,7 @@ unsigned pow2_at_least(long long v) {
 
 // workspace layout: [QueueCtl | pad to 256] [tile_state: ntiles ints] [ring: slots ints]
 struct WsLayout {
-    size_t ctl_off, state_off, ring_off, prio_off, win_off, level_off, total;
+    size_t ctl_off, state_off, ring_off, prio_off, win_off, level_off, runprio_off, total;
     unsigned ring_slots;
 };
 WsLayout ws_layout(long long ntiles) {
@@ -133,7 +136,8 @@ WsLayout ws_layout(long long ntiles) {
     // windowed order: [inv_delta double | hint int | pad] [lev_count: WIN_LEVELS ints] [tile_level: ntiles ints]
     L.win_off = (L.prio_off + (size_t)ntiles * sizeof(unsigned long long) + 255) & ~(size_t)255;
     L.level_off = L.win_off + 256 + (size_t)fmb::WIN_LEVELS * sizeof(int);
-    L.total = L.level_off + (size_t)ntiles * sizeof(int);
+    L.runprio_off = (L.level_off + (size_t)ntiles * sizeof(int) + 255) & ~(size_t)255;
+    L.total = L.runprio_off + (size_t)ntiles * sizeof(unsigned long long);
     return L;
 }
 
@@ -227,6 +231,37 @@ int launch_solve2d_cta(fmb::Problem2D<real> P, const WsLayout &L, cudaStream_t s
     return FMB_OK;
 }
 
+// Sweep engine (eikonal2d_cta.cuh): 4 warps per tile visit, one diagonal-wavefront sweep each
+template <typename real, bool BEST>
+int launch_solve2d_sweep(fmb::Problem2D<real> P, const WsLayout &L, cudaStream_t st, int resume_activate = -1) {
+    const size_t smem = fmb::Tile2D<real, 32>::WARP_BYTES + 256;
+    auto kern = fmb::solve2d_sweep_kernel<real, BEST>;
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem), "occupancy(solve2d_sweep)");
+    if (per_sm < 1) return fail(FMB_E_CUDA, "solve2d_sweep kernel does not fit on an SM%s");
+    const long long ntiles = (long long)P.nq * P.ntx * P.nty;
+    long long blocks = (long long)per_sm * sm_count();
+    const fmb_options O = opt();
+    const int div = O.worker_div > 0 ? O.worker_div : (P.nq == 1 ? 2 : 1);
+    const long long need = (ntiles + div - 1) / div;
+    if (blocks > need) blocks = need;
+    if (blocks < 1) blocks = 1;
+    if (O.max_blocks > 0 && blocks > O.max_blocks) blocks = O.max_blocks;
+    const long long cells = (long long)P.rows * P.cols * P.nq;
+    long long fill_blocks = (cells + 256 * 8 - 1) / (256 * 8);
+    if (fill_blocks > (long long)sm_count() * 16) fill_blocks = (long long)sm_count() * 16;
+    if (fill_blocks < 1) fill_blocks = 1;
+    cudaGetLastError();
+    timing_begin(st);
+    launch_init2d<real, 32>(P, L, st, resume_activate, fill_blocks);
+    timing_mid(st);
+    kern<<<(unsigned)blocks, 128, smem, st>>>(P);
+    cudaError_t le = cudaGetLastError();
+    timing_end(st);
+    CK(le, "launch solve2d_sweep");
+    return FMB_OK;
+}
+
 template <typename real>
 int solve2d(const real *d_cost, int64_t cost_pitch, int64_t cost_qstride, real *d_T, int64_t T_pitch,
             int64_t T_qstride, int rows, int cols, int nq, const int32_t *d_seeds, void *d_ws, size_t ws_bytes,
@@ -236,8 +271,8 @@ int solve2d(const real *d_cost, int64_t cost_pitch, int64_t cost_qstride, real *
     if (cost_pitch < cols || T_pitch < cols) return fail(FMB_E_INVALID, "pitch smaller than cols%s");
     const fmb_options O = opt();
     // engine: CTA-per-tile (32-wide tiles) unless the warp-per-tile engine of round 1 is asked for
-    const int engine = O.engine2d > 0 ? O.engine2d : 2;
-    int tw = engine == 2 ? 32 : O.tile_w2d;
+    const int engine = O.engine2d > 0 ? O.engine2d : 3;
+    int tw = engine >= 2 ? 32 : O.tile_w2d;
     if (tw != 16 && tw != 32) return fail(FMB_E_INVALID, "tile_w2d must be 16 or 32%s");
     const long long ntiles = tiles2d(rows, cols, tw) * nq;
     if (ntiles >= (1LL << 30)) return fail(FMB_E_INVALID, "too many tiles for one launch%s");
@@ -264,13 +299,26 @@ int solve2d(const real *d_cost, int64_t cost_pitch, int64_t cost_qstride, real *
     P.arm_rows = arm_rows;
     if (resume_activate >= 0) P.best_first = 0;
     // windowed FIFO (deferral of tiles far ahead of the lowest queued level): one large map only
-    P.windowed = (!P.best_first && resume_activate < 0 && nq == 1) ? (O.windowed >= 0 ? O.windowed : (ntiles >= 16384 ? 1 : 0)) : 0;
-    P.win_window = O.window > 0 ? O.window : 2;
+    // one map: the sweep engine runs the local causal order at every size; the older engines keep the windowed FIFO
+    // for maps of >= 16384 tiles
+    P.windowed = (!P.best_first && resume_activate < 0 && nq == 1)
+                     ? (O.windowed >= 0 ? O.windowed : (engine == 3 ? 2 : (ntiles >= 16384 ? 1 : 0))) : 0;
+    if (P.windowed == 2 && engine != 3) P.windowed = 1;       // the local causal order exists in the sweep engine only
+    P.win_window = O.window >= 0 ? O.window : 2;
+    P.check_passes = O.check_passes > 0 ? O.check_passes : 4;
+    P.precheck = 0;
+    P.win_div = engine == 3 ? (O.level_div > 0 ? O.level_div : 1) : 1;
+    P.win_running = engine == 3 ? (O.win_running >= 0 ? O.win_running : 1) : 0;
     P.win_inv_delta = (double *)(ws + L.win_off);
     P.win_hint = (int *)(ws + L.win_off + 8);
     P.lev_count = (int *)(ws + L.win_off + 256);
     P.tile_level = (int *)(ws + L.level_off);
+    P.run_prio = (unsigned long long *)(ws + L.runprio_off);
     cudaStream_t st = (cudaStream_t)stream;
+    if (engine == 3) {
+        if (P.best_first) return launch_solve2d_sweep<real, true>(P, L, st);
+        return launch_solve2d_sweep<real, false>(P, L, st, resume_activate);
+    }
     if (engine == 2) {
         const int R = O.cta_cells > 0 ? O.cta_cells : 2;
         if (R != 1 && R != 2 && R != 4) return fail(FMB_E_INVALID, "cta_cells must be 1, 2 or 4%s");
@@ -293,7 +341,27 @@ int solve2d(const real *d_cost, int64_t cost_pitch, int64_t cost_qstride, real *
 
 }  // namespace
 
+namespace {
+// bitwise comparison of the branch-free square root with sqrt.rn.f64 (self-test entry, tests/test_gpu_parity.py)
+__global__ void sqrt_check_kernel(const double *x, long long n, unsigned long long *bad) {
+    unsigned long long mine = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double v = x[i];
+        if (!fmb::sqrt_fast_ok(v)) continue;
+        if (__double_as_longlong(fmb::sqrt_rn_fast(v)) != __double_as_longlong(__dsqrt_rn(v))) ++mine;
+    }
+    if (mine) atomicAdd(bad, mine);
+}
+}  // namespace
+
 extern "C" {
+
+int fmb_debug_sqrt_check(const double *d_x, int64_t n, uint64_t *d_bad, void *stream) {
+    if (!d_x || !d_bad || n < 1) return fail(FMB_E_INVALID, "bad argument%s");
+    sqrt_check_kernel<<<1184, 256, 0, (cudaStream_t)stream>>>(d_x, n, (unsigned long long *)d_bad);
+    CK(cudaGetLastError(), "launch sqrt_check");
+    return FMB_OK;
+}
 
 int fmb_version(void) { return 100; }
 const char *fmb_last_error(void) { return g_err; }
@@ -345,6 +413,7 @@ int fmb_finish(void *d_ws, size_t ws_bytes, void *stream, fmb_stats *stats) {
         stats->tile_visits = h.visits; stats->steps = h.steps; stats->evals = h.evals;
         stats->pushes = h.pushes; stats->cells_written = h.cells_written;
         stats->reserved[0] = h.pad[0];     /* deferrals of the windowed order */
+        stats->cyc_check = h.pad[1]; stats->noop_visits = h.noop_visits; stats->rounds = h.rounds;
         stats->cyc_wait = h.cyc_wait; stats->cyc_load = h.cyc_load; stats->cyc_relax = h.cyc_relax; stats->cyc_store = h.cyc_store;
         Timing *tm = timing_slot((cudaStream_t)stream, false);
         if (tm && tm->armed) {
@@ -355,6 +424,7 @@ int fmb_finish(void *d_ws, size_t ws_bytes, void *stream, fmb_stats *stats) {
         }
     }
     if (h.abort == fmb::DEV_WATCHDOG) return fail(FMB_E_WATCHDOG, "device watchdog fired: a queue wait exceeded FMB_WATCHDOG_MS%s");
+    if (h.abort == fmb::DEV_COSTRANGE) return fail(FMB_E_INVALID, "a finite cost lies outside the supported range [1e-140, 1e140] (fp32: [1e-15, 1e15])%s");
     if (h.abort == fmb::DEV_STEPCAP) return fail(FMB_E_STEPCAP, "in-tile iteration cap (FMB_STEP_CAP) exceeded%s");
     if (h.abort) return fail(FMB_E_CUDA, "unknown device-side failure%s");
     if (h.pending != 0) return fail(FMB_E_CUDA, "solver left with pending tiles%s");

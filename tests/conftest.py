@@ -58,3 +58,20 @@ def rel_err(a, ref):
     if not pos.any():
         return 0.0
     return float(np.max(np.abs(a[pos] - ref[pos]) / np.abs(ref[pos])))
+
+
+@pytest.fixture
+def fmb_opts():
+    """Set solver tunables (fmb_options of include/fm_b200.h) for one test; restored afterwards."""
+    from planning_motion_planning_b200 import _capi
+    saved = _capi.get_options()
+
+    def setter(**kw):
+        _capi.set_options(**kw)
+    yield setter
+    _capi.set_options(**saved)
+
+
+# 2D engines of the library: name -> fmb_options fields
+ENGINES_2D = {"sweep": dict(engine2d=3), "cta1": dict(engine2d=2, cta_cells=1), "cta2": dict(engine2d=2, cta_cells=2),
+              "cta4": dict(engine2d=2, cta_cells=4), "warp32": dict(engine2d=1, tile_w2d=32), "warp16": dict(engine2d=1, tile_w2d=16)}

@@ -35,17 +35,44 @@ def _gpu3d(eng, c, seeds, **kw):
 
 
 # ------------------------------------------------------------------ 2D solve
-@pytest.mark.parametrize("tw", ["32", "16"])
+@pytest.mark.parametrize("engine", ["sweep", "cta1", "cta2", "cta4", "warp32", "warp16"])
 @pytest.mark.parametrize("shape,goal", [((9, 9), [4, 4]), ((100, 100), [25, 25]), ((257, 300), [290, 3]),
                                         ((33, 65), [32, 31]), ((512, 512), [100, 400])])
-def test_solve2d_random_vs_oracle(eng, shape, goal, tw, monkeypatch):
+def test_solve2d_random_vs_oracle(eng, shape, goal, engine, fmb_opts):
+    from conftest import ENGINES_2D
     from oracle import oracle as O
-    monkeypatch.setenv("FMB_TW2D", tw)
+    fmb_opts(**ENGINES_2D[engine])
     c = rand_map(shape, 0)
     T = _gpu2d(eng, c, [goal])[0]
     assert rel_err(T, O.computeTmap(c, goal)) < TOL64
     st = eng.last_stats()
     assert st["tile_visits"] > 0 and st["evals"] >= np.isfinite(T).sum() - 1
+
+
+def test_branch_free_sqrt_is_correctly_rounded(eng):
+    """sqrt_rn_fast (csrc/fm_common.cuh) == sqrt.rn.f64 bit for bit: 3e7 random mantissas over the whole exponent
+    range it accepts, values next to perfect squares and powers of two, and the discriminants 2c^2 - d^2 of the
+    update for planner-like costs."""
+    import torch
+    from planning_motion_planning_b200 import _capi
+    g = torch.Generator(device="cuda").manual_seed(1)
+    n = 10_000_000
+    mant = torch.rand(n, dtype=torch.float64, device="cuda", generator=g) + 1.0
+    expo = torch.randint(-960, 1020, (n,), device="cuda", generator=g).to(torch.float64)
+    xs = [mant * torch.exp2(expo)]
+    k = torch.arange(1, n + 1, dtype=torch.float64, device="cuda")
+    sq = k * k
+    xs.append(torch.cat([sq, torch.nextafter(sq, sq * 2), torch.nextafter(sq, sq * 0)])[:n])
+    c = 1.0 + 304.0 * torch.rand(n, dtype=torch.float64, device="cuda", generator=g)
+    d = c * torch.rand(n, dtype=torch.float64, device="cuda", generator=g)
+    xs.append(2.0 * (c * c) - d * d)
+    p2 = torch.exp2(torch.arange(-960, 1020, dtype=torch.float64, device="cuda"))
+    xs.append(torch.cat([p2, torch.nextafter(p2, p2 * 2), torch.nextafter(p2, p2 * 0)]))
+    for x in xs:
+        bad = torch.zeros(1, dtype=torch.int64, device="cuda")
+        _capi.check(_capi.lib().fmb_debug_sqrt_check(x.data_ptr(), x.numel(), bad.data_ptr(), None))
+        torch.cuda.synchronize()
+        assert int(bad.item()) == 0
 
 
 def test_kat1_and_kat3_values(eng):
@@ -155,29 +182,32 @@ def test_solve2d_differential_random_obstacles(eng, seed):
     assert rel_err(T, O.computeTmap(c, [int(gx), int(gy)])) < TOL64
 
 
-def test_best_first_and_fifo_agree(eng, monkeypatch):
+@pytest.mark.parametrize("engine", ["sweep", "cta2", "warp32"])
+def test_best_first_and_fifo_agree(eng, engine, fmb_opts):
     """The two work orders of the persistent kernel reach the same fixed point."""
     import torch
     from oracle import oracle as O
     c = rand_map((160, 200), 9)
     goals = [[int(5 + 7 * i) % 190 + 2, int(3 + 11 * i) % 150 + 2] for i in range(16)]
     outs = []
-    for bf in ("0", "1"):
-        monkeypatch.setenv("FMB_BEST_FIRST", bf)
+    from conftest import ENGINES_2D
+    for bf in (0, 1):
+        fmb_opts(best_first=bf, **ENGINES_2D[engine])
         outs.append(_gpu2d(eng, c, goals))
     for q, g in enumerate(goals):
         ref = O.computeTmap(c, g)
         assert rel_err(outs[0][q], ref) < TOL64 and rel_err(outs[1][q], ref) < TOL64
 
 
-@pytest.mark.parametrize("window", ["1", "2", "8"])
-def test_windowed_order_reaches_the_same_field(eng, window, monkeypatch):
+@pytest.mark.parametrize("engine", ["sweep", "cta2", "warp32"])
+@pytest.mark.parametrize("window", [1, 2, 8])
+def test_windowed_order_reaches_the_same_field(eng, window, engine, fmb_opts):
     """Windowed FIFO (deferral of tiles far above the lowest queued level; the default for one map of
     >= 16384 tiles) forced on for smaller maps: same fixed point as the oracle, whatever the window."""
     from oracle import oracle as O
     from planning_motion_planning_b200 import synth
-    monkeypatch.setenv("FMB_WINDOWED", "1")
-    monkeypatch.setenv("FMB_WINDOW", window)
+    from conftest import ENGINES_2D
+    fmb_opts(windowed=1, window=window, **ENGINES_2D[engine])
     for c, g in ((rand_map((257, 300), 3), [290, 3]), (plateau_map(400, 2), [8, 8]), (synth.mars_costmap(768, 4), None)):
         if g is None:
             g = list(synth.free_cell_near(c, 100, 650))
@@ -270,12 +300,12 @@ def test_solve2d_8192_fixed_point_property(eng):
 
 
 # ------------------------------------------------------------------ 3D solve
-@pytest.mark.parametrize("tz", ["32", "16"])
+@pytest.mark.parametrize("tz", [32, 16])
 @pytest.mark.parametrize("shape,goal", [((9, 9, 9), [4, 4, 4]), ((24, 24, 24), [5, 6, 7]), ((13, 21, 40), [10, 5, 33]),
                                         ((44, 44, 28), [35, 27, 6]), ((64, 64, 64), [10, 50, 30])])
-def test_solve3d_random_vs_oracle(eng, shape, goal, tz, monkeypatch):
+def test_solve3d_random_vs_oracle(eng, shape, goal, tz, fmb_opts):
     from oracle import oracle as O
-    monkeypatch.setenv("FMB_TZ3D", tz)
+    fmb_opts(tile_z3d=tz)
     c = rand_map(shape, 0)
     T = _gpu3d(eng, c, [goal])[0]
     assert rel_err(T, O.computeTmap3D(c, goal)) < TOL64
@@ -428,18 +458,18 @@ def test_domain_decomposition_local_slabs(eng):
         assert float(((T - single).abs() / single.clamp_min(1e-300))[fin].max()) < 1e-12
 
 
-def test_device_side_failure_is_reported_not_hidden(eng, monkeypatch):
+def test_device_side_failure_is_reported_not_hidden(eng, fmb_opts):
     """A solve that cannot finish (in-tile iteration cap hit) raises; the next solve is unaffected."""
     import torch
     from oracle import oracle as O
     from planning_motion_planning_b200 import _capi
     c = rand_map((120, 120), 3)
     cd = torch.from_numpy(c).cuda()
-    monkeypatch.setenv("FMB_STEP_CAP", "3")
+    fmb_opts(step_cap=3)
     with pytest.raises(_capi.FmbError) as ei:
         eng.solve2d(cd, [[60, 60]])
     assert ei.value.code == _capi.FMB_E_STEPCAP
-    monkeypatch.delenv("FMB_STEP_CAP")
+    fmb_opts(step_cap=1 << 20)
     T = eng.solve2d(cd, [[60, 60]])[0].cpu().numpy()
     assert rel_err(T, O.computeTmap(c, [60, 60])) < TOL64
     with pytest.raises(_capi.FmbError):           # bad arguments are rejected by the C ABI

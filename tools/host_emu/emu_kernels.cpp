@@ -42,7 +42,7 @@ int run2d(const real *cost, long long cost_qstride, real *T, int rows, int cols,
     std::vector<int> lev_count(fmb::WIN_LEVELS), tile_level(ntiles);
     int win_hint = 0; double win_inv_delta = 1.0;
     P.windowed = (!P.best_first && nq == 1 && getenv("FMB_WINDOWED")) ? atoi(getenv("FMB_WINDOWED")) : 0;
-    P.win_window = getenv("FMB_WINDOW") ? atoi(getenv("FMB_WINDOW")) : 16;
+    P.win_window = getenv("FMB_WINDOW") ? atoi(getenv("FMB_WINDOW")) : 16; P.win_div = 1; P.win_running = 0; P.check_passes = 1; P.precheck = 0;
     P.lev_count = lev_count.data(); P.tile_level = tile_level.data(); P.win_hint = &win_hint; P.win_inv_delta = &win_inv_delta;
     emu::launch(2, 64, 0, [&] { fmb::init_fill2d_kernel<real>(P, (int)ring.size()); });
     emu::launch(1, 32 * ((nq + 31) / 32), 0, [&] { fmb::init_seed2d_kernel<real, TW>(P); });
@@ -75,13 +75,22 @@ int run2d_cta(const real *cost, long long cost_qstride, real *T, int rows, int c
     std::vector<int> lev_count(fmb::WIN_LEVELS), tile_level(ntiles);
     int win_hint = 0; double win_inv_delta = 1.0;
     P.windowed = (!best_first && nq == 1) ? windowed : 0;
-    P.win_window = window;
+    P.check_passes = 4; P.precheck = 0; P.win_window = window; P.win_div = R == 0 ? 2 : 1; P.win_running = R == 0 ? 1 : 0;
     P.lev_count = lev_count.data(); P.tile_level = tile_level.data(); P.win_hint = &win_hint; P.win_inv_delta = &win_inv_delta;
+    std::vector<unsigned long long> run_prio(ntiles);
+    P.run_prio = run_prio.data();
     emu::launch(2, 64, 0, [&] { fmb::init_fill2d_kernel<real>(P, (int)ring.size()); });
     emu::launch(1, 32 * ((nq + 31) / 32), 0, [&] { fmb::init_seed2d_kernel<real, TW>(P); });
-    const size_t smem = fmb::CtaTile2D<real>::BYTES;
-    if (best_first) emu::launch(nblocks, 1024 / R, smem, [&] { fmb::solve2d_cta_kernel<real, R, true>(P); });
-    else emu::launch(nblocks, 1024 / R, smem, [&] { fmb::solve2d_cta_kernel<real, R, false>(P); });
+    if (R == 0) {          // sweep engine
+        const size_t smem = fmb::Tile2D<real, 32>::WARP_BYTES + 256;
+        if (best_first) emu::launch(nblocks, 128, smem, [&] { fmb::solve2d_sweep_kernel<real, true>(P); });
+        else emu::launch(nblocks, 128, smem, [&] { fmb::solve2d_sweep_kernel<real, false>(P); });
+    } else {
+        const size_t smem = fmb::CtaTile2D<real>::BYTES;
+        constexpr int RR = R ? R : 1;
+        if (best_first) emu::launch(nblocks, 1024 / RR, smem, [&] { fmb::solve2d_cta_kernel<real, RR, true>(P); });
+        else emu::launch(nblocks, 1024 / RR, smem, [&] { fmb::solve2d_cta_kernel<real, RR, false>(P); });
+    }
     if (stats) { stats[0] = ctl.visits; stats[1] = ctl.steps; stats[2] = ctl.evals; stats[3] = ctl.pushes; stats[4] = ctl.cells_written; }
     return ctl.abort ? ctl.abort : (ctl.pending != 0 ? -1 : 0);
 }
@@ -135,12 +144,14 @@ int emu_solve2d_f32(const float *cost, long long cost_qstride, float *T, int row
 }
 int emu_solve2d_cta_f64(const double *cost, long long cost_qstride, double *T, int rows, int cols, int nq, const int *seeds,
                         int R, int nblocks, int best_first, int windowed, int window, unsigned long long *stats) {
+    if (R == 0) return run2d_cta<double, 0>(cost, cost_qstride, T, rows, cols, nq, seeds, nblocks, best_first, windowed, window, stats);
     if (R == 1) return run2d_cta<double, 1>(cost, cost_qstride, T, rows, cols, nq, seeds, nblocks, best_first, windowed, window, stats);
     if (R == 4) return run2d_cta<double, 4>(cost, cost_qstride, T, rows, cols, nq, seeds, nblocks, best_first, windowed, window, stats);
     return run2d_cta<double, 2>(cost, cost_qstride, T, rows, cols, nq, seeds, nblocks, best_first, windowed, window, stats);
 }
 int emu_solve2d_cta_f32(const float *cost, long long cost_qstride, float *T, int rows, int cols, int nq, const int *seeds,
                         int R, int nblocks, int best_first, int windowed, int window, unsigned long long *stats) {
+    if (R == 0) return run2d_cta<float, 0>(cost, cost_qstride, T, rows, cols, nq, seeds, nblocks, best_first, windowed, window, stats);
     if (R == 1) return run2d_cta<float, 1>(cost, cost_qstride, T, rows, cols, nq, seeds, nblocks, best_first, windowed, window, stats);
     if (R == 4) return run2d_cta<float, 4>(cost, cost_qstride, T, rows, cols, nq, seeds, nblocks, best_first, windowed, window, stats);
     return run2d_cta<float, 2>(cost, cost_qstride, T, rows, cols, nq, seeds, nblocks, best_first, windowed, window, stats);
@@ -206,7 +217,7 @@ int emu_resolve2d_f64(const double *cost, double *T, int rows, int cols, const i
     std::vector<unsigned long long> prio(ntiles);
     fmb::QueueCtl ctl;
     P.tile_state = state.data(); P.q.ctl = &ctl; P.q.ring = ring.data(); P.q.ring_mask = (unsigned)ring.size() - 1;
-    P.q.watchdog_cycles = 1LL << 40; P.step_cap = 1 << 20; P.tile_prio = prio.data(); P.best_first = 0; P.arm_rows = halo_rows; P.windowed = 0; P.win_window = 0;
+    P.q.watchdog_cycles = 1LL << 40; P.step_cap = 1 << 20; P.tile_prio = prio.data(); P.best_first = 0; P.arm_rows = halo_rows; P.windowed = 0; P.win_window = 0; P.win_div = 1; P.win_running = 0; P.check_passes = 1; P.precheck = 0;
     P.lev_count = nullptr; P.tile_level = nullptr; P.win_hint = nullptr; P.win_inv_delta = nullptr;
     emu::launch(2, 64, 0, [&] { fmb::init_resume2d_kernel<double>(P, (int)ring.size()); });
     if (activate & 7) emu::launch((unsigned)((ntiles + 63) / 64), 64, 0, [&] { fmb::activate_rows2d_kernel<double>(P, activate); });
