@@ -65,7 +65,9 @@ def computeTmap(costMap, goal, start):
     T0 = T[0]
     s = _c.node2(start, swap)
     rows, cols = T0.shape
-    if 0 <= s[0] < cols and 0 <= s[1] < rows and bool(torch.isfinite(T0[s[1], s[0]])):
+    # start == goal: the reference closes the goal before its loop, so the goal is never popped, the early exit never
+    # fires and the FULL field comes back (FastMarching3D.py:127-142, same loop)
+    if 0 <= s[0] < cols and 0 <= s[1] < rows and bool(torch.isfinite(T0[s[1], s[0]])) and s != _c.node2(goal, swap):
         rank = _c.pop_ranks_lifo2d(T0, cd, _c.node2(goal, swap), transposed=swap)
         T0 = _c.truncate(T0, cd, rank, int(rank[s[1], s[0]]))
     return _to_numpy_field(T0, swap)
@@ -82,7 +84,13 @@ def biComputeTmap(costMap, goal, start):
     # run side by side on two streams
     rG, rS = _c.both_fronts(lambda: _c.pop_ranks_lifo2d(TG, cd, _c.node2(goal, swap), transposed=swap),
                             lambda: _c.pop_ranks_lifo2d(TS, cd, _c.node2(start, swap), transposed=swap))
-    k, j = _c.bi_join(rG, rS)
+    if _c.node2(goal, swap) == _c.node2(start, swap):
+        # both fronts leave the same cell: each pops its first node (the same one) in round 1 and G's is found closed
+        # in S straight away (FastMarching.py:143-152): k = 1, the join is the first popped node
+        hit = torch.nonzero(rG.reshape(-1) == 1)
+        k, j = (1, int(hit[0])) if hit.numel() else (None, None)
+    else:
+        k, j = _c.bi_join(rG, rS)
     if k is None:
         raise NameError("name 'nodeJoin' is not defined")
     cols = TG.shape[1]

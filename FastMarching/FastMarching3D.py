@@ -29,9 +29,12 @@ def computeTmap(costMap, goal, start):
         raise IndexError(f"goal {g} is outside the {ny}x{nx}x{nz} volume")
     dev = _c.device()
     cd = torch.from_numpy(c).to(dev)
-    T = engine.solve3d(cd, [g], nq=1)[0]
+    # exact=True: the polish pass gives the field the reference's own rounding (libm pow for `**2` on scalars), so
+    # that exactly tied values are tied here too and the early exit accepts the reference's set of cells
+    T = engine.solve3d(cd, [g], nq=1, exact=_c.EXACT_3D)[0]
     s = [int(np.int64(v)) for v in start]
-    if 0 <= s[0] < nx and 0 <= s[1] < ny and 0 <= s[2] < nz and bool(torch.isfinite(T[s[1], s[0], s[2]])):
+    # (start == goal: the goal is closed before the loop and never popped, so the reference returns the full field)
+    if 0 <= s[0] < nx and 0 <= s[1] < ny and 0 <= s[2] < nz and s != g and bool(torch.isfinite(T[s[1], s[0], s[2]])):
         # Only the order INSIDE the tie group of `start` decides which cells are accepted when it pops:
         # the plain sort is exact unless another cell carries T[start] (to the tolerance of the device field); then the reference's LIFO
         # order among equal values is reproduced by the ordered sweep (csrc/tiekeys.cuh).

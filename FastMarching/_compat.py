@@ -75,6 +75,7 @@ _BIG = torch.iinfo(torch.int64).max
 # here) but on plateau maps the reference itself holds many DISTINCT values one or two ulp apart, and merging
 # those misorders far more cells (154 vs 1 on the case that motivated it).
 TIE_TOL_2D = 0.0
+EXACT_3D = False         # FastMarching3D.computeTmap: follow the solve with the exact polish pass (fmb_polish3d_f64); measured: no fewer tie mismatches
 TIE_TOL_3D = 0.0
 
 

@@ -73,6 +73,7 @@ typedef struct fmb_stats {
     uint64_t cyc_check;     /* sweep engine: cycles of the check passes (part of cyc_relax), thread 0 of every CTA */
     uint64_t noop_visits;   /* sweep engine: visits whose first check pass found the tile already at its fixed point */
     uint64_t rounds;        /* sweep engine: rounds of four sweeps */
+    uint64_t continuations; /* sweep engine: re-activations of a running tile served in place */
 } fmb_stats;
 
 /* Tunables of the solvers: process-wide, read by every solve call (no getenv() on the call path; the FMB_*
@@ -93,7 +94,9 @@ typedef struct fmb_options {
     int32_t level_div;    /* windowed order: levels per tile crossing at the source's cost (0 = default) */
     int32_t win_running;  /* windowed order: running tiles hold their level (-1 auto, 0 off, 1 on) */
     int32_t check_passes; /* sweep engine: Jacobi check passes tried before another round of sweeps (0 = default) */
-    int32_t reserved[1];
+    int32_t pipeline;     /* sweep engine, one map: pipelined visits (-1 auto, 0 off, 1 on) */
+    int32_t precheck;     /* sweep engine: open every visit with a check pass (-1 auto, 0, 1) */
+    int32_t reserved[3];
 } fmb_options;
 void fmb_get_options(fmb_options *out);
 int fmb_set_options(const fmb_options *in);
@@ -146,6 +149,16 @@ int fmb_solve3d_f64(const double *d_cost, int64_t cost_qstride, double *d_T, int
 int fmb_solve3d_f32(const float *d_cost, int64_t cost_qstride, float *d_T, int64_t T_qstride,
                     int ny, int nx, int nz, int nq, const int32_t *d_seeds,
                     void *d_ws, size_t ws_bytes, void *stream);
+
+/* Polish pass: re-relaxes EVERY cell of the converged field(s) in d_T with the reference's own rounding of the squares
+ * it takes on NumPy scalars (FastMarching3D.py:68-71: `**2` = libm pow(x, 2.0), not correctly rounded; csrc/pow2_glibc.cuh
+ * reproduces it bit for bit) until the field is the exact fixed point of THAT update.  The values move by an ulp in a
+ * fraction of a percent of the cells: irrelevant for the 1e-9 tolerance, decisive for exact ties of the pop order
+ * (early exit of FastMarching3D.computeTmap :141-142 on uniform-cost volumes).  Same arguments as fmb_solve3d_f64,
+ * d_T = its result; asynchronous, fmb_finish() reports. */
+int fmb_polish3d_f64(const double *d_cost, int64_t cost_qstride, double *d_T, int64_t T_qstride,
+                     int ny, int nx, int nz, int nq, const int32_t *d_seeds,
+                     void *d_ws, size_t ws_bytes, void *stream);
 
 /* Synchronise `stream`, report device-side failures of the solves issued with
  * this workspace, and (optionally) return the counters.  Synchronous. */

@@ -639,4 +639,7 @@ int64_t orc_trace3d(const double *T, int ny, int nx, int nz, const double *init,
     return K;
 }
 
+/* libm pow(x, 2.0) over an array: what `x**2` on a NumPy scalar evaluates to (test helper for the device port) */
+void orc_pow2_array(const double *x, double *out, int64_t n) { for (int64_t i = 0; i < n; ++i) out[i] = pw2(x[i]); }
+
 int orc_version(void) { return 1; }

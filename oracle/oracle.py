@@ -51,6 +51,8 @@ def lib():
         L.orc_trace2d.restype = C.c_int64
         L.orc_trace2d.argtypes = [dp, C.c_int, C.c_int, dp, dp, C.c_double, dp, C.c_int64, C.POINTER(C.c_int)]
         L.orc_fmm3d.restype = C.c_int
+        L.orc_pow2_array.argtypes = [dp, dp, C.c_int64]
+        L.orc_pow2_array.restype = None
         L.orc_fmm3d.argtypes = [dp, C.c_int, C.c_int, C.c_int, ip32, ip32, dp, ip64, ip64, ip64]
         L.orc_interp3d.restype = C.c_double
         L.orc_interp3d.argtypes = [dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_int)]
@@ -202,3 +204,11 @@ def getPathGDM3D(totalCostMap, initWaypoint, endWaypoint, tau, return_status=Fal
     if st.value in _EXC:
         raise _EXC[st.value]("reference getPathGDM (3D) raises here")
     return out[:k].copy()
+
+
+def pow2(x):
+    """libm ``pow(x, 2.0)`` element-wise: the value of ``x**2`` for a NumPy *scalar* x (FastMarching3D.py:68-71)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.empty_like(x)
+    lib().orc_pow2_array(_dp(x), _dp(out), x.size)
+    return out

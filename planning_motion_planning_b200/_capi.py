@@ -21,11 +21,12 @@ class FmbStats(C.Structure):
                 ("pushes", C.c_uint64), ("cells_written", C.c_uint64), ("solve_kernel_ms", C.c_double),
                 ("init_kernel_ms", C.c_double), ("cyc_wait", C.c_uint64), ("cyc_load", C.c_uint64),
                 ("cyc_relax", C.c_uint64), ("cyc_store", C.c_uint64), ("reserved", C.c_uint64 * 1),
-                ("cyc_check", C.c_uint64), ("noop_visits", C.c_uint64), ("rounds", C.c_uint64)]
+                ("cyc_check", C.c_uint64), ("noop_visits", C.c_uint64), ("rounds", C.c_uint64),
+                ("continuations", C.c_uint64)]
 
     def as_dict(self):
         d = {k: int(getattr(self, k)) for k in ("tile_visits", "steps", "evals", "pushes", "cells_written",
-                                                "cyc_wait", "cyc_load", "cyc_relax", "cyc_store", "cyc_check", "noop_visits", "rounds")}
+                                                "cyc_wait", "cyc_load", "cyc_relax", "cyc_store", "cyc_check", "noop_visits", "rounds", "continuations")}
         d["deferrals"] = int(self.reserved[0])
         d["solve_kernel_ms"] = float(self.solve_kernel_ms)
         d["init_kernel_ms"] = float(self.init_kernel_ms)
@@ -36,8 +37,8 @@ class FmbOptions(C.Structure):
     """fmb_options of include/fm_b200.h (process-wide solver tunables)."""
     _fields_ = [(k, C.c_int32) for k in ("engine2d", "cta_cells", "tile_w2d", "tile_z3d", "best_first", "windowed",
                                          "window", "worker_div", "max_blocks", "watchdog_ms", "step_cap", "engine3d",
-                                         "level_div", "win_running", "check_passes")]
-    _fields_ += [("reserved", C.c_int32 * 1)]
+                                         "level_div", "win_running", "check_passes", "pipeline", "precheck")]
+    _fields_ += [("reserved", C.c_int32 * 3)]
 
 
 class FmbError(RuntimeError):
@@ -63,6 +64,7 @@ SIGNATURES = {
     "fmb_workspace_bytes_3d": (_sz, [_i32, _i32, _i32, _i32]),
     "fmb_solve3d_f64": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
     "fmb_solve3d_f32": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
+    "fmb_polish3d_f64": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
     "fmb_finish": (C.c_int, [_vp, _sz, _vp, C.POINTER(FmbStats)]),
     "fmb_trace2d_f64": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _dbl, _i32, _vp, _i64, _vp, _vp, _vp]),
     "fmb_trace3d_f64": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _dbl, _i32, _vp, _i64, _vp, _vp, _vp]),

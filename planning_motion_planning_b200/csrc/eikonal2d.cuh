@@ -39,6 +39,7 @@ struct Problem2D {
     int *tile_level;         // [ntiles] level recorded when the tile was queued
     double *win_inv_delta;   // 1 / (T units per level), set by the seed kernel
     unsigned long long *run_prio;   // [ntiles] priority a tile had when its current / last visit started (windowed == 2)
+    int pipeline;            // sweep engine, local causal order: pipelined visits (streaming halos, early activation)
     int precheck;            // sweep engine: 1 = a visit opens with one check pass (recognises no-op visits)
     int check_passes;        // sweep engine: Jacobi check passes tried before another round of sweeps (>= 1)
     int win_div;             // levels per tile crossing at the source's cost (1 in the warp engine)

@@ -8,6 +8,7 @@
 // neighbours are other lanes, reached by shuffle; z neighbours are mask bits).
 #pragma once
 #include "fm_common.cuh"
+#include "pow2_glibc.cuh"
 
 namespace fmb {
 
@@ -24,6 +25,7 @@ struct Problem3D {
     int *tile_state;
     Queue q;
     int step_cap;
+    int arm_all;             // 1: every visit re-arms all cells of its tile (polish pass over an existing field)
 };
 
 // FastMarching3D.py:59-75 -- descending-dimension quadratic solver, in the
@@ -71,6 +73,40 @@ __device__ __forceinline__ real solve3d_update(real t0, real t1, real t2, real C
         }
     }
     return num<real>::inf();                          // no finite neighbour (reference: max([]) raises)
+}
+
+// The same solver with the reference's OWN rounding of the squares it takes on NumPy scalars
+// (FastMarching3D.py:68-71: (Tmax-Tarray[a])**2, C**2 and (sumlist(Tarray))**2 go through libm pow, which is not
+// correctly rounded; array(Tarray)**2 is an exact-rounded product): bit-for-bit the value the reference assigns.
+// ~5x the arithmetic of solve3d_update, so it runs as a polish pass over the converged field (fmb_polish3d_f64):
+// the two fixed points differ by an ulp in a fraction of a percent of the cells -- enough to decide exact ties of
+// the pop order, and with them the accepted set of the early exit on uniform-cost volumes.
+__device__ __forceinline__ double solve3d_update_exact(double t0, double t1, double t2, double C) {
+    using N = num<double>;
+    const double C2 = pow2_glibc(C);
+    double a[3] = {t0, t1, t2};
+#pragma unroll
+    for (int n = 3; n >= 1; --n) {
+        int im = 0;
+#pragma unroll
+        for (int i = 1; i < 3; ++i) if (i < n && a[i] > a[im]) im = i;          // max(): first maximum
+        const double mx = a[im];
+        double sumT = 0.0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) if (i < n) sumT = N::add(sumT, pow2_glibc(N::sub(mx, a[i])));
+        if (C2 > sumT) {
+            double S, Q;
+            if (n == 3) { S = N::add(a[0], N::add(a[1], a[2])); Q = N::add(N::mul(a[0], a[0]), N::add(N::mul(a[1], a[1]), N::mul(a[2], a[2]))); }
+            else if (n == 2) { S = N::add(a[0], a[1]); Q = N::add(N::mul(a[0], a[0]), N::mul(a[1], a[1])); }
+            else { S = a[0]; Q = N::mul(a[0], a[0]); }
+            const double disc = N::sub(N::add(N::mul((double)n, C2), pow2_glibc(S)), N::mul((double)n, Q));
+            const double num_ = N::add(S, N::sqrt(disc));
+            return n == 3 ? N::div3(num_) : n == 2 ? N::mul(num_, 0.5) : num_;
+        }
+        // Tarray.remove(Tmax)
+        if (im == 0) { a[0] = a[1]; a[1] = a[2]; } else if (im == 1) { a[1] = a[2]; }
+    }
+    return N::inf();                                  // no finite neighbour (reference: max([]) raises)
 }
 
 // fp32 variant: the reference expression n*C^2 + S^2 - n*Q cancels catastrophically in single
@@ -155,7 +191,24 @@ __global__ void init_seed3d_kernel(Problem3D<real> P) {
     }
 }
 
-template <typename real, int TZ, int WARPS>
+// resume: keep T, reset the scheduler state; activate_all3d then queues every tile (polish pass)
+template <typename real>
+__global__ void init_resume3d_kernel(Problem3D<real> P, int ring_slots) {
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nth = (long long)gridDim.x * blockDim.x;
+    const long long ntiles = (long long)P.nq * P.nty * P.ntx * P.ntz;
+    for (long long i = tid; i < ntiles; i += nth) P.tile_state[i] = ST_IDLE;
+    for (long long i = tid; i < ring_slots; i += nth) P.q.ring[i] = -1;
+    if (tid == 0) { QueueCtl z = {}; *P.q.ctl = z; }
+}
+template <typename real>
+__global__ void activate_all3d_kernel(Problem3D<real> P) {
+    const long long ntiles = (long long)P.nq * P.nty * P.ntx * P.ntz;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < ntiles && tile_activate(P.tile_state, P.q.ctl, (int)t)) q_push(P.q, (int)t);
+}
+
+template <typename real, int TZ, int WARPS, bool EXACT = false>
 __global__ void __launch_bounds__(WARPS * 32) solve3d_kernel(Problem3D<real> P) {
     using TL = Tile3D<real, TZ>;
     constexpr int PZ = TL::PZ, PS = TL::PS;
@@ -296,6 +349,7 @@ __global__ void __launch_bounds__(WARPS * 32) solve3d_kernel(Problem3D<real> P) 
                 if (lx == sx && (ly == sy - 1 || ly == sy + 1)) mask |= 1u << sz;
             }
         }
+        if (P.arm_all) mask = cmask;
         mask &= cmask;
 
         // ---- relax to the fixed point (same lock-step scheme as 2D; see eikonal2d.cuh) --------
@@ -317,11 +371,15 @@ __global__ void __launch_bounds__(WARPS * 32) solve3d_kernel(Problem3D<real> P) 
                 real *p = col + k;
                 const real zm = p[-1], zp = p[1], xm = p[-PZ], xp = p[PZ], ym = p[-PS], yp = p[PS], cur = p[0];
                 // FastMarching3D.py:44-57: per-axis minimum, Tarray = [Tx, Ty, Tz]
-                const real v = solve3d_update<real>(xm < xp ? xm : xp, ym < yp ? ym : yp, zm < zp ? zm : zp, colC[k]);
+                real v;
+                if (EXACT) v = (real)solve3d_update_exact((double)(xm < xp ? xm : xp), (double)(ym < yp ? ym : yp), (double)(zm < zp ? zm : zp), (double)colC[k]);
+                else v = solve3d_update<real>(xm < xp ? xm : xp, ym < yp ? ym : yp, zm < zp ? zm : zp, colC[k]);
                 // lower values always win; a value a few ulp higher also replaces the stored one, so that the field
                 // ends as an exact fixed point of the update instead of the minimum over a history of roundings
                 // (see eikonal2d.cuh)
-                if (v != cur && v <= num<real>::mul(cur, (real)(1.0 + 8.0 / 4503599627370496.0))) {      // lower, or at most ~4 ulp higher
+                // (polish pass: the reference's 3D expression is ill-conditioned -- a 1-ulp change of an input moves the
+                // result by ~200 ulp -- so the exact-arithmetic value may lie well above the fast one: accept within 1e-11)
+                if (v != cur && v <= num<real>::mul(cur, EXACT ? (real)(1.0 + 1e-11) : (real)(1.0 + 8.0 / 4503599627370496.0))) {      // lower, or at most ~4 ulp higher
                     *p = v;
                     dirty |= bit;
                     mask |= (zm > v ? bit >> 1 : 0u) | (zp > v ? bit << 1 : 0u);

@@ -12,6 +12,7 @@
 
 #include "eikonal2d.cuh"
 #include "eikonal2d_cta.cuh"
+#include "eikonal2d_sweep.cuh"
 #include "eikonal3d.cuh"
 #include "trace2d.cuh"
 #include "trace3d.cuh"
@@ -94,6 +95,8 @@ void opt_defaults_locked() {
     g_opt.level_div = env_int("FMB_LEVEL_DIV", 0);
     g_opt.win_running = env_int("FMB_WIN_RUNNING", -1);
     g_opt.check_passes = env_int("FMB_CHECK_PASSES", 0);
+    g_opt.pipeline = env_int("FMB_PIPELINE", -1);
+    g_opt.precheck = env_int("FMB_PRECHECK", -1);
     g_opt_init = true;
 }
 fmb_options opt() {
@@ -270,8 +273,14 @@ int solve2d(const real *d_cost, int64_t cost_pitch, int64_t cost_qstride, real *
     if (rows < 1 || cols < 1 || nq < 1) return fail(FMB_E_INVALID, "rows, cols and nq must be positive%s");
     if (cost_pitch < cols || T_pitch < cols) return fail(FMB_E_INVALID, "pitch smaller than cols%s");
     const fmb_options O = opt();
-    // engine: CTA-per-tile (32-wide tiles) unless the warp-per-tile engine of round 1 is asked for
-    const int engine = O.engine2d > 0 ? O.engine2d : 3;
+    // Work order first (it decides the engine): best-first per query pays off when many queries share the GPU and a
+    // query's tile table is small enough to scan per claim (batched planning: a throughput regime).
+    const long long tiles_per_q32 = tiles2d(rows, cols, 32);
+    const int best_first = resume_activate >= 0 ? 0 : (O.best_first >= 0 ? O.best_first : ((nq >= 8 && tiles_per_q32 <= 1024) ? 1 : 0));
+    // Engine: the four-warp sweep visit (eikonal2d_sweep.cuh) where the solve is a chain of dependent visits (one map,
+    // a few maps); the warp-per-tile visit (eikonal2d.cuh) for batches, where throughput per warp counts (measured
+    // 4096 x 512^2: 64 ms against 142 ms).
+    const int engine = O.engine2d > 0 ? O.engine2d : (best_first ? 1 : 3);
     int tw = engine >= 2 ? 32 : O.tile_w2d;
     if (tw != 16 && tw != 32) return fail(FMB_E_INVALID, "tile_w2d must be 16 or 32%s");
     const long long ntiles = tiles2d(rows, cols, tw) * nq;
@@ -292,21 +301,19 @@ int solve2d(const real *d_cost, int64_t cost_pitch, int64_t cost_qstride, real *
     P.q.watchdog_cycles = (long long)(O.watchdog_ms > 0 ? O.watchdog_ms : 20000) * 2000000LL;   // ~2 GHz
     P.step_cap = O.step_cap > 0 ? O.step_cap : 1 << 20;
     P.tile_prio = (unsigned long long *)(ws + L.prio_off);
-    // best-first per query pays off when many queries share the GPU and a query's tile table is
-    // small enough to scan per claim; one large map is faster in plain FIFO order
-    const long long tiles_per_q = ntiles / nq;
-    P.best_first = O.best_first >= 0 ? O.best_first : ((nq >= 8 && tiles_per_q <= 1024) ? 1 : 0);     // claim = scan of the query's tile table
+    P.best_first = best_first;
     P.arm_rows = arm_rows;
-    if (resume_activate >= 0) P.best_first = 0;
     // windowed FIFO (deferral of tiles far ahead of the lowest queued level): one large map only
     // one map: the sweep engine runs the local causal order at every size; the older engines keep the windowed FIFO
     // for maps of >= 16384 tiles
-    P.windowed = (!P.best_first && resume_activate < 0 && nq == 1)
-                     ? (O.windowed >= 0 ? O.windowed : (engine == 3 ? 2 : (ntiles >= 16384 ? 1 : 0))) : 0;
+    P.windowed = (!P.best_first && resume_activate < 0)
+                     ? (O.windowed >= 0 ? O.windowed : (engine == 3 ? 2 : ((nq == 1 && ntiles >= 16384) ? 1 : 0))) : 0;
     if (P.windowed == 2 && engine != 3) P.windowed = 1;       // the local causal order exists in the sweep engine only
+    if (P.windowed == 1 && nq != 1) P.windowed = 0;           // the level window is kept per launch, not per query
     P.win_window = O.window >= 0 ? O.window : 2;
     P.check_passes = O.check_passes > 0 ? O.check_passes : 4;
-    P.precheck = 0;
+    P.precheck = O.precheck >= 0 ? O.precheck : 0;
+    P.pipeline = O.pipeline >= 0 ? O.pipeline : 0;      // early publish: measured slower (more rounds per visit)
     P.win_div = engine == 3 ? (O.level_div > 0 ? O.level_div : 1) : 1;
     P.win_running = engine == 3 ? (O.win_running >= 0 ? O.win_running : 1) : 0;
     P.win_inv_delta = (double *)(ws + L.win_off);
@@ -413,7 +420,7 @@ int fmb_finish(void *d_ws, size_t ws_bytes, void *stream, fmb_stats *stats) {
         stats->tile_visits = h.visits; stats->steps = h.steps; stats->evals = h.evals;
         stats->pushes = h.pushes; stats->cells_written = h.cells_written;
         stats->reserved[0] = h.pad[0];     /* deferrals of the windowed order */
-        stats->cyc_check = h.pad[1]; stats->noop_visits = h.noop_visits; stats->rounds = h.rounds;
+        stats->cyc_check = h.pad[1]; stats->noop_visits = h.noop_visits; stats->rounds = h.rounds; stats->continuations = h.continuations;
         stats->cyc_wait = h.cyc_wait; stats->cyc_load = h.cyc_load; stats->cyc_relax = h.cyc_relax; stats->cyc_store = h.cyc_store;
         Timing *tm = timing_slot((cudaStream_t)stream, false);
         if (tm && tm->armed) {

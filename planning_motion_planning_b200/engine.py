@@ -166,10 +166,13 @@ def trace2d(T: torch.Tensor, init, end, tau: float = 0.5, field_of_path=None,
 
 # ------------------------------------------------------------------ 3D ------
 def solve3d(cost: torch.Tensor, seeds, out: Optional[torch.Tensor] = None, nq: Optional[int] = None,
-            sync: bool = True) -> torch.Tensor:
+            sync: bool = True, exact: bool = False) -> torch.Tensor:
     """3D analogue of :func:`solve2d` (FastMarching3D.py:126-145, full field).
 
     cost (ny, nx, nz) shared or (nq, ny, nx, nz); seeds (nq, 3) [x, y, z].
+    exact: follow the solve with the polish pass (``fmb_polish3d_f64``) that reproduces the reference's own
+    rounding of ``**2`` on NumPy scalars (libm pow), i.e. the reference field bit for bit up to iteration order;
+    needed where exact ties of the pop order matter (the early exit of ``FastMarching3D.computeTmap``).
     """
     _require_cuda(cost, "cost")
     if cost.dtype not in (torch.float64, torch.float32):
@@ -195,6 +198,12 @@ def solve3d(cost: torch.Tensor, seeds, out: Optional[torch.Tensor] = None, nq: O
     with torch.cuda.device(dev):
         _capi.check(fn(cost.data_ptr(), 0 if shared else ny * nx * nz, out.data_ptr(), ny * nx * nz, ny, nx, nz, nq,
                        s.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+        if exact:
+            if cost.dtype != torch.float64:
+                raise TypeError("the exact polish pass exists for float64 only")
+            finish(dev)            # the polish pass reuses the workspace: the solve's own failures are reported first
+            _capi.check(L.fmb_polish3d_f64(cost.data_ptr(), 0 if shared else ny * nx * nz, out.data_ptr(), ny * nx * nz,
+                                           ny, nx, nz, nq, s.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
         if sync:
             finish(dev)
     return out

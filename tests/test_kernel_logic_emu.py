@@ -297,3 +297,32 @@ def test_emulated_field_carries_the_references_bits():
         T, _ = emu.solve2d(c, [g], nblocks=3)
         ref = O.computeTmap(c, g)
         assert np.array_equal(T[0], ref)
+
+
+def test_device_pow2_reproduces_libm_pow_bit_for_bit():
+    """csrc/pow2_glibc.cuh (the port of glibc's pow for y = 2 that the exact 3D update uses) == libm pow(x, 2.0), the
+    value of `x**2` on a NumPy scalar (FastMarching3D.py:68-71), on 1e7 inputs: wide exponents, cost-like values,
+    integers and halves, sevenths, [1, 2), T-like sums of square roots, the neighbourhood of 1, subnormals / 0 / inf."""
+    rng = np.random.default_rng(7)
+    n = 1_500_000
+    xs = [np.ldexp(1.0 + rng.random(n), rng.integers(-200, 200, n)),
+          1.0 + 304.0 * rng.random(n),
+          rng.integers(0, 100000, n) * 0.5,
+          rng.integers(0, 100000, n) / 7.0,
+          1.0 + rng.random(n),
+          20.0 * np.sqrt(rng.integers(1, 4000, n).astype(np.float64)) + rng.integers(0, 100, n),
+          np.abs(np.float64(1.0) + (rng.integers(-1000, 1000, n) * np.finfo(np.float64).eps)),
+          np.array([0.0, np.inf, 5e-324, 1e-310, 2.2250738585072014e-308, 1.0, 2.0, 0.5, 1e-100, 1e100])]
+    x = np.ascontiguousarray(np.concatenate(xs))
+    assert x.size >= 10_000_000
+    L = emu.lib()
+    import ctypes as C
+    L.emu_pow2.argtypes = [emu.dp, emu.dp, C.c_longlong]
+    out = np.empty_like(x)
+    L.emu_pow2(x.ctypes.data_as(emu.dp), out.ctypes.data_as(emu.dp), x.size)
+    ref = O.pow2(x)
+    assert np.array_equal(out.view(np.uint64), ref.view(np.uint64))
+    assert int((ref != x * x).sum()) > 1000          # the inputs do exercise the cases where pow(x, 2) != x*x
+    # and the reference really evaluates numpy-scalar squares through that function
+    for v in x[::997_003]:
+        assert np.float64(v) ** 2 == ref[np.where(x == v)[0][0]] or not np.isfinite(v)

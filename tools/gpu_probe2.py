@@ -42,7 +42,7 @@ for cfg in configs:
     print(json.dumps({"cfg": cfg, "ms": round(best["solve_kernel_ms"], 3), "evals/cell": round(best["evals"] / cells, 2),
                       "visits/tile": round(best["tile_visits"] / ((n / 32) ** 2), 2), "steps/visit": round(best["steps"] / max(1, best["tile_visits"]), 1),
                       "cyc/step(relax)": round(best["cyc_relax"] / max(1, best["steps"]), 1),
-                      "noop%": round(100 * best.get("noop_visits", 0) / max(1, best["tile_visits"]), 1), "rounds/visit": round(best.get("rounds", 0) / max(1, best["tile_visits"]), 2),
+                      "noop%": round(100 * best.get("noop_visits", 0) / max(1, best["tile_visits"]), 1), "rounds/visit": round(best.get("rounds", 0) / max(1, best["tile_visits"]), 2), "cont/visit": round(best.get("continuations", 0) / max(1, best["tile_visits"]), 2),
                       "cyc_check/round": round(best.get("cyc_check", 0) / max(1, best["steps"] / 64)),
                       "cyc_wait/visit": round(best["cyc_wait"] / max(1, best["tile_visits"])),
                       "cyc_load/visit": round(best["cyc_load"] / max(1, best["tile_visits"])),

@@ -1,10 +1,10 @@
-"""Tuning probe (GPU): batched goal queries on one map under several env settings."""
+"""Tuning probe (GPU): batched goal queries on one map under several fmb_options settings (k=v,k=v ...)."""
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np, torch
 from bench import make_map
-from planning_motion_planning_b200 import engine
+from planning_motion_planning_b200 import _capi, engine
 n = int(sys.argv[1]); Q = int(sys.argv[2]); kind = sys.argv[3]
 configs = sys.argv[4:] or [""]
 c = make_map(n, kind, seed=1)
@@ -14,12 +14,11 @@ seeds = torch.tensor(ok[rng.integers(0, len(ok), size=Q)][:, ::-1].copy(), dtype
 cd = torch.from_numpy(c).cuda()
 T = torch.empty((Q, n, n), dtype=torch.float64, device="cuda")
 ref = None
+base = _capi.get_options()
 for cfg in configs:
-    kv = dict(x.split("=") for x in cfg.split(",") if x)
-    for k in list(os.environ):
-        if k.startswith("FMB_") and k not in ("FMB_WATCHDOG_MS", "FMB_LIB"):
-            del os.environ[k]
-    os.environ.update(kv)
+    kv = {k: int(v) for k, v in (x.split("=") for x in cfg.split(",") if x)}
+    _capi.set_options(**base)
+    _capi.set_options(**kv)
     best = None
     for rep in range(3):
         engine.solve2d(cd, seeds, out=T, nq=Q, sync=False)

@@ -8,7 +8,9 @@
 
 #include "../../planning_motion_planning_b200/csrc/eikonal2d.cuh"
 #include "../../planning_motion_planning_b200/csrc/eikonal2d_cta.cuh"
+#include "../../planning_motion_planning_b200/csrc/eikonal2d_sweep.cuh"
 #include "../../planning_motion_planning_b200/csrc/eikonal3d.cuh"
+#include "../../planning_motion_planning_b200/csrc/pow2_glibc.cuh"
 #include "../../planning_motion_planning_b200/csrc/trace2d.cuh"
 #include "../../planning_motion_planning_b200/csrc/trace3d.cuh"
 #include "../../planning_motion_planning_b200/csrc/truncate.cuh"
@@ -42,7 +44,7 @@ int run2d(const real *cost, long long cost_qstride, real *T, int rows, int cols,
     std::vector<int> lev_count(fmb::WIN_LEVELS), tile_level(ntiles);
     int win_hint = 0; double win_inv_delta = 1.0;
     P.windowed = (!P.best_first && nq == 1 && getenv("FMB_WINDOWED")) ? atoi(getenv("FMB_WINDOWED")) : 0;
-    P.win_window = getenv("FMB_WINDOW") ? atoi(getenv("FMB_WINDOW")) : 16; P.win_div = 1; P.win_running = 0; P.check_passes = 1; P.precheck = 0;
+    P.win_window = getenv("FMB_WINDOW") ? atoi(getenv("FMB_WINDOW")) : 16; P.win_div = 1; P.win_running = 0; P.check_passes = 1; P.precheck = 0; P.pipeline = getenv("FMB_PIPELINE") ? atoi(getenv("FMB_PIPELINE")) : 1;
     P.lev_count = lev_count.data(); P.tile_level = tile_level.data(); P.win_hint = &win_hint; P.win_inv_delta = &win_inv_delta;
     emu::launch(2, 64, 0, [&] { fmb::init_fill2d_kernel<real>(P, (int)ring.size()); });
     emu::launch(1, 32 * ((nq + 31) / 32), 0, [&] { fmb::init_seed2d_kernel<real, TW>(P); });
@@ -75,7 +77,7 @@ int run2d_cta(const real *cost, long long cost_qstride, real *T, int rows, int c
     std::vector<int> lev_count(fmb::WIN_LEVELS), tile_level(ntiles);
     int win_hint = 0; double win_inv_delta = 1.0;
     P.windowed = (!best_first && nq == 1) ? windowed : 0;
-    P.check_passes = 4; P.precheck = 0; P.win_window = window; P.win_div = R == 0 ? 2 : 1; P.win_running = R == 0 ? 1 : 0;
+    P.check_passes = 4; P.precheck = 0; P.pipeline = getenv("FMB_PIPELINE") ? atoi(getenv("FMB_PIPELINE")) : 1; P.win_window = window; P.win_div = R == 0 ? 2 : 1; P.win_running = R == 0 ? 1 : 0;
     P.lev_count = lev_count.data(); P.tile_level = tile_level.data(); P.win_hint = &win_hint; P.win_inv_delta = &win_inv_delta;
     std::vector<unsigned long long> run_prio(ntiles);
     P.run_prio = run_prio.data();
@@ -110,7 +112,14 @@ int run3d(const real *cost, long long cost_qstride, real *T, int ny, int nx, int
     P.q.watchdog_cycles = 1LL << 40; P.step_cap = 1 << 20;
     emu::launch(2, 64, 0, [&] { fmb::init_fill3d_kernel<real>(P, (int)ring.size()); });
     emu::launch(1, 32 * ((nq + 31) / 32), 0, [&] { fmb::init_seed3d_kernel<real, TZ>(P); });
+    P.arm_all = 0;
     emu::launch(nblocks, WARPS * 32, fmb::Tile3D<real, TZ>::WARP_BYTES * WARPS, [&] { fmb::solve3d_kernel<real, TZ, WARPS>(P); });
+    if (getenv("FMB_EMU_POLISH3D") && atoi(getenv("FMB_EMU_POLISH3D")) && sizeof(real) == 8 && !ctl.abort && ctl.pending == 0) {
+        P.arm_all = 1;
+        emu::launch(2, 64, 0, [&] { fmb::init_resume3d_kernel<real>(P, (int)ring.size()); });
+        emu::launch((unsigned)((ntiles + 63) / 64), 64, 0, [&] { fmb::activate_all3d_kernel<real>(P); });
+        emu::launch(nblocks, WARPS * 32, fmb::Tile3D<real, TZ>::WARP_BYTES * WARPS, [&] { fmb::solve3d_kernel<real, TZ, WARPS, true>(P); });
+    }
     if (stats) { stats[0] = ctl.visits; stats[1] = ctl.steps; stats[2] = ctl.evals; stats[3] = ctl.pushes; stats[4] = ctl.cells_written; }
     return ctl.abort ? ctl.abort : (ctl.pending != 0 ? -1 : 0);
 }
@@ -201,6 +210,7 @@ int emu_truncate3d_f64(const double *F, const double *cost, const int *rank, int
     return counters[1];
 }
 
+void emu_pow2(const double *x, double *out, long long n) { for (long long i = 0; i < n; ++i) out[i] = fmb::pow2_glibc(x[i]); }
 void emu_div3(const double *x, double *out, long long n) { for (long long i = 0; i < n; ++i) out[i] = fmb::num<double>::div3(x[i]); }
 
 // resume a 2D solve from the current contents of T (domain decomposition tests)
@@ -217,7 +227,7 @@ int emu_resolve2d_f64(const double *cost, double *T, int rows, int cols, const i
     std::vector<unsigned long long> prio(ntiles);
     fmb::QueueCtl ctl;
     P.tile_state = state.data(); P.q.ctl = &ctl; P.q.ring = ring.data(); P.q.ring_mask = (unsigned)ring.size() - 1;
-    P.q.watchdog_cycles = 1LL << 40; P.step_cap = 1 << 20; P.tile_prio = prio.data(); P.best_first = 0; P.arm_rows = halo_rows; P.windowed = 0; P.win_window = 0; P.win_div = 1; P.win_running = 0; P.check_passes = 1; P.precheck = 0;
+    P.q.watchdog_cycles = 1LL << 40; P.step_cap = 1 << 20; P.tile_prio = prio.data(); P.best_first = 0; P.arm_rows = halo_rows; P.windowed = 0; P.win_window = 0; P.win_div = 1; P.win_running = 0; P.check_passes = 1; P.precheck = 0; P.pipeline = getenv("FMB_PIPELINE") ? atoi(getenv("FMB_PIPELINE")) : 1;
     P.lev_count = nullptr; P.tile_level = nullptr; P.win_hint = nullptr; P.win_inv_delta = nullptr;
     emu::launch(2, 64, 0, [&] { fmb::init_resume2d_kernel<double>(P, (int)ring.size()); });
     if (activate & 7) emu::launch((unsigned)((ntiles + 63) / 64), 64, 0, [&] { fmb::activate_rows2d_kernel<double>(P, activate); });
