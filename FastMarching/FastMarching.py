@@ -44,13 +44,13 @@ def _solve_fields(costMap, nodes):
         _c.check_node2(q, rows, cols)
         seeds.append(q)
     dev = _c.device()
-    cd = torch.from_numpy(np.ascontiguousarray(c)).to(dev)
+    cd = _c.to_device(np.ascontiguousarray(c), dev)
     T = engine.solve2d(cd, seeds, nq=len(seeds))
     return T, cd, swap
 
 
 def _to_numpy_field(Tt: torch.Tensor, swap: bool) -> np.ndarray:
-    a = Tt.cpu().numpy()
+    a = _c.to_host(Tt)
     return a.T if swap else a          # .T of a C array is F-ordered, like zeros_like() of the planner's view
 
 
@@ -108,7 +108,7 @@ def getPathGDM(totalCostMap, initWaypoint, endWaypoint, tau):
     init = np.asarray(initWaypoint, dtype=np.float64).reshape(-1)[:2]
     end = np.asarray(endWaypoint, dtype=np.float64).reshape(-1)[:2]
     dev = _c.device()
-    Td = torch.from_numpy(np.ascontiguousarray(c)).to(dev)
+    Td = _c.to_device(np.ascontiguousarray(c), dev)
     if swap:
         # unlike the solver, the tracer is NOT symmetric in x and y (the reference normalises dx
         # first and reuses it for dy, FastMarching.py:226-227), so an F-ordered field is put back

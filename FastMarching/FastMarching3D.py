@@ -28,7 +28,7 @@ def computeTmap(costMap, goal, start):
     if not (0 <= g[0] < nx and 0 <= g[1] < ny and 0 <= g[2] < nz):
         raise IndexError(f"goal {g} is outside the {ny}x{nx}x{nz} volume")
     dev = _c.device()
-    cd = torch.from_numpy(c).to(dev)
+    cd = _c.to_device(c, dev)
     # exact=True: the polish pass gives the field the reference's own rounding (libm pow for `**2` on scalars), so
     # that exactly tied values are tied here too and the early exit accepts the reference's set of cells
     T = engine.solve3d(cd, [g], nq=1, exact=_c.EXACT_3D)[0]
@@ -44,7 +44,7 @@ def computeTmap(costMap, goal, start):
         else:
             rank = _c.pop_ranks(T)
         T = _c.truncate(T, cd, rank, int(rank[s[1], s[0], s[2]]))
-    return T.cpu().numpy()
+    return _c.to_host(T)
 
 
 def getPathGDM(totalCostMap, initWaypoint, endWaypoint, tau):
@@ -55,7 +55,7 @@ def getPathGDM(totalCostMap, initWaypoint, endWaypoint, tau):
     init = np.asarray(initWaypoint, dtype=np.float64).reshape(-1)[:3]
     end = np.asarray(endWaypoint, dtype=np.float64).reshape(-1)[:3]
     dev = _c.device()
-    Td = torch.from_numpy(Tn).to(dev)
+    Td = _c.to_device(Tn, dev)
     out, count, status = engine.trace3d(Td, init[None, :], end[None, :], tau)
     n, st = int(count[0]), int(status[0])
     _c.raise_trace(st)

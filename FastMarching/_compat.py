@@ -20,6 +20,58 @@ def device() -> torch.device:
     return torch.device("cuda", torch.cuda.current_device())
 
 
+# ---- host <-> device plumbing of the NumPy boundary ------------------------------------------------
+# The planner hands pageable NumPy arrays over and gets NumPy arrays back.  A pageable copy of a 128 MiB field moves
+# at 3-4 GB/s; through page-locked memory it moves at PCIe speed.  So: uploads are staged chunk-wise through two small
+# pinned buffers (the memcpy of chunk k+1 overlaps the DMA of chunk k), and results are downloaded straight into a
+# pinned tensor whose memory backs the returned NumPy array (owned by the caller through the array's base).  An array
+# that came from here is recognised as pinned on its way back in (getPathGDM on a field biComputeTmap returned) and
+# uploaded with one DMA.
+_STAGE = {}
+_STAGE_ELEMS = 4 << 20            # 32 MiB of float64 per staging buffer
+
+
+def to_device(a: np.ndarray, dev: torch.device) -> torch.Tensor:
+    """C-contiguous float64 NumPy array -> device tensor of the same shape."""
+    t = torch.from_numpy(a)
+    if a.size < (1 << 18):
+        return t.to(dev)
+    try:
+        if t.is_pinned():
+            return t.to(dev, non_blocking=True)
+    except RuntimeError:
+        pass
+    out = torch.empty(a.shape, dtype=torch.float64, device=dev)
+    flat_src, flat_dst = t.reshape(-1), out.reshape(-1)
+    key = dev.index
+    if key not in _STAGE:
+        _STAGE[key] = ([torch.empty(_STAGE_ELEMS, dtype=torch.float64).pin_memory() for _ in range(2)],
+                       [torch.cuda.Event(), torch.cuda.Event()])
+    bufs, evs = _STAGE[key]
+    n = flat_src.numel()
+    stream = torch.cuda.current_stream(dev)
+    for k, lo in enumerate(range(0, n, _STAGE_ELEMS)):
+        hi = min(n, lo + _STAGE_ELEMS)
+        b = k & 1
+        if k >= 2:
+            evs[b].synchronize()                       # the DMA that last read this staging buffer is done
+        bufs[b][:hi - lo].copy_(flat_src[lo:hi])
+        flat_dst[lo:hi].copy_(bufs[b][:hi - lo], non_blocking=True)
+        evs[b].record(stream)
+    return out
+
+
+def to_host(t: torch.Tensor) -> np.ndarray:
+    """Device tensor -> fresh NumPy array (page-locked memory for large fields, see above)."""
+    t = t.contiguous()
+    if t.numel() < (1 << 18):
+        return t.cpu().numpy()
+    h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    h.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return h.numpy()
+
+
 def as_c_field(a):
     """Return (C-contiguous float64 view or copy, transposed?) for an array of any order.
 
@@ -75,7 +127,9 @@ _BIG = torch.iinfo(torch.int64).max
 # here) but on plateau maps the reference itself holds many DISTINCT values one or two ulp apart, and merging
 # those misorders far more cells (154 vs 1 on the case that motivated it).
 TIE_TOL_2D = 0.0
-EXACT_3D = False         # FastMarching3D.computeTmap: follow the solve with the exact polish pass (fmb_polish3d_f64); measured: no fewer tie mismatches
+EXACT_3D = True          # FastMarching3D.computeTmap: follow the solve with the exact polish pass (fmb_polish3d_f64): the field then
+                         # carries the reference's own rounding (libm pow for `**2` on scalars) and exact ties are the reference's:
+                         # tools/gpu_fuzz_3d.py 300 volumes: 0 pattern mismatches with it, 13 without
 TIE_TOL_3D = 0.0
 
 

@@ -13,9 +13,11 @@ path extraction over the result.  With N GPUs every rank runs that query on its 
 
   value = cells solved per second over the whole job = N * 4096^2 * K / t, t = device time of
           the K timed steps (CUDA events), max over ranks; inputs resident in HBM.
-  e2e   = the same through the public engine API with HOST buffers: per step the costmap is
-          copied from pinned host memory, solved, traced, and the field + path copied back.
-  roofline: dominant kernel = the persistent solve2d kernel; algorithmic bytes = 2*8 B per
+  e2e   = the same work through the reference-facing PLUGIN CALL, single caller thread like the planner
+          (Coupled_motion_planner.py:1226-1230): FastMarching.FastMarching.computeTmap(costMap, goal, start) +
+          getPathGDM(T, start, goal, tau) on NumPy arrays; host<->device copies inside the timed region.
+          (`e2e_pipelined` keeps round 1's number: the engine API with pinned buffers, queries in flight.)
+  roofline: dominant kernel = the persistent solve kernel (solve2d_sweep_kernel); algorithmic bytes = 2*8 B per
           cell (read cost once, write T once); duration = CUDA events recorded
           by the library around that kernel.
 One JSON line on stdout (rank 0).
@@ -73,6 +75,17 @@ def make_map(n, kind, seed=0):
     except Exception:
         pass
     return c
+
+
+def make_config(args):
+    """The workload both arms measure (identical dict in both lines)."""
+    n = args.size
+    return {"workload": f"{n}x{n} fp64 planner-like costmap ({args.map}, seed 0), goal at (n/4, n/4), path from (3n/4, 3n/4): "
+                        "one step = one full-field Eikonal solve + 1 gradient-descent path per GPU",
+            "size": n, "map": args.map, "tau": 0.5,
+            "l2_policy": "inputs larger than L2 (cost + T = %d MiB)" % (2 * n * n * 8 >> 20),
+            "parallelism": "one query per GPU per step (replicas; weak scaling)",
+            "e2e_call": "FastMarching.computeTmap + getPathGDM on NumPy arrays, one caller thread per GPU"}
 
 
 def goals_for(c, n_ranks):
@@ -193,18 +206,18 @@ def reference_arm(args):
     cores = len(os.sched_getaffinity(0))
     n = args.size
     c = make_map(n, args.map)
-    nq = max(1, args.gpus) * max(1, args.inflight)
+    nq = max(1, args.gpus)                      # one caller thread per GPU of the other arm (its e2e = single-threaded plugin calls)
     threads = min(nq, cores)
-    goals, starts = goals_for(c, nq)
+    goals, starts = goals_for(c, nq * max(1, args.inflight))
 
     def one(i):
         T = O.computeTmap(c, goals[i])
         p, _ = O.getPathGDM(T, np.array(starts[i]), goals[i], 0.5, return_status=True)
         return len(p)
 
-    def step():
-        with ThreadPoolExecutor(max_workers=threads) as ex:
-            return list(ex.map(one, range(nq)))
+    def step(count, workers):
+        with ThreadPoolExecutor(max_workers=workers) as ex:
+            return list(ex.map(one, range(count)))
 
     small = min(n, 1024)          # warm-up on a crop: page in the library, spin up the pool
     crop = np.ascontiguousarray(c[:small, :small]).copy()
@@ -213,21 +226,39 @@ def reference_arm(args):
         O.computeTmap(crop, [small // 4, small // 4])
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        step()
+        step(nq, threads)
     total = time.perf_counter() - t0
     value = nq * n * n * args.steps / total
-    allc, _, _ = cpu_port_run(c, None, None, min(cores, 32), small)     # context: every core busy on crops
+    # context 1: the concurrency the other arm's device-resident loop runs with (--gpus x --inflight queries at a time)
+    nq2 = nq * max(1, args.inflight)
+    th2 = min(nq2, cores)
+    k2 = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(k2):
+        step(nq2, th2)
+    inflight_value = nq2 * n * n * k2 / (time.perf_counter() - t0)
+    # context 2: every core busy on crops
+    allc, _, _ = cpu_port_run(c, None, None, min(cores, 32), small)
+    # context 3: the planner's own call, biComputeTmap (two fronts, real early exit) + the two half paths
+    s_bi = starts[0]
+    t0 = time.perf_counter()
+    TG, TS, j = O.biComputeTmap(c, goals[0], s_bi)
+    O.getPathGDM(TG, np.array(j, dtype=np.float64), goals[0], 0.5)
+    O.getPathGDM(TS, np.array(j, dtype=np.float64), s_bi, 0.5)
+    bi_s = time.perf_counter() - t0
     sample = (f"{nq} full {n}x{n} solve(s) + path per step, one host thread per query "
               f"({threads} of {cores} cores; C port of FastMarching.py heap FMM + tracer)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{n}x{n} fp64 planner-like costmap ({args.map}, seed 0): full-field solve + 1 path "
-                               f"per query, {nq} independent queries at a time (--gpus x --inflight)", "cpu_threads": threads},
+        "config": make_config(args),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "with_inflight_concurrency": {"value": inflight_value, "unit": UNIT, "cores": th2,
+                                                       "sample": f"{nq2} queries at a time (--gpus x --inflight), {k2} step(s)"},
                          "throughput_all_cores": {"value": allc, "unit": UNIT, "cores": min(cores, 32),
-                                                  "sample": f"{min(cores, 32)} threads x one {small}x{small} crop each"}},
+                                                  "sample": f"{min(cores, 32)} threads x one {small}x{small} crop each"},
+                         "planner_call_bicompute_plus_2_paths_s": bi_s},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -362,15 +393,15 @@ def own_arm(args):
     achieved = alg_bytes / (solve_ms * 1e-3) / 1e9
     traffic, traffic_src = None, None
     try:        # DRAM bytes of one launch of this kernel on this workload, from the committed ncu capture
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
         if n == 4096 and args.map == "mars":
-            ent = tj["solve2d_kernel<double,32,4,false>|4096x4096 mars seed0|" + ("fifo" if os.environ.get("FMB_WINDOWED") == "0" else "windowed")]
+            ent = tj["solve2d_sweep_kernel<double,false>|4096x4096 mars seed0"]
             traffic, traffic_src = ent["dram_bytes_read"] + ent["dram_bytes_write"], ent["source"]
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_src,
-                "kernel": "solve2d_kernel<double,32,4,false>", "kernel_ms": solve_ms,
+                "kernel": "solve2d_sweep_kernel<double,false>", "kernel_ms": solve_ms,
                 "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
                 "note": "single-source solve is dependency-latency bound (DESIGN.md 5); see batch.roofline_frac_solve_kernel for the throughput regime"}
 
@@ -462,9 +493,52 @@ def own_arm(args):
         tt = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt[0])
-    e2e = {"value": world * cells * K / e2e_s, "unit": UNIT, "ms_per_step": 1e3 * e2e_s / K,
-           "h2d_bytes_per_step": int(cost_h.numel() * 8), "d2h_bytes_per_step": int(T_h.numel() * 8 + path_h.numel() * 8 + 4),
-           "pipelining": f"{NF} queries in flight, each lane with its own upload / solve / download / trace streams and double buffers"}
+    e2e_pipelined = {"value": world * cells * K / e2e_s, "unit": UNIT, "ms_per_step": 1e3 * e2e_s / K,
+                     "h2d_bytes_per_step": int(cost_h.numel() * 8), "d2h_bytes_per_step": int(T_h.numel() * 8 + path_h.numel() * 8 + 4),
+                     "api": "planning_motion_planning_b200.engine (pinned host buffers)",
+                     "pipelining": f"{NF} queries in flight, each lane with its own upload / solve / download / trace streams and double buffers"}
+
+    # ---- end to end through the reference-facing plugin call: NumPy in, NumPy out, ONE caller thread (what the planner
+    # does, Coupled_motion_planner.py:1226-1230).  computeTmap with an unreachable start returns the full field (the same
+    # work as `value`'s step); every host<->device copy (cost map up, field down, field up again for the tracer, path
+    # down) is inside the timed region.
+    import FastMarching.FastMarching as FM
+    far = [-1, -1]
+    c_np = c                                    # pageable NumPy array, as a caller would hold it
+    for _ in range(2):
+        Tn = FM.computeTmap(c_np, goal, far)
+        pn = FM.getPathGDM(Tn, np.array(start, dtype=np.float64), goal, tau)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        Tn = FM.computeTmap(c_np, goal, far)
+        pn = FM.getPathGDM(Tn, np.array(start, dtype=np.float64), goal, tau)
+    torch.cuda.synchronize()
+    plug_s = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([plug_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        plug_s = float(tt[0])
+    e2e = {"value": world * cells * K / plug_s, "unit": UNIT, "ms_per_step": 1e3 * plug_s / K,
+           "h2d_bytes_per_step": int(2 * cells * 8), "d2h_bytes_per_step": int(cells * 8 + pn.size * 8),
+           "api": "FastMarching.FastMarching.computeTmap(costMap, goal, start) + getPathGDM(T, start, goal, tau): NumPy in, NumPy out, "
+                  "one caller thread, pageable host arrays",
+           "path_rows": int(len(pn))}
+    # the planner's own call: biComputeTmap (two full solves + the early-exit emulation) + the two half paths
+    bi = None
+    if rank == 0:
+        s_bi = start
+        for _ in range(2):
+            TG, TS, jn = FM.biComputeTmap(c_np, goal, s_bi)
+        t0 = time.perf_counter()
+        TG, TS, jn = FM.biComputeTmap(c_np, goal, s_bi)
+        t_bi = time.perf_counter() - t0
+        pG = FM.getPathGDM(TG, jn, goal, tau)
+        pS = FM.getPathGDM(TS, jn, s_bi, tau)
+        torch.cuda.synchronize()
+        bi = {"call": "FastMarching.biComputeTmap(costMap, goal, start) + 2 x getPathGDM, NumPy in / out",
+              "bicompute_ms": 1e3 * t_bi, "total_ms": 1e3 * (time.perf_counter() - t0), "join": [int(v) for v in jn],
+              "path_rows": [int(len(pG)), int(len(pS))]}
 
     # ---- batched independent queries (config 4 style): Q goal queries on one 512^2 map per GPU
     batch = None
@@ -507,6 +581,56 @@ def own_arm(args):
                  "roofline_frac_solve_kernel": (2 * 8 * bcells / (sb["solve_kernel_ms"] * 1e-3) / 1e9) / peak,
                  "evals_per_cell": sb["evals"] / bcells}
 
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            # parity of the batch at full size: sampled queries against the oracle (field 1e-9, path 1e-3 cell)
+            from oracle import oracle as O
+            O.build()
+            pth, pcnt, pst = engine.trace2d(Tb, starts_b, ends_b, tau)
+            wf, wp, same = 0.0, 0.0, True
+            for qi in rng.choice(Q, size=8, replace=False):
+                gq = [int(v) for v in seeds_b[qi].tolist()]
+                ref = O.computeTmap(cb, gq)
+                got = Tb[qi].cpu().numpy()
+                fin = np.isfinite(ref)
+                same = same and bool(np.array_equal(np.isfinite(got), fin))
+                wf = max(wf, float(np.max(np.abs(got[fin] - ref[fin]) / np.maximum(ref[fin], 1e-300))))
+                po, so = O.getPathGDM(ref, starts_b[qi].cpu().numpy(), gq, tau, return_status=True)
+                pg = pth[qi, :int(pcnt[qi])].cpu().numpy()
+                same = same and int(pst[qi]) == so and pg.shape == po.shape
+                if pg.shape == po.shape and len(po):
+                    wp = max(wp, float(np.abs(pg - po).max()))
+            batch["parity"] = {"sampled_queries": 8, "field_max_rel_err": wf, "path_max_abs_dev_cells": wp, "same_inf_pattern_status_and_rows": same}
+            del pth
+        del Tb
+
+    # ---- config 4 as BASELINE words it: ONE job of Q goal queries on a 512^2 map, sharded over the N ranks through
+    # batch.solve_queries (contiguous blocks, no data-path collective), the paths gathered on rank 0's host: strong scaling
+    sharded = None
+    if not args.no_batch:
+        from planning_motion_planning_b200 import batch as BT
+        Qs = args.batch_queries
+        cbs = make_map(512, args.map, seed=1)
+        rs = np.random.default_rng(100)                      # the SAME job on every rank
+        oks = np.argwhere(np.isfinite(cbs) & (cbs <= 2.0))
+        goals_s = oks[rs.integers(0, len(oks), size=Qs)][:, ::-1].tolist()
+        starts_s = oks[rs.integers(0, len(oks), size=Qs)][:, ::-1].tolist()
+        cbs_d = torch.from_numpy(cbs).to(dev)
+        BT.solve_queries(cbs_d, goals_s[:64 * world], starts_s[:64 * world], chunk=64, gather=True)
+        barrier()
+        t0 = time.perf_counter()
+        lo_s, res_s = BT.solve_queries(cbs_d, goals_s, starts_s, chunk=1024, gather=True)
+        barrier()
+        dts = time.perf_counter() - t0
+        if world > 1:
+            tt = torch.tensor([dts], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dts = float(tt[0])
+        sharded = {"workload": f"ONE job of {Qs} goal queries on a 512x512 fp64 map (solve + 1 path each) sharded over {world} GPU(s) "
+                               "through batch.solve_queries(gather=True): waypoints of all queries on rank 0's host at the end",
+                   "queries_per_s": Qs / dts, "seconds": dts, "scaling": "strong",
+                   "results_on_rank0": len(res_s) if rank == 0 else None}
+        del res_s
+
     # ---- coupled plan, 3D half (config 3): arm-workspace cost volume solve + path
     vol = None
     if not args.no_3d and rank == 0:
@@ -541,6 +665,31 @@ def own_arm(args):
                "solve_kernel_ms": k3, "trace_ms": float(np.mean(ts[1:])), "cells_per_s": m3 ** 3 / (k3 * 1e-3),
                "roofline_frac_solve_kernel": (2 * 8 * m3 ** 3 / (k3 * 1e-3) / 1e9) / peak,
                "evals_per_cell": s3d["evals"] / m3 ** 3, "path_rows": int(n3[0]), "path_status": int(st3[0])}
+        # the exact arithmetic the drop-in uses (the reference's rounding of `**2`), timed on its own: from scratch / as a polish pass
+        for mode, key in ((True, "solve_exact_ms"), ("polish", "solve_plus_exact_polish_ms")):
+            engine.solve3d(c3d, [g3], out=T3, nq=1, sync=True, exact=mode)
+            e0.record()
+            engine.solve3d(c3d, [g3], out=T3, nq=1, sync=False, exact=mode)
+            e1.record()
+            torch.cuda.synchronize()
+            vol[key] = e0.elapsed_time(e1)
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import oracle as O
+            O.build()
+            t0 = time.perf_counter()
+            r3 = O.computeTmap3D(c3, g3)
+            p3o, s3o = O.getPathGDM3D(r3, np.uint32(s3), np.uint32(g3), tau, return_status=True)
+            dt3 = time.perf_counter() - t0
+            engine.solve3d(c3d, [g3], out=T3, nq=1, sync=True)
+            o3, n3, st3 = engine.trace3d(T3, [s3], [g3], tau)
+            g3f = T3[0].cpu().numpy()
+            f3 = np.isfinite(r3)
+            p3g = o3[0, :int(n3[0])].cpu().numpy()
+            vol["cpu_port_seconds"] = dt3
+            vol["parity"] = {"field_max_rel_err": float(np.max(np.abs(g3f[f3] - r3[f3]) / np.maximum(r3[f3], 1e-300))),
+                             "same_inf_pattern": bool(np.array_equal(np.isfinite(g3f), f3)),
+                             "path_rows": [int(len(p3g)), int(len(p3o))], "path_status": [int(st3[0]), int(s3o)],
+                             "path_max_abs_dev_cells": float(np.abs(p3g - p3o).max()) if p3g.shape == p3o.shape else None}
         del c3d, T3
 
     # ---- the cost-map construction that precedes the 2D solve (DEM -> cost map)
@@ -625,11 +774,11 @@ def own_arm(args):
         Tref = O.computeTmap(c, goal)
         pref, pst = O.getPathGDM(Tref, np.array(start), goal, tau, return_status=True)
         dt = time.perf_counter() - t0
-        Tg = T_h[0].numpy()
+        Tg = np.asarray(Tn)                      # the field the plugin call returned
         fin = np.isfinite(Tref)
         same_inf = bool(np.array_equal(np.isfinite(Tg), fin))
         rel = float(np.max(np.abs(Tg[fin] - Tref[fin]) / np.maximum(Tref[fin], 1e-300)))
-        gp = path_h[0, :int(cnt_h[0])].numpy()
+        gp = np.asarray(pn)
         pdev = float(np.abs(gp - pref).max()) if gp.shape == pref.shape else None
         cpu = {"value": cells / dt, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": f"the full {n}x{n} solve + path, once, single thread (C restatement of the reference FMM; "
@@ -644,16 +793,15 @@ def own_arm(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W, 3),
             "ms_per_step": t_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{n}x{n} fp64 planner-like costmap ({args.map}, seed 0): full-field solve + 1 path "
-                                   f"per GPU per step", "l2_policy": "inputs larger than L2 (cost + T = %d MiB)" % (2 * cells * 8 >> 20),
-                       "tau": tau, "path_rows": path_len, "path_status": path_status, "parallelism": f"{world} replicas, one query per GPU per step",
-                       "pipelining": f"{NF} independent queries in flight per GPU (own streams and buffers); a query's path is traced "
-                                     "while the next query of its lane solves"},
+            "config": make_config(args),
+            "run": {"path_rows": path_len, "path_status": path_status,
+                    "device_resident_pipelining": f"{NF} independent queries in flight per GPU (own streams and buffers); a query's path "
+                                                  "is traced while the next query of its lane solves"},
             "latency_ms_one_query": init_ms + solve_ms + trace_ms,
             "breakdown_ms": {"init_fill": init_ms, "solve_kernel": solve_ms, "trace_kernel": trace_ms},
             "solver_stats": {k: stats[k] for k in ("tile_visits", "steps", "evals", "pushes", "cells_written")},
             "evals_per_cell": stats["evals"] / cells,
-            "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "batch": batch, "volume3d": vol, "costmap2d": cmap, "costvolume3d": cvol,
+            "roofline": roofline, "e2e": e2e, "e2e_pipelined": e2e_pipelined, "planner_call": bi, "cpu_baseline": cpu, "batch": batch, "batch_sharded": sharded, "volume3d": vol, "costmap2d": cmap, "costvolume3d": cvol,
             "gpu_launches": 4 * K, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

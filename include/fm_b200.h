@@ -156,6 +156,11 @@ int fmb_solve3d_f32(const float *d_cost, int64_t cost_qstride, float *d_T, int64
  * fraction of a percent of the cells: irrelevant for the 1e-9 tolerance, decisive for exact ties of the pop order
  * (early exit of FastMarching3D.computeTmap :141-142 on uniform-cost volumes).  Same arguments as fmb_solve3d_f64,
  * d_T = its result; asynchronous, fmb_finish() reports. */
+/* The whole solve with that exact arithmetic from the start (same result as solve + polish; faster on large volumes,
+ * where the polish pass re-relaxes nearly every cell anyway). */
+int fmb_solve3d_exact_f64(const double *d_cost, int64_t cost_qstride, double *d_T, int64_t T_qstride,
+                          int ny, int nx, int nz, int nq, const int32_t *d_seeds,
+                          void *d_ws, size_t ws_bytes, void *stream);
 int fmb_polish3d_f64(const double *d_cost, int64_t cost_qstride, double *d_T, int64_t T_qstride,
                      int ny, int nx, int nz, int nq, const int32_t *d_seeds,
                      void *d_ws, size_t ws_bytes, void *stream);

@@ -64,6 +64,7 @@ SIGNATURES = {
     "fmb_workspace_bytes_3d": (_sz, [_i32, _i32, _i32, _i32]),
     "fmb_solve3d_f64": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
     "fmb_solve3d_f32": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
+    "fmb_solve3d_exact_f64": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
     "fmb_polish3d_f64": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
     "fmb_finish": (C.c_int, [_vp, _sz, _vp, C.POINTER(FmbStats)]),
     "fmb_trace2d_f64": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _dbl, _i32, _vp, _i64, _vp, _vp, _vp]),

@@ -45,8 +45,12 @@ def solve_chunk_gpu(cost, goals, starts, tau: float = 0.5):
     T = engine.solve2d(c, np.asarray(goals, dtype=np.int32), nq=n, sync=False)
     out, cnt, st = engine.trace2d(T, np.asarray(starts, dtype=np.float64), np.asarray(goals, dtype=np.float64), tau)
     engine.finish(dev)
-    out, cnt, st = out.cpu().numpy(), cnt.cpu().numpy(), st.cpu().numpy()
-    return [(out[i, :cnt[i]].copy(), int(st[i])) for i in range(n)]
+    # only the rows that were written travel to the host: the path slab is (n, 30002, 2) fp64 = 480 KB per query
+    keep = torch.arange(out.shape[1], device=dev)[None, :] < cnt[:, None]
+    flat = out[keep].cpu().numpy()
+    cnt, st = cnt.cpu().numpy(), st.cpu().numpy()
+    ends = np.cumsum(cnt)
+    return [(flat[ends[i] - cnt[i]:ends[i]].copy(), int(st[i])) for i in range(n)]
 
 
 def solve_queries(cost, goals: Sequence, starts: Sequence, tau: float = 0.5, chunk: int = 64,

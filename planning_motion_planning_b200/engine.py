@@ -170,9 +170,10 @@ def solve3d(cost: torch.Tensor, seeds, out: Optional[torch.Tensor] = None, nq: O
     """3D analogue of :func:`solve2d` (FastMarching3D.py:126-145, full field).
 
     cost (ny, nx, nz) shared or (nq, ny, nx, nz); seeds (nq, 3) [x, y, z].
-    exact: follow the solve with the polish pass (``fmb_polish3d_f64``) that reproduces the reference's own
-    rounding of ``**2`` on NumPy scalars (libm pow), i.e. the reference field bit for bit up to iteration order;
-    needed where exact ties of the pop order matter (the early exit of ``FastMarching3D.computeTmap``).
+    exact: solve with the reference's own rounding of ``**2`` on NumPy scalars (libm pow, csrc/pow2_glibc.cuh): the
+    field is then the exact fixed point of the reference's arithmetic; needed where exact ties of the pop order matter
+    (the early exit of ``FastMarching3D.computeTmap``).  True = the whole solve in that arithmetic
+    (``fmb_solve3d_exact_f64``); "polish" = the fast solve followed by ``fmb_polish3d_f64``.
     """
     _require_cuda(cost, "cost")
     if cost.dtype not in (torch.float64, torch.float32):
@@ -196,14 +197,21 @@ def solve3d(cost: torch.Tensor, seeds, out: Optional[torch.Tensor] = None, nq: O
     ws = _workspace(L.fmb_workspace_bytes_3d(ny, nx, nz, nq), dev)
     fn = L.fmb_solve3d_f64 if cost.dtype == torch.float64 else L.fmb_solve3d_f32
     with torch.cuda.device(dev):
-        _capi.check(fn(cost.data_ptr(), 0 if shared else ny * nx * nz, out.data_ptr(), ny * nx * nz, ny, nx, nz, nq,
-                       s.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
-        if exact:
+        if exact == "polish":
             if cost.dtype != torch.float64:
-                raise TypeError("the exact polish pass exists for float64 only")
+                raise TypeError("the exact arithmetic exists for float64 only")
+            _capi.check(fn(cost.data_ptr(), 0 if shared else ny * nx * nz, out.data_ptr(), ny * nx * nz, ny, nx, nz, nq,
+                           s.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
             finish(dev)            # the polish pass reuses the workspace: the solve's own failures are reported first
             _capi.check(L.fmb_polish3d_f64(cost.data_ptr(), 0 if shared else ny * nx * nz, out.data_ptr(), ny * nx * nz,
                                            ny, nx, nz, nq, s.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+        else:
+            if exact:
+                if cost.dtype != torch.float64:
+                    raise TypeError("the exact arithmetic exists for float64 only")
+                fn = L.fmb_solve3d_exact_f64
+            _capi.check(fn(cost.data_ptr(), 0 if shared else ny * nx * nz, out.data_ptr(), ny * nx * nz, ny, nx, nz, nq,
+                           s.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
         if sync:
             finish(dev)
     return out

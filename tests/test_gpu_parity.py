@@ -856,11 +856,11 @@ def test_polish3d_reaches_the_fixed_point_of_the_reference_arithmetic(eng):
 
 
 def test_dropin_3d_early_exit_fuzz_slice():
-    """60 volumes of tools/gpu_fuzz_3d.py (70 % uniform-cost with obstacles: the tie-heavy class; 30 % random) through
-    FM3D.computeTmap: values always within 1e-9; the accepted / narrow-band / far pattern is the reference's in all but
-    the cases where cells tied with T[start] straddle the stopping rank (the reference's 3D update is
-    ill-conditioned, a 1-ulp input change moves its result by ~200 ulp, so which cells are EXACTLY tied depends on the
-    reference's evaluation history) -- those differ in a handful of cells, bounded here."""
+    """120 volumes of tools/gpu_fuzz_3d.py (70 % uniform-cost with obstacles: the tie-heavy class the planner's real
+    volume belongs to; 30 % random) through FM3D.computeTmap: the accepted / narrow-band / far pattern is the
+    reference's in EVERY case and the values agree to 1e-9.  This needs the field to carry the reference's own rounding
+    (libm pow for `**2` on NumPy scalars, csrc/pow2_glibc.cuh + fmb_polish3d_f64): without the polish pass 13 of 300
+    such volumes differ in 1-10 cells around T[start] (tools/gpu_fuzz_3d.py <n> <seed> 0)."""
     import importlib.util
     import FastMarching.FastMarching3D as FM3D
     from conftest import ROOT
@@ -869,18 +869,13 @@ def test_dropin_3d_early_exit_fuzz_slice():
     fz = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(fz)
     rng = np.random.default_rng(0)
-    bad = 0
-    for it in range(60):
+    for it in range(120):
         c, g, s, uniform = fz.case(rng)
         ref = O.computeTmap3D(c, g, s)
         got = FM3D.computeTmap(c, np.uint32(g), np.uint32(s))
-        f = np.isfinite(ref) & np.isfinite(got)
+        assert np.array_equal(np.isfinite(got), np.isfinite(ref)), (it, uniform, int((np.isfinite(got) != np.isfinite(ref)).sum()))
+        f = np.isfinite(ref)
         assert float(np.max(np.abs(got[f] - ref[f]) / np.maximum(ref[f], 1.0))) < 1e-9
-        ndiff = int((np.isfinite(got) != np.isfinite(ref)).sum())
-        if ndiff:
-            bad += 1
-            assert uniform and ndiff <= 16, (it, ndiff)
-    assert bad <= 6, bad
 
 
 def test_one_host_thread_two_devices_timing_events():
