@@ -288,6 +288,49 @@ size_t fmb_workspace_bytes_costvolume(int sX, int sY, int sZ);
 int fmb_costvolume_f64(const fmb_costvolume_desc *desc, double *d_cmap, double *d_tunnel, double *d_terrain,
                        void *d_ws, size_t ws_bytes, void *stream);
 
+/* ---- path post-processing (the step right after the tracers) -------------------------
+ * Batched, row counts read from the tracer's device-side counters (d_count of fmb_trace*_f64), asynchronous.
+ *
+ * fmb_path_stitch2d_f64: Coupled_motion_planner.py:1232-1234 -- out = resolution * (vstack(flipud(pathS), pathG[1:]) + 1)
+ *   d_pathS / d_pathG [npairs][cap][2], d_out [npairs][2*cap][2], d_count_out[p] = countS[p] + countG[p] - 1.
+ * fmb_path_post3d_f64: Coupled_motion_planner.py:1641-1671 -- per-axis scaling (scale3 = resX, resY, resZ; host array),
+ *   scipy.signal.savgol_filter(., 11, 3) with its default mode='interp' (cubic fitted to the first / last 11 samples at
+ *   the ends), + offset3 (host array: Xmin, Ymin, Zmin), last row := d_last[p] (device [npaths][3], or NULL), then
+ *   interp1d(range(n), .)(np.linspace(0, n - 1, m)) (np.interp semantics).  d_out [npaths][m][3];
+ *   d_status[p] = 1 when the path has fewer than 11 rows (scipy raises ValueError; the rows are NaN then).
+ *   d_ws: fmb_workspace_bytes_pathpost() bytes. */
+size_t fmb_workspace_bytes_pathpost(void);
+int fmb_path_stitch2d_f64(const double *d_pathS, const int32_t *d_countS, const double *d_pathG, const int32_t *d_countG,
+                          int64_t cap, int npairs, double resolution, double *d_out, int32_t *d_count_out, void *stream);
+int fmb_path_post3d_f64(const double *d_paths, const int32_t *d_count, int64_t cap, int npaths, const double *scale3,
+                        const double *offset3, const double *d_last, int m, double *d_out, int32_t *d_status,
+                        void *d_ws, size_t ws_bytes, void *stream);
+
+/* ---- batch entry for a native host ---------------------------------------------------
+ * Replaces, for N queries at once, the call sequence of the reference's C++ host: MotionPlanning.cpp:31-54
+ * runPyFunction (one query per call into the embedded interpreter) followed by :66-91 returnPyArrayDouble/Int
+ * (raw PyArray_DATA pointers into module globals, Coupled_motion_planner.py:1402-1406, 1678-1693, whose references
+ * are leaked).  HOST pointers in; the result is OWNED by the caller and released with fmb_plan2d_free(); all device
+ * memory and the stream live only inside the call (`device` = CUDA device to use, -1 = the current one).
+ * Synchronous, re-entrant (one call per host thread).
+ *   h_cost    [rows][cost_pitch] fp64 cost map shared by every query (+inf = obstacle)
+ *   h_goals / h_starts  int32 [nq][2] = [x, y]
+ *   per query: full-field solve from the goal (FastMarching.py:92-112), path start -> goal (FastMarching.py:164-236,
+ *   tau, max_steps <= 0 = round(15000 / tau)), waypoints scaled as the planner does, resolution * (cell + 1)
+ *   (Coupled_motion_planner.py:1234; resolution = 1 and subtract 1 for cell units).
+ * Result: query q owns rows offsets[q] .. offsets[q + 1] of `waypoints` ([row][2] = x, y); status[q] = FMB_TRACE_*. */
+typedef struct fmb_plan2d_result {
+    int32_t nq;
+    int64_t *offsets;       /* [nq + 1] */
+    double *waypoints;      /* [offsets[nq]][2] */
+    int32_t *status;        /* [nq] */
+    double solve_ms, trace_ms;   /* device time of the solves / tracers of all chunks (CUDA events) */
+} fmb_plan2d_result;
+int fmb_plan_batch2d_host(const double *h_cost, int64_t cost_pitch, int rows, int cols, const int32_t *h_goals,
+                          const int32_t *h_starts, int nq, double tau, int max_steps, double resolution, int device,
+                          fmb_plan2d_result **out);
+void fmb_plan2d_free(fmb_plan2d_result *r);
+
 #ifdef __cplusplus
 }
 #endif

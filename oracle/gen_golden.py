@@ -296,11 +296,117 @@ def gen_costvolume(n=200, res=0.05):
     print("costvolume.npz: %.0f kB" % (os.path.getsize(os.path.join(OUT, "costvolume.npz")) / 1e3))
 
 
+def gen_pathpost(n=200, res=0.05):
+    """Pins oracle/pathpost_oracle.py on the reference itself:
+      * stitch (Coupled_motion_planner.py:1232-1234): the UNMODIFIED planner main() is run on the synthetic DEM of
+        gen_planner and the local ``roverPath`` of main() is read at its return (profile hook);
+      * smoothing + resampling (:1641-1671): on that DEM the arm path is shorter than the 11-tap window (scipy raises
+        ValueError inside main(), frozen as the status-1 case), so the reference's OWN source lines 1641-1671 are read
+        from the reference tree at run time and executed, unmodified, on longer seeded paths.
+    Asserts the oracle reproduces both bit for bit, freezes inputs and outputs in tests/golden/pathpost.npz."""
+    import importlib
+    from scipy import interpolate, signal
+    from oracle import pathpost_oracle as PO
+    sys.path.insert(0, R.REF_SRC)
+    sys.dont_write_bytecode = True
+    for k in [k for k in sys.modules if k == "FastMarching" or k.startswith("FastMarching.")]:
+        del sys.modules[k]
+    cmp_ = importlib.import_module("Coupled_motion_planner")
+    calls = []
+
+    def wrap(mod, fname, tag):
+        orig = getattr(mod, fname)
+
+        def f(*a):
+            r = orig(*a)
+            calls.append((tag, a, r))
+            return r
+        setattr(mod, fname, f)
+    wrap(cmp_.FM, "getPathGDM", "path2d"); wrap(cmp_.FM3D, "getPathGDM", "path3d")
+    grabbed = {}
+    main_code = cmp_.main.__code__
+
+    def prof(frame, event, arg):
+        if event == "return" and frame.f_code is main_code:
+            grabbed.update(frame.f_locals)
+    size = n * res
+    ax = (np.arange(n) + 0.5) * res
+    X, Y = np.meshgrid(ax, ax)
+    Z = 0.03 * np.sin(2 * np.pi * X / (0.5 * size)) * np.cos(2 * np.pi * Y / (0.7 * size))
+    Z += 0.5 * np.exp(-((X - 0.5 * size) ** 2 + (Y - 0.45 * size) ** 2) / (2 * (0.06 * size) ** 2))
+    d = tempfile.mkdtemp()
+    with open(os.path.join(d, "PRL_DEM.txt"), "w") as f:
+        for row in Z:
+            f.write(",".join(repr(float(v)) for v in row) + "\n")
+    sys.setprofile(prof)
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            cmp_.main(0.8 * size, 0.8 * size, 0.2 * size, 0.2 * size, 0.0, d + "/", res, size)
+        status = "completed"
+    except Exception as e:
+        status = f"raised {type(e).__name__}: {e}"
+    finally:
+        sys.setprofile(None)
+    print("planner main():", status)
+    L = grabbed
+    if "roverPath" not in L:
+        raise SystemExit("planner did not reach the rover-path stitch")
+    paths2d = [c for c in calls if c[0] == "path2d"]
+    pathG, pathS = paths2d[0][2], paths2d[1][2]
+    out = {"status": status, "resolution": float(L["resolution"]), "pathG": pathG, "pathS": pathS}
+    # roverPath is trimmed in place after :1234 (waypoints near the sample / the rover are deleted, :1236-1247) and gets
+    # a z column (:1250): every row the planner kept must be a row of the stitched array, bit for bit and in order
+    stitched = PO.stitch_rover_path(pathS, pathG, out["resolution"])
+    rp = np.asarray(L["roverPath"], dtype=np.float64)
+    j = 0
+    for row in rp:
+        while j < len(stitched) and not np.array_equal(stitched[j], row[:2]):
+            j += 1
+        if j == len(stitched):
+            raise SystemExit("stitched rover path does not contain the planner's roverPath rows")
+        j += 1
+    out["roverPath_trimmed"] = rp
+    p3 = [c for c in calls if c[0] == "path3d"]
+    if p3:
+        out["planner_path3d"] = np.asarray(p3[0][2], dtype=np.float64)      # shorter than the window: ValueError in main()
+    # the reference's own lines 1641-1671, executed unmodified
+    with open(os.path.join(R.REF_SRC, "Coupled_motion_planner.py")) as f:
+        lines = f.read().split("\n")
+    import textwrap
+    block = textwrap.dedent("\n".join(lines[1640:1671]))
+    assert block.lstrip().startswith("gamma3D[:, 0] = gamma3D[:, 0]*resX") and "resizedGamma3D[:, 2] = fz(" in block, block[:200]
+    code = compile(block, "Coupled_motion_planner.py:1641-1671", "exec")
+    rng = np.random.default_rng(7)
+    ncase = 0
+    for (rows, m) in ((11, 25), (12, 7), (57, 57), (57, 200), (300, 41), (23, 1), (16, 2)):
+        t = np.linspace(0.0, 1.0, rows)
+        path = np.stack([5 + 40 * t + rng.normal(0, 0.4, rows), 30 - 12 * t ** 2 + rng.normal(0, 0.4, rows),
+                         8 + 6 * np.sin(3 * t) + rng.normal(0, 0.2, rows)], axis=1)
+        res3 = np.array([0.03 + 0.01 * rng.random(), 0.03 + 0.01 * rng.random(), 0.02 + 0.01 * rng.random()])
+        off3 = rng.normal(0, 2.0, 3)
+        last3 = rng.normal(0, 2.0, 3)
+        ns = {"gamma3D": path.copy(), "resX": res3[0], "resY": res3[1], "resZ": res3[2], "signal": signal,
+              "interpolate": interpolate, "np": np, "effectorBasePath": np.zeros((3, 3)), "Xmin": off3[0], "Ymin": off3[1],
+              "Zmin": off3[2], "xm": last3[0], "ym": last3[1], "zm": last3[2], "finalBasePath": np.zeros((m + 4, 3)), "index": 5}
+        exec(code, ns)
+        ref = np.asarray(ns["resizedGamma3D"], dtype=np.float64)
+        assert ref.shape == (m, 3), ref.shape
+        same(PO.smooth_resample_arm(path, res3, off3, last3, m), ref, f"reference lines 1641-1671, case {ncase}")
+        for k, v in (("path", path), ("res3", res3), ("off3", off3), ("last3", last3), ("resized", ref)):
+            out[f"post{ncase}_{k}"] = v
+        ncase += 1
+    out["npost"] = ncase
+    np.savez_compressed(os.path.join(OUT, "pathpost.npz"), **out)
+    print("pathpost.npz: pathS", pathS.shape, "pathG", pathG.shape, "roverPath rows kept", len(rp), "of", len(stitched),
+          "| post cases", ncase)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     if not R.available():
         raise SystemExit("reference tree not found: run this in the build container")
-    which = sys.argv[1:] or ["2d", "3d", "planner", "costvolume"]
+    which = sys.argv[1:] or ["2d", "3d", "planner", "costvolume", "pathpost"]
     if "2d" in which:
         gen_2d()
     if "3d" in which:
@@ -309,3 +415,5 @@ if __name__ == "__main__":
         gen_planner()
     if "costvolume" in which:
         gen_costvolume()
+    if "pathpost" in which:
+        gen_pathpost()

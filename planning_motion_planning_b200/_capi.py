@@ -41,6 +41,12 @@ class FmbOptions(C.Structure):
     _fields_ += [("reserved", C.c_int32 * 3)]
 
 
+class FmbPlan2DResult(C.Structure):
+    """fmb_plan2d_result of include/fm_b200.h (owned by the caller, released by fmb_plan2d_free)."""
+    _fields_ = [("nq", C.c_int32), ("offsets", C.POINTER(C.c_int64)), ("waypoints", C.POINTER(C.c_double)),
+                ("status", C.POINTER(C.c_int32)), ("solve_ms", C.c_double), ("trace_ms", C.c_double)]
+
+
 class FmbError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"libfm_b200 error {code}: {msg}")
@@ -78,6 +84,12 @@ SIGNATURES = {
     "fmb_workspace_bytes_costmap2d": (_sz, [_i32]),
     "fmb_costmap2d_f64": (C.c_int, [_vp, _vp, _i32, _dbl, _dbl, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "fmb_costmap2d_finish": (C.c_int, [_vp, _sz, _vp, C.POINTER(C.c_int32)]),
+    "fmb_workspace_bytes_pathpost": (_sz, []),
+    "fmb_path_stitch2d_f64": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _dbl, _vp, _vp, _vp]),
+    "fmb_path_post3d_f64": (C.c_int, [_vp, _vp, _i64, _i32, C.POINTER(C.c_double), C.POINTER(C.c_double), _vp, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "fmb_plan_batch2d_host": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _i32, _dbl, _i32, _dbl, _i32,
+                                        C.POINTER(C.POINTER(FmbPlan2DResult))]),
+    "fmb_plan2d_free": (None, [C.POINTER(FmbPlan2DResult)]),
     "fmb_workspace_bytes_costvolume": (_sz, [_i32, _i32, _i32]),
     "fmb_costvolume_f64": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _sz, _vp]),
 }

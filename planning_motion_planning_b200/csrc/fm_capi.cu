@@ -8,7 +8,11 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <math.h>
+
+#include <algorithm>
 #include <mutex>
+#include <vector>
 
 #include "eikonal2d.cuh"
 #include "eikonal2d_cta.cuh"
@@ -465,3 +469,5 @@ int fmb_trace2d_f64(const double *d_T, int64_t T_pitch, int64_t T_qstride, int r
 
 #include "fm_capi3d.inc"
 #include "fm_capi_costmap.inc"
+#include "fm_capi_pathpost.inc"
+#include "fm_capi_host.inc"
