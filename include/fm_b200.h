@@ -90,13 +90,15 @@ typedef struct fmb_options {
     int32_t max_blocks;   /* cap on the persistent grid (0 = none) */
     int32_t watchdog_ms;  /* device watchdog, time without progress */
     int32_t step_cap;     /* in-tile iteration cap */
-    int32_t engine3d;     /* 0 auto, 1 warp-per-tile, 2 CTA-per-tile */
+    int32_t engine3d;     /* 0 auto, 1 warp-per-tile visits (round 1), 3 eight-warp sweep visits */
     int32_t level_div;    /* windowed order: levels per tile crossing at the source's cost (0 = default) */
     int32_t win_running;  /* windowed order: running tiles hold their level (-1 auto, 0 off, 1 on) */
     int32_t check_passes; /* sweep engine: Jacobi check passes tried before another round of sweeps (0 = default) */
     int32_t pipeline;     /* sweep engine, one map: pipelined visits (-1 auto, 0 off, 1 on) */
     int32_t precheck;     /* sweep engine: open every visit with a check pass (-1 auto, 0, 1) */
-    int32_t reserved[3];
+    int32_t causal_slack; /* sweep engines, local causal order: a tile only waits for a neighbour whose priority lies more than
+                             this many percent of one tile crossing (at the seed's cost) below its own (0 = default, -1 = none) */
+    int32_t reserved[2];
 } fmb_options;
 void fmb_get_options(fmb_options *out);
 int fmb_set_options(const fmb_options *in);

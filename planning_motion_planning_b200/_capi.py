@@ -37,8 +37,9 @@ class FmbOptions(C.Structure):
     """fmb_options of include/fm_b200.h (process-wide solver tunables)."""
     _fields_ = [(k, C.c_int32) for k in ("engine2d", "cta_cells", "tile_w2d", "tile_z3d", "best_first", "windowed",
                                          "window", "worker_div", "max_blocks", "watchdog_ms", "step_cap", "engine3d",
-                                         "level_div", "win_running", "check_passes", "pipeline", "precheck")]
-    _fields_ += [("reserved", C.c_int32 * 3)]
+                                         "level_div", "win_running", "check_passes", "pipeline", "precheck",
+                                         "causal_slack")]
+    _fields_ += [("reserved", C.c_int32 * 2)]
 
 
 class FmbPlan2DResult(C.Structure):

@@ -43,6 +43,8 @@ struct Problem2D {
     int precheck;            // sweep engine: 1 = a visit opens with one check pass (recognises no-op visits)
     int check_passes;        // sweep engine: Jacobi check passes tried before another round of sweeps (>= 1)
     int win_div;             // levels per tile crossing at the source's cost (1 in the warp engine)
+    double *slack;           // local causal order: tolerance of the wait rule in T units, written by the seed kernel
+    double slack_frac;       //   = slack_frac x (tile width x cost at the seed of query 0)
     int win_running;         // 1: a tile keeps its level count while it RUNS (released when it finishes), so the
                              //    window is measured from the lowest queued-or-running level
 };
@@ -154,6 +156,10 @@ __global__ void init_seed2d_kernel(Problem2D<real> P) {
         const real c0 = P.cost[q * P.cost_qstride + (long long)sy * P.cost_pitch + sx];
         const double div = P.win_div > 0 ? (double)P.win_div : 1.0;
         *P.win_inv_delta = (c0 > (real)0 && c0 < num<real>::inf()) ? div / ((double)TW * (double)c0) : div / (double)TW;
+    }
+    if (P.windowed == 2 && q == 0) {
+        const real c0 = P.cost[(long long)sy * P.cost_pitch + sx];
+        *P.slack = (c0 > (real)0 && c0 < num<real>::inf()) ? P.slack_frac * (double)TW * (double)c0 : 0.0;
     }
     int cand[5][2] = {{tx, ty}, {-1, -1}, {-1, -1}, {-1, -1}, {-1, -1}};
     if (sx % TW == 0 && tx > 0) { cand[1][0] = tx - 1; cand[1][1] = ty; }

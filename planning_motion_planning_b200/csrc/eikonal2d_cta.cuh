@@ -60,6 +60,7 @@ __device__ __forceinline__ int cta_acquire(const Problem2D<real> &P, int lane, i
             const int tt = item % tiles_per_q;
             const int tty = tt / P.ntx, ttx = tt - tty * P.ntx;
             const unsigned long long mine = *reinterpret_cast<const volatile unsigned long long *>(&P.tile_prio[item]);
+            const double slack = *reinterpret_cast<const volatile double *>(P.slack);
             bool blocked = false;
             if (lane < 4) {
                 const bool ex = lane == 0 ? ttx > 0 : lane == 1 ? ttx < P.ntx - 1 : lane == 2 ? tty > 0 : tty < P.nty - 1;
@@ -72,7 +73,8 @@ __device__ __forceinline__ int cta_acquire(const Problem2D<real> &P, int lane, i
                         const unsigned long long rk = *reinterpret_cast<const volatile unsigned long long *>(&P.run_prio[n]);
                         key = rk < key ? rk : key;
                     }
-                    blocked = key < mine;
+                    // (~0 reads as NaN: never blocks)
+                    blocked = __longlong_as_double((long long)key) + slack < __longlong_as_double((long long)mine);
                 }
             }
             const bool any_blocked = __any_sync(FULL, blocked) && streak < 100000;

@@ -18,6 +18,7 @@
 #include "eikonal2d_cta.cuh"
 #include "eikonal2d_sweep.cuh"
 #include "eikonal3d.cuh"
+#include "eikonal3d_sweep.cuh"
 #include "trace2d.cuh"
 #include "trace3d.cuh"
 
@@ -101,6 +102,7 @@ void opt_defaults_locked() {
     g_opt.check_passes = env_int("FMB_CHECK_PASSES", 0);
     g_opt.pipeline = env_int("FMB_PIPELINE", -1);
     g_opt.precheck = env_int("FMB_PRECHECK", -1);
+    g_opt.causal_slack = env_int("FMB_CAUSAL_SLACK", 0);
     g_opt_init = true;
 }
 fmb_options opt() {
@@ -332,6 +334,8 @@ int solve2d(const real *d_cost, int64_t cost_pitch, int64_t cost_qstride, real *
     P.lev_count = (int *)(ws + L.win_off + 256);
     P.tile_level = (int *)(ws + L.level_off);
     P.run_prio = (unsigned long long *)(ws + L.runprio_off);
+    P.slack = (double *)(ws + L.win_off + 16);
+    P.slack_frac = O.causal_slack > 0 ? 0.01 * O.causal_slack : 0.0;      // measured 4096^2: 10.4 / 10.6 / 11.9 / 15.9 ms at 0 / 25 / 50 / 100 %
     cudaStream_t st = (cudaStream_t)stream;
     if (engine == 3) {
         if (P.best_first) return launch_solve2d_sweep<real, true>(P, L, st);

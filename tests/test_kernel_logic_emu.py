@@ -326,3 +326,61 @@ def test_device_pow2_reproduces_libm_pow_bit_for_bit():
     # and the reference really evaluates numpy-scalar squares through that function
     for v in x[::997_003]:
         assert np.float64(v) ** 2 == ref[np.where(x == v)[0][0]] or not np.isfinite(v)
+
+
+# ------------------------------------------------------------------ 3D sweep engine (csrc/eikonal3d_sweep.cuh)
+@pytest.mark.parametrize("shape,goal", [((9, 9, 9), [4, 4, 4]), ((20, 20, 20), [4, 4, 4]), ((13, 21, 40), [10, 5, 33]),
+                                        ((10, 12, 28), [8, 7, 6])])
+def test_solve3d_sweep_engine_random(shape, goal):
+    """tz=0 selects the eight-warp sweep visits with the local causal order (the library's default 3D engine)."""
+    c = rand_map(shape, 5)
+    if shape == (20, 20, 20):
+        c[8:10, 3:15, 3:15] = np.inf
+    T, st = emu.solve3d(c, [goal], tz=0, nblocks=3)
+    assert rel_err(T[0], O.computeTmap3D(c, goal)) < TOL64
+    assert st["visits"] > 0
+
+
+def test_solve3d_sweep_engine_uniform_batch_and_fp32():
+    c = np.full((16, 20, 36), 20.0)
+    for d in range(3):
+        for e in (0, -1):
+            sl = [slice(None)] * 3
+            sl[d] = e
+            c[tuple(sl)] = np.inf
+    goals = [[5, 5, 5], [10, 8, 30]]
+    T, _ = emu.solve3d(c, goals, tz=0, nblocks=2)
+    for q, g in enumerate(goals):
+        assert rel_err(T[q], O.computeTmap3D(c, g)) < TOL64
+    T32, _ = emu.solve3d(c.astype(np.float32), [goals[0]], tz=0)
+    assert rel_err(T32[0].astype(np.float64), O.computeTmap3D(c, goals[0])) < TOL32
+
+
+def test_update3d_branch_free_form_is_bitwise_the_branching_form():
+    """solve3d_update_sel<EXACT> (one quadratic chosen by selects) == solve3d_update / solve3d_update_exact bit for bit,
+    incl. inf patterns, ties and dropped dimensions; the exact form == the oracle's libm-pow arithmetic."""
+    import ctypes as C
+    L = emu.lib()
+    rng = np.random.default_rng(0)
+    n = 200000
+    t = np.empty((n, 4))
+    base = rng.random(n) * 1000
+    for k in range(3):
+        t[:, k] = base + rng.random(n) * 8
+    t[:, 3] = np.where(rng.random(n) < 0.5, 20.0, 1 + rng.random(n) * 30)
+    m = rng.random((n, 3)) < 0.15
+    t[:, :3][m] = np.inf
+    tie = rng.random(n) < 0.1; t[tie, 1] = t[tie, 0]
+    tie = rng.random(n) < 0.05; t[tie, 2] = t[tie, 1]
+    far = rng.random(n) < 0.1; t[far, 0] += 100
+    t = np.ascontiguousarray(t)
+    for exact in (0, 1):
+        a, b, sl = np.empty(n), np.empty(n), np.zeros(n, dtype=np.int32)
+        L.emu_update3d(t.ctypes.data_as(emu.dp), C.c_longlong(n), exact, a.ctypes.data_as(emu.dp), b.ctypes.data_as(emu.dp),
+                       sl.ctypes.data_as(emu.ip))
+        assert np.array_equal(a.view(np.uint64)[sl == 0], b.view(np.uint64)[sl == 0])
+        assert sl.sum() == 0
+        if exact:
+            some = ~np.all(np.isinf(t[:5000, :3]), axis=1)           # all-inf: the reference raises, the device returns inf
+            ref = np.array([O.solve3d(*row) for row in t[:5000]])
+            assert np.array_equal(ref.view(np.uint64)[some], a[:5000].view(np.uint64)[some])

@@ -3,7 +3,7 @@ import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np, torch
-from planning_motion_planning_b200 import engine, synth
+from planning_motion_planning_b200 import _capi, engine, synth
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 check = len(sys.argv) > 2 and sys.argv[2] == "check"
 configs = sys.argv[3:] or [""]
@@ -15,12 +15,11 @@ else:
     np.savez(cache, c=c, g=np.array(goal), s=np.array(start))
 cd = torch.from_numpy(c).cuda()
 T = torch.empty((1, n, n, n), dtype=torch.float64, device="cuda")
+base = _capi.get_options()
 for cfg in configs:
-    kv = dict(x.split("=") for x in cfg.split(",") if x)
-    for k in list(os.environ):
-        if k.startswith("FMB_") and k not in ("FMB_WATCHDOG_MS", "FMB_LIB"):
-            del os.environ[k]
-    os.environ.update(kv)
+    kv = {k: int(v) for k, v in (x.split("=") for x in cfg.split(",") if x)}
+    _capi.set_options(**base)
+    _capi.set_options(**kv)
     best = None
     for rep in range(3):
         engine.solve3d(cd, [goal], out=T, nq=1, sync=False)
@@ -37,6 +36,10 @@ for cfg in configs:
                       "visits": best["tile_visits"], "steps/visit": round(best["steps"] / max(1, best["tile_visits"]), 1),
                       "cyc/step": round(best["cyc_relax"] / max(1, best["steps"]), 1),
                       "cyc_load/visit": round(best["cyc_load"] / max(1, best["tile_visits"])),
+                      "visits/tile": round(best["tile_visits"] / (n ** 3 / 512), 2), "rounds/visit": round(best.get("rounds", 0) / max(1, best["tile_visits"]), 2),
+                      "cont/visit": round(best.get("continuations", 0) / max(1, best["tile_visits"]), 2), "deferrals": best.get("deferrals", 0),
+                      "cyc_wait/visit": round(best["cyc_wait"] / max(1, best["tile_visits"])), "cyc_relax/visit": round(best["cyc_relax"] / max(1, best["tile_visits"])),
+                      "cyc_store/visit": round(best["cyc_store"] / max(1, best["tile_visits"])),
                       "phase%": {k: round(100 * best["cyc_" + k] / tot, 1) for k in ("wait", "load", "relax", "store")}}), flush=True)
 if check:
     from oracle import oracle as O

@@ -9,6 +9,7 @@
 #include "../../planning_motion_planning_b200/csrc/eikonal2d.cuh"
 #include "../../planning_motion_planning_b200/csrc/eikonal2d_cta.cuh"
 #include "../../planning_motion_planning_b200/csrc/eikonal2d_sweep.cuh"
+#include "../../planning_motion_planning_b200/csrc/eikonal3d_sweep.cuh"
 #include "../../planning_motion_planning_b200/csrc/eikonal3d.cuh"
 #include "../../planning_motion_planning_b200/csrc/pow2_glibc.cuh"
 #include "../../planning_motion_planning_b200/csrc/trace2d.cuh"
@@ -81,6 +82,7 @@ int run2d_cta(const real *cost, long long cost_qstride, real *T, int rows, int c
     P.lev_count = lev_count.data(); P.tile_level = tile_level.data(); P.win_hint = &win_hint; P.win_inv_delta = &win_inv_delta;
     std::vector<unsigned long long> run_prio(ntiles);
     P.run_prio = run_prio.data();
+    double slack = 0.0; P.slack = &slack; P.slack_frac = getenv("FMB_EMU_SLACK") ? atof(getenv("FMB_EMU_SLACK")) : 0.0;
     emu::launch(2, 64, 0, [&] { fmb::init_fill2d_kernel<real>(P, (int)ring.size()); });
     emu::launch(1, 32 * ((nq + 31) / 32), 0, [&] { fmb::init_seed2d_kernel<real, TW>(P); });
     if (R == 0) {          // sweep engine
@@ -99,7 +101,7 @@ int run2d_cta(const real *cost, long long cost_qstride, real *T, int rows, int c
 
 template <typename real, int TZ>
 int run3d(const real *cost, long long cost_qstride, real *T, int ny, int nx, int nz, int nq, const int *seeds, int nblocks,
-          unsigned long long *stats) {
+          unsigned long long *stats, bool sweep = false) {
     fmb::Problem3D<real> P;
     P.cost = cost; P.cost_qstride = cost_qstride; P.T = T; P.T_qstride = (long long)ny * nx * nz;
     P.ny = ny; P.nx = nx; P.nz = nz; P.nq = nq;
@@ -110,15 +112,21 @@ int run3d(const real *cost, long long cost_qstride, real *T, int ny, int nx, int
     fmb::QueueCtl ctl;
     P.tile_state = state.data(); P.q.ctl = &ctl; P.q.ring = ring.data(); P.q.ring_mask = (unsigned)ring.size() - 1;
     P.q.watchdog_cycles = 1LL << 40; P.step_cap = 1 << 20;
+    std::vector<unsigned long long> prio(ntiles), run_prio(ntiles);
+    P.tile_prio = prio.data(); P.run_prio = run_prio.data(); P.causal = sweep ? 1 : 0; P.check_passes = 4; P.arm_all = 0;
+    double slack = 0.0; P.slack = &slack; P.slack_frac = getenv("FMB_EMU_SLACK") ? atof(getenv("FMB_EMU_SLACK")) : 0.0;
+    using TL16 = fmb::Tile3D<real, 16>;
+    const size_t smem_sweep = sizeof(real) * (TL16::T_ELEMS + TL16::C_ELEMS + 8) + 32 * sizeof(unsigned) + 4 * sizeof(int);
     emu::launch(2, 64, 0, [&] { fmb::init_fill3d_kernel<real>(P, (int)ring.size()); });
     emu::launch(1, 32 * ((nq + 31) / 32), 0, [&] { fmb::init_seed3d_kernel<real, TZ>(P); });
-    P.arm_all = 0;
-    emu::launch(nblocks, WARPS * 32, fmb::Tile3D<real, TZ>::WARP_BYTES * WARPS, [&] { fmb::solve3d_kernel<real, TZ, WARPS>(P); });
+    if (sweep) emu::launch(nblocks, 256, smem_sweep, [&] { fmb::solve3d_sweep_kernel<real, false>(P); });
+    else emu::launch(nblocks, WARPS * 32, fmb::Tile3D<real, TZ>::WARP_BYTES * WARPS, [&] { fmb::solve3d_kernel<real, TZ, WARPS>(P); });
     if (getenv("FMB_EMU_POLISH3D") && atoi(getenv("FMB_EMU_POLISH3D")) && sizeof(real) == 8 && !ctl.abort && ctl.pending == 0) {
         P.arm_all = 1;
         emu::launch(2, 64, 0, [&] { fmb::init_resume3d_kernel<real>(P, (int)ring.size()); });
         emu::launch((unsigned)((ntiles + 63) / 64), 64, 0, [&] { fmb::activate_all3d_kernel<real>(P); });
-        emu::launch(nblocks, WARPS * 32, fmb::Tile3D<real, TZ>::WARP_BYTES * WARPS, [&] { fmb::solve3d_kernel<real, TZ, WARPS, true>(P); });
+        if (sweep) emu::launch(nblocks, 256, smem_sweep, [&] { fmb::solve3d_sweep_kernel<real, true>(P); });
+        else emu::launch(nblocks, WARPS * 32, fmb::Tile3D<real, TZ>::WARP_BYTES * WARPS, [&] { fmb::solve3d_kernel<real, TZ, WARPS, true>(P); });
     }
     if (stats) { stats[0] = ctl.visits; stats[1] = ctl.steps; stats[2] = ctl.evals; stats[3] = ctl.pushes; stats[4] = ctl.cells_written; }
     return ctl.abort ? ctl.abort : (ctl.pending != 0 ? -1 : 0);
@@ -167,11 +175,13 @@ int emu_solve2d_cta_f32(const float *cost, long long cost_qstride, float *T, int
 }
 int emu_solve3d_f64(const double *cost, long long cost_qstride, double *T, int ny, int nx, int nz, int nq,
                     const int *seeds, int tz, int nblocks, unsigned long long *stats) {
+    if (tz == 0) return run3d<double, 16>(cost, cost_qstride, T, ny, nx, nz, nq, seeds, nblocks, stats, true);      // sweep engine
     if (tz == 16) return run3d<double, 16>(cost, cost_qstride, T, ny, nx, nz, nq, seeds, nblocks, stats);
     return run3d<double, 32>(cost, cost_qstride, T, ny, nx, nz, nq, seeds, nblocks, stats);
 }
 int emu_solve3d_f32(const float *cost, long long cost_qstride, float *T, int ny, int nx, int nz, int nq,
                     const int *seeds, int tz, int nblocks, unsigned long long *stats) {
+    if (tz == 0) return run3d<float, 16>(cost, cost_qstride, T, ny, nx, nz, nq, seeds, nblocks, stats, true);
     if (tz == 16) return run3d<float, 16>(cost, cost_qstride, T, ny, nx, nz, nq, seeds, nblocks, stats);
     return run3d<float, 32>(cost, cost_qstride, T, ny, nx, nz, nq, seeds, nblocks, stats);
 }
@@ -211,6 +221,16 @@ int emu_truncate3d_f64(const double *F, const double *cost, const int *rank, int
 }
 
 void emu_pow2(const double *x, double *out, long long n) { for (long long i = 0; i < n; ++i) out[i] = fmb::pow2_glibc(x[i]); }
+// the two forms of the 3D update on n (t0, t1, t2, c) tuples: out_sel / out_ref = branch-free / branching, slow = flag of the former
+void emu_update3d(const double *t, long long n, int exact, double *out_sel, double *out_ref, int *slow) {
+    for (long long i = 0; i < n; ++i) {
+        bool sl = false;
+        const double *a = t + 4 * i;
+        if (exact) { out_sel[i] = fmb::solve3d_update_sel<true>(a[0], a[1], a[2], a[3], sl); out_ref[i] = fmb::solve3d_update_exact(a[0], a[1], a[2], a[3]); }
+        else { out_sel[i] = fmb::solve3d_update_sel<false>(a[0], a[1], a[2], a[3], sl); out_ref[i] = fmb::solve3d_update<double>(a[0], a[1], a[2], a[3]); }
+        slow[i] = sl;
+    }
+}
 void emu_div3(const double *x, double *out, long long n) { for (long long i = 0; i < n; ++i) out[i] = fmb::num<double>::div3(x[i]); }
 
 // resume a 2D solve from the current contents of T (domain decomposition tests)
