@@ -34,19 +34,18 @@ def getEikonal(Thor, Tver, cost):
     return .5 * (Thor + Tver + math.sqrt(2 * np.square(cost) - np.square(Thor - Tver)))
 
 
-def _solve_fields(costMap, nodes):
-    """Full fields from each node of ``nodes`` over one map; returns (T tensor (n,rows,cols), swap, shape)."""
+def _device_map(costMap, nodes):
+    """(device copy of the map in C order, swap, nodes in the device map's orientation)."""
     c, swap = _c.as_c_field(costMap)
     rows, cols = c.shape
-    seeds = []
-    for p in nodes:
+    out = []
+    for k, p in enumerate(nodes):
         q = _c.node2(p, swap)
-        _c.check_node2(q, rows, cols)
-        seeds.append(q)
+        if k == 0:
+            _c.check_node2(q, rows, cols)
+        out.append(q)
     dev = _c.device()
-    cd = _c.to_device(np.ascontiguousarray(c), dev)
-    T = engine.solve2d(cd, seeds, nq=len(seeds))
-    return T, cd, swap
+    return _c.to_device(np.ascontiguousarray(c), dev), swap, out, dev
 
 
 def _to_numpy_field(Tt: torch.Tensor, swap: bool) -> np.ndarray:
@@ -60,45 +59,35 @@ def computeTmap(costMap, goal, start):
     The shipped reference function raises ValueError on its first iteration
     (FastMarching.py:107 unpacks three values into two); this implements the evident
     intent, i.e. the semantics of the working 3D driver (FastMarching3D.py:126-145).
+    One library call (fmb_solve2d_until_f64): full solve, pop ranks in the reference's order, replay of the first
+    rank[start] pops.  start == goal, or an unreached / outside start: the FULL field (the goal is closed before the
+    loop and never popped, FastMarching3D.py:127-142).
     """
-    T, cd, swap = _solve_fields(costMap, [goal])
-    T0 = T[0]
-    s = _c.node2(start, swap)
-    rows, cols = T0.shape
-    # start == goal: the reference closes the goal before its loop, so the goal is never popped, the early exit never
-    # fires and the FULL field comes back (FastMarching3D.py:127-142, same loop)
-    if 0 <= s[0] < cols and 0 <= s[1] < rows and bool(torch.isfinite(T0[s[1], s[0]])) and s != _c.node2(goal, swap):
-        rank = _c.pop_ranks_lifo2d(T0, cd, _c.node2(goal, swap), transposed=swap)
-        T0 = _c.truncate(T0, cd, rank, int(rank[s[1], s[0]]))
-    return _to_numpy_field(T0, swap)
+    cd, swap, (g, s), dev = _device_map(costMap, [goal, start])
+    T, info, ws = _c.solve2d_until(cd, g, s, swap)
+    out = _to_numpy_field(T, swap)                      # synchronises
+    _c.finish(ws, dev)
+    _c.check_info(info.tolist())
+    return out
 
 
 def biComputeTmap(costMap, goal, start):
     """Two fronts (G from ``goal``, S from ``start``) advanced alternately until they meet,
     FastMarching.py:114-162.  Returns ``(TmapG, TmapS, nodeJoin)`` with ``nodeJoin`` a
     ``np.uint32[2]`` ``[x, y]``.  Raises ``NameError`` when the fronts never meet, like the
-    reference (:161)."""
-    T, cd, swap = _solve_fields(costMap, [goal, start])
-    TG, TS = T[0], T[1]
-    # the two fronts are independent until they are joined: ranks (and later the truncations) of G and S
-    # run side by side on two streams
-    rG, rS = _c.both_fronts(lambda: _c.pop_ranks_lifo2d(TG, cd, _c.node2(goal, swap), transposed=swap),
-                            lambda: _c.pop_ranks_lifo2d(TS, cd, _c.node2(start, swap), transposed=swap))
-    if _c.node2(goal, swap) == _c.node2(start, swap):
-        # both fronts leave the same cell: each pops its first node (the same one) in round 1 and G's is found closed
-        # in S straight away (FastMarching.py:143-152): k = 1, the join is the first popped node
-        hit = torch.nonzero(rG.reshape(-1) == 1)
-        k, j = (1, int(hit[0])) if hit.numel() else (None, None)
-    else:
-        k, j = _c.bi_join(rG, rS)
-    if k is None:
+    reference (:161).  One library call (fmb_bisolve2d_f64); the S front's ranks and replay run on a second stream."""
+    cd, swap, (g, s), dev = _device_map(costMap, [goal, start])
+    _c.check_node2(s, *cd.shape)
+    TG, TS, info, ws = _c.bisolve2d(cd, g, s, swap)
+    _c.finish(ws, dev)                                  # synchronises; device-side failures of the solve surface here
+    inf = info.tolist()
+    k, j = inf[0], inf[1]
+    if k == 0x7fffffff:
         raise NameError("name 'nodeJoin' is not defined")
-    cols = TG.shape[1]
-    jy, jx = divmod(j, cols)
-    TGt, TSt = _c.both_fronts(lambda: _c.truncate(TG, cd, rG, k), lambda: _c.truncate(TS, cd, rS, k))
+    _c.check_info(inf, fronts=2)
+    jy, jx = divmod(j, cd.shape[1])
     node = (jy, jx) if swap else (jx, jy)
-    outG, outS = _to_numpy_field(TGt, swap), _to_numpy_field(TSt, swap)      # synchronous copies: the side-stream tensors stay alive until here
-    return outG, outS, np.uint32(node)
+    return _to_numpy_field(TG, swap), _to_numpy_field(TS, swap), np.uint32(node)
 
 
 def getPathGDM(totalCostMap, initWaypoint, endWaypoint, tau):

@@ -29,22 +29,16 @@ def computeTmap(costMap, goal, start):
         raise IndexError(f"goal {g} is outside the {ny}x{nx}x{nz} volume")
     dev = _c.device()
     cd = _c.to_device(c, dev)
-    # exact=True: the polish pass gives the field the reference's own rounding (libm pow for `**2` on scalars), so
-    # that exactly tied values are tied here too and the early exit accepts the reference's set of cells
-    T = engine.solve3d(cd, [g], nq=1, exact=_c.EXACT_3D)[0]
     s = [int(np.int64(v)) for v in start]
-    # (start == goal: the goal is closed before the loop and never popped, so the reference returns the full field)
-    if 0 <= s[0] < nx and 0 <= s[1] < ny and 0 <= s[2] < nz and s != g and bool(torch.isfinite(T[s[1], s[0], s[2]])):
-        # Only the order INSIDE the tie group of `start` decides which cells are accepted when it pops:
-        # the plain sort is exact unless another cell carries T[start] (to the tolerance of the device field); then the reference's LIFO
-        # order among equal values is reproduced by the ordered sweep (csrc/tiekeys.cuh).
-        Ts = T[s[1], s[0], s[2]]
-        if int(((T - Ts).abs() <= _c.TIE_TOL_3D * Ts).sum()) > 1:
-            rank = _c.pop_ranks_lifo3d(T, cd, g)
-        else:
-            rank = _c.pop_ranks(T)
-        T = _c.truncate(T, cd, rank, int(rank[s[1], s[0], s[2]]))
-    return _c.to_host(T)
+    # One library call (fmb_solve3d_until_f64): the solve in the reference's own arithmetic (libm pow for `**2` on
+    # scalars, so exactly tied values are tied here too), pop ranks with the reference's LIFO order inside the tie
+    # group of `start` (only that group decides which cells are accepted when it pops), replay of the first
+    # rank[start] pops.  start == goal / outside / unreached: the full field (the goal is closed before the loop).
+    T, info, ws = _c.solve3d_until(cd, g, s)
+    out = _c.to_host(T)                                 # synchronises
+    _c.finish(ws, dev)
+    _c.check_info(info.tolist())
+    return out
 
 
 def getPathGDM(totalCostMap, initWaypoint, endWaypoint, tau):

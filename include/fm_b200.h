@@ -79,7 +79,8 @@ typedef struct fmb_stats {
 /* Tunables of the solvers: process-wide, read by every solve call (no getenv() on the call path; the FMB_*
  * environment variables only give the INITIAL values, read once at first use).  0 / -1 = automatic. */
 typedef struct fmb_options {
-    int32_t engine2d;     /* 0 auto, 1 warp-per-tile visits (round 1), 2 CTA-per-tile Jacobi visits, 3 four-warp sweep visits */
+    int32_t engine2d;     /* 0 auto, 1 warp-per-tile armed-cell visits (round 1), 2 CTA-per-tile Jacobi visits, 3 four-warp sweep visits,
+                             4 / 5 warp-per-tile sweep visits for batches (costs staged in shared memory / read from global) */
     int32_t cta_cells;    /* cells per thread of the CTA engine: 0 auto, 1, 2 or 4 */
     int32_t tile_w2d;     /* tile width of the warp engine: 16 or 32 */
     int32_t tile_z3d;     /* 3D tile depth: 16 or 32 */
@@ -307,6 +308,46 @@ int fmb_path_stitch2d_f64(const double *d_pathS, const int32_t *d_countS, const 
 int fmb_path_post3d_f64(const double *d_paths, const int32_t *d_count, int64_t cap, int npaths, const double *scale3,
                         const double *offset3, const double *d_last, int m, double *d_out, int32_t *d_status,
                         void *d_ws, size_t ws_bytes, void *stream);
+
+/* ---- the early-exit front end inside the library ------------------------------------------------------------
+ * Pop ranks of a FULL field (what fmb_truncate* and fmb_bi_join consume), incl. the reference's LIFO order among
+ * exactly equal values (FastMarching.py:65-67,76-78 / FastMarching3D.py:77-95 bisect_left + insert): a stable radix
+ * sort of T, the tie groups, and the ordered sweep of fmb_tie_order* -- one call, caller-supplied workspace of
+ * fmb_workspace_bytes_pop_ranks(cells) bytes, asynchronous, no host synchronisation (whether ties exist at all and
+ * whether a tie group is too large for the sweep is decided on the device).  d_T / d_cost dense; seed_index = flat
+ * index of the source.  3D: focus_index >= 0 restricts the question to the tie group of that cell (the early exit
+ * only depends on the order inside the group of `start`), -1 = every group.
+ * fmb_pop_ranks_status (synchronises): out4 = {ties exist, largest tie group, waits that hit the safety limit
+ * (must be 0), a group exceeded 4096 cells (the ranks are then the plain stable order -- not the reference's on
+ * that degenerate map)}. */
+size_t fmb_workspace_bytes_pop_ranks(int64_t cells);
+int fmb_pop_ranks2d_f64(const double *d_T, const double *d_cost, int rows, int cols, int32_t seed_index, int32_t transposed,
+                        int32_t *d_rank, void *d_ws, size_t ws_bytes, void *stream);
+int fmb_pop_ranks3d_f64(const double *d_T, const double *d_cost, int ny, int nx, int nz, int32_t seed_index, int32_t focus_index,
+                        int32_t *d_rank, void *d_ws, size_t ws_bytes, void *stream);
+int fmb_pop_ranks_status(const void *d_ws, void *stream, int32_t *out4);
+
+/* biComputeTmap in ONE call (FastMarching.py:114-162): both full fields, both rank sets, the join, both partial
+ * fields.  d_cost dense [rows][cols]; goal_xy / start_xy HOST int32[2]; transposed: see fmb_tie_order2d_f64.
+ * d_TG / d_TS: out, the partial fields the reference returns; d_join: device int32[16], [0] = k (pops per front when
+ * the loop breaks), [1] = flat index of nodeJoin, both INT32_MAX when the fronts never meet (reference: NameError);
+ * [4..7] / [8..11] = fmb_pop_ranks_status of the G / S front, [12] / [13] = waits of the G / S replay that hit the
+ * safety limit (must be 0).
+ * stream2: optional second stream for the S front (NULL = everything on `stream`); on return `stream` has joined it.
+ * Asynchronous; fmb_finish(d_ws, ...) reports device-side failures of the solve. */
+size_t fmb_workspace_bytes_bisolve2d(int rows, int cols);
+int fmb_bisolve2d_f64(const double *d_cost, int rows, int cols, const int32_t *goal_xy, const int32_t *start_xy, int32_t transposed,
+                      double *d_TG, double *d_TS, int32_t *d_join, void *d_ws, size_t ws_bytes, void *stream, void *stream2);
+/* Single front with the reference's early exit in ONE call: FastMarching.py:92-112 (as intended) / FastMarching3D.py:126-145.
+ * The partial field after `start` is accepted; the full field when start is outside the array, unreached, or == goal
+ * (closed before the loop, never popped).  3D: solved in the reference's own arithmetic (fmb_solve3d_exact_f64).
+ * d_info: device int32[16], [0] = k (INT32_MAX = no truncation), [4..7] rank status, [12] replay waits at the limit. */
+size_t fmb_workspace_bytes_until2d(int rows, int cols);
+size_t fmb_workspace_bytes_until3d(int ny, int nx, int nz);
+int fmb_solve2d_until_f64(const double *d_cost, int rows, int cols, const int32_t *goal_xy, const int32_t *start_xy, int32_t transposed,
+                          double *d_T, int32_t *d_info, void *d_ws, size_t ws_bytes, void *stream);
+int fmb_solve3d_until_f64(const double *d_cost, int ny, int nx, int nz, const int32_t *goal_xyz, const int32_t *start_xyz,
+                          double *d_T, int32_t *d_info, void *d_ws, size_t ws_bytes, void *stream);
 
 /* ---- batch entry for a native host ---------------------------------------------------
  * Replaces, for N queries at once, the call sequence of the reference's C++ host: MotionPlanning.cpp:31-54

@@ -88,6 +88,16 @@ SIGNATURES = {
     "fmb_workspace_bytes_pathpost": (_sz, []),
     "fmb_path_stitch2d_f64": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _dbl, _vp, _vp, _vp]),
     "fmb_path_post3d_f64": (C.c_int, [_vp, _vp, _i64, _i32, C.POINTER(C.c_double), C.POINTER(C.c_double), _vp, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "fmb_workspace_bytes_pop_ranks": (_sz, [_i64]),
+    "fmb_pop_ranks2d_f64": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
+    "fmb_pop_ranks3d_f64": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
+    "fmb_pop_ranks_status": (C.c_int, [_vp, _vp, C.POINTER(C.c_int32)]),
+    "fmb_workspace_bytes_bisolve2d": (_sz, [_i32, _i32]),
+    "fmb_bisolve2d_f64": (C.c_int, [_vp, _i32, _i32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _i32, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "fmb_workspace_bytes_until2d": (_sz, [_i32, _i32]),
+    "fmb_workspace_bytes_until3d": (_sz, [_i32, _i32, _i32]),
+    "fmb_solve2d_until_f64": (C.c_int, [_vp, _i32, _i32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _i32, _vp, _vp, _vp, _sz, _vp]),
+    "fmb_solve3d_until_f64": (C.c_int, [_vp, _i32, _i32, _i32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _vp, _vp, _vp, _sz, _vp]),
     "fmb_plan_batch2d_host": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _i32, _dbl, _i32, _dbl, _i32,
                                         C.POINTER(C.POINTER(FmbPlan2DResult))]),
     "fmb_plan2d_free": (None, [C.POINTER(FmbPlan2DResult)]),

@@ -17,6 +17,7 @@
 #include "eikonal2d.cuh"
 #include "eikonal2d_cta.cuh"
 #include "eikonal2d_sweep.cuh"
+#include "eikonal2d_wsweep.cuh"
 #include "eikonal3d.cuh"
 #include "eikonal3d_sweep.cuh"
 #include "trace2d.cuh"
@@ -278,6 +279,39 @@ int launch_solve2d_sweep(fmb::Problem2D<real> P, const WsLayout &L, cudaStream_t
     return FMB_OK;
 }
 
+// Warp-per-tile sweep engine for batches (eikonal2d_wsweep.cuh): 4 independent warps per CTA
+template <typename real, bool BEST, bool STAGE_C>
+int launch_solve2d_wsweep(fmb::Problem2D<real> P, const WsLayout &L, cudaStream_t st) {
+    using TL = fmb::Tile2D<real, 32>;
+    const size_t smem = sizeof(real) * (TL::T_ELEMS + (STAGE_C ? TL::C_ELEMS : 0)) * WARPS;
+    auto kern = fmb::solve2d_wsweep_kernel<real, BEST, STAGE_C>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(solve2d_wsweep)");
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem), "occupancy(solve2d_wsweep)");
+    if (per_sm < 1) return fail(FMB_E_CUDA, "solve2d_wsweep kernel does not fit on an SM%s");
+    const long long ntiles = (long long)P.nq * P.ntx * P.nty;
+    long long blocks = (long long)per_sm * sm_count();
+    const fmb_options O = opt();
+    const int div = O.worker_div > 0 ? O.worker_div : (P.nq == 1 ? 2 : 1);
+    const long long need = (ntiles + (long long)WARPS * div - 1) / ((long long)WARPS * div);
+    if (blocks > need) blocks = need;
+    if (blocks < 1) blocks = 1;
+    if (O.max_blocks > 0 && blocks > O.max_blocks) blocks = O.max_blocks;
+    const long long cells = (long long)P.rows * P.cols * P.nq;
+    long long fill_blocks = (cells + 256 * 8 - 1) / (256 * 8);
+    if (fill_blocks > (long long)sm_count() * 16) fill_blocks = (long long)sm_count() * 16;
+    if (fill_blocks < 1) fill_blocks = 1;
+    cudaGetLastError();
+    timing_begin(st);
+    launch_init2d<real, 32>(P, L, st, -1, fill_blocks);
+    timing_mid(st);
+    kern<<<(unsigned)blocks, WARPS * 32, smem, st>>>(P);
+    cudaError_t le = cudaGetLastError();
+    timing_end(st);
+    CK(le, "launch solve2d_wsweep");
+    return FMB_OK;
+}
+
 template <typename real>
 int solve2d(const real *d_cost, int64_t cost_pitch, int64_t cost_qstride, real *d_T, int64_t T_pitch,
             int64_t T_qstride, int rows, int cols, int nq, const int32_t *d_seeds, void *d_ws, size_t ws_bytes,
@@ -294,7 +328,7 @@ int solve2d(const real *d_cost, int64_t cost_pitch, int64_t cost_qstride, real *
     // a few maps); the warp-per-tile visit (eikonal2d.cuh) for batches, where throughput per warp counts (measured
     // 4096 x 512^2: 64 ms against 142 ms).
     const int engine = O.engine2d > 0 ? O.engine2d : (best_first ? 1 : 3);
-    int tw = engine >= 2 ? 32 : O.tile_w2d;
+    int tw = engine >= 2 ? 32 : O.tile_w2d;       // engines 2-5 use 32 x 32 tiles
     if (tw != 16 && tw != 32) return fail(FMB_E_INVALID, "tile_w2d must be 16 or 32%s");
     const long long ntiles = tiles2d(rows, cols, tw) * nq;
     if (ntiles >= (1LL << 30)) return fail(FMB_E_INVALID, "too many tiles for one launch%s");
@@ -321,7 +355,8 @@ int solve2d(const real *d_cost, int64_t cost_pitch, int64_t cost_qstride, real *
     // for maps of >= 16384 tiles
     P.windowed = (!P.best_first && resume_activate < 0)
                      ? (O.windowed >= 0 ? O.windowed : (engine == 3 ? 2 : ((nq == 1 && ntiles >= 16384) ? 1 : 0))) : 0;
-    if (P.windowed == 2 && engine != 3) P.windowed = 1;       // the local causal order exists in the sweep engine only
+    if (P.windowed == 2 && engine != 3 && engine < 4) P.windowed = 1;       // the local causal order exists in the sweep engines only
+    if (engine >= 4 && P.windowed == 1) P.windowed = 0;       // (the warp-sweep engine has FIFO, causal and best-first orders)
     if (P.windowed == 1 && nq != 1) P.windowed = 0;           // the level window is kept per launch, not per query
     P.win_window = O.window >= 0 ? O.window : 2;
     P.check_passes = O.check_passes > 0 ? O.check_passes : 4;
@@ -337,7 +372,11 @@ int solve2d(const real *d_cost, int64_t cost_pitch, int64_t cost_qstride, real *
     P.slack = (double *)(ws + L.win_off + 16);
     P.slack_frac = O.causal_slack > 0 ? 0.01 * O.causal_slack : 0.0;      // measured 4096^2: 10.4 / 10.6 / 11.9 / 15.9 ms at 0 / 25 / 50 / 100 %
     cudaStream_t st = (cudaStream_t)stream;
-    if (engine == 3) {
+    if (engine >= 4 && resume_activate < 0) {
+        if (engine == 4) return P.best_first ? launch_solve2d_wsweep<real, true, true>(P, L, st) : launch_solve2d_wsweep<real, false, true>(P, L, st);
+        return P.best_first ? launch_solve2d_wsweep<real, true, false>(P, L, st) : launch_solve2d_wsweep<real, false, false>(P, L, st);
+    }
+    if (engine == 3 || engine >= 4) {
         if (P.best_first) return launch_solve2d_sweep<real, true>(P, L, st);
         return launch_solve2d_sweep<real, false>(P, L, st, resume_activate);
     }
@@ -474,4 +513,5 @@ int fmb_trace2d_f64(const double *d_T, int64_t T_pitch, int64_t T_qstride, int r
 #include "fm_capi3d.inc"
 #include "fm_capi_costmap.inc"
 #include "fm_capi_pathpost.inc"
+#include "fm_capi_ranks.inc"
 #include "fm_capi_host.inc"

@@ -92,8 +92,9 @@ template <> __device__ __forceinline__ int tie_child_index<3>(int i, int) { cons
 template <int D>
 __global__ void tie_sweep_kernel(Grid<D> g, const double *T, const double *cost, const int *members, const int *gstart,
                                  const int *gsize, int seed_idx, int transposed, int *rank, int *tau, long long *key, int *done,
-                                 int *gcount, int *ticket, int *failed) {
+                                 int *gcount, int *ticket, int *failed, const int *enable = nullptr) {
     constexpr int NN = Grid<D>::NN;
+    if (enable && !*enable) return;                // decided on the device (fm_capi_ranks.inc): no ties, or nothing to settle
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
     const long long BIG = 0x7fffffffLL;
     const long long total = g.size();

@@ -92,12 +92,13 @@ __device__ __forceinline__ int last_update_time(const Grid<D> &g, const int *ran
 // pass 1: accepted cells keep their final value, everything else starts at +inf (narrow-band cells
 // are overwritten by pass 2); order[r] = the cell popped r-th, for r <= k.
 template <typename real, int D>
-__global__ void truncate_mark_kernel(Grid<D> g, const real *F, const int *rank, int k, real *out, int *order) {
+__global__ void truncate_mark_kernel(Grid<D> g, const real *F, const int *rank, int k, real *out, int *order, const int *k_dev = nullptr) {
     const real INF = num<real>::inf();
     const long long total = g.size();
+    if (k_dev) k = *k_dev;                         // k decided on the device (fm_capi_ranks.inc)
     for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < total; c += (long long)gridDim.x * blockDim.x) {
         const int r = rank[c];
-        if (r <= k) { out[c] = F[c]; if (r >= 0) order[r] = (int)c; }
+        if (r <= k) { out[c] = F[c]; if (r >= 0 && r < total) order[r] = (int)c; }
         else out[c] = INF;
     }
 }
@@ -119,10 +120,12 @@ __device__ __forceinline__ real memo_wait(const real *memo, long long slot, real
 // pass 2: every relaxation of the first k pops, in pop order (see the header of this file)
 template <typename real, int D>
 __global__ void truncate_sweep_kernel(Grid<D> g, const real *F, const real *cost, const int *rank, const int *order, int k,
-                                      real *out, real *memo, int *ticket, int *overflow) {
+                                      real *out, real *memo, int *ticket, int *overflow, const int *k_dev = nullptr) {
     constexpr int NN = Grid<D>::NN;
     const real INF = num<real>::inf();
     const int lane = threadIdx.x & 31;
+    if (k_dev) k = *k_dev;
+    if (k >= g.size()) return;                     // every reached cell is accepted (no early exit): nothing to replay
     const long long n_tickets = ((long long)k + 1) * NN;
     for (;;) {
         int base = 0;

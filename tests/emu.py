@@ -182,7 +182,7 @@ def costvolume(Zs, resX, resY, resZ, sX, sY, sZ, xm, ym, rlim, rO, rm, gamma2D, 
 def tie_groups(F, tol=None):
     """(members, gstart, gsize) of the T-sorted tie groups, as FastMarching/_compat.py builds them
     (values closer than `tol`, relative, are tied; default = the 2D / 3D tolerance of _compat)."""
-    from FastMarching import _compat
+    import ranks_ref as _compat
     if tol is None:
         tol = _compat.TIE_TOL_2D if np.ndim(F) == 2 else _compat.TIE_TOL_3D
     flat = np.ascontiguousarray(F, dtype=np.float64).ravel()

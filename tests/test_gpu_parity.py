@@ -477,17 +477,21 @@ def test_device_side_failure_is_reported_not_hidden(eng, fmb_opts):
 
 
 def test_tie_order_kernel_matches_torch_reference_and_oracle_order():
-    """csrc/tiekeys.cuh (device path of pop_ranks_lifo2d) == the torch implementation of the same
-    rule on the CPU, and both reproduce the reference's true pop order on tie-heavy maps."""
+    """fmb_pop_ranks2d_f64 (radix sort + tie groups + the ordered sweep of csrc/tiekeys.cuh, one library call) == the
+    torch implementation of the same rule on the CPU (tests/ranks_ref.py), and both reproduce the reference's true pop
+    order on tie-heavy maps."""
     import torch
+    import ranks_ref
     from FastMarching import _compat
     from oracle import oracle as O
     uniform = np.pad(np.ones((60, 60)), 1, constant_values=np.inf)
     for c, g, max_bad in ((uniform, [30, 30], 0), (uniform, [12, 40], 0), (plateau_map(80, 1), [8, 8], 0),
                           (plateau_map(80, 2), [8, 8], 0)):
         T, order, _ = O.computeTmap(c, g, return_stats=True)
-        r_cpu = _compat.pop_ranks_lifo2d(torch.from_numpy(T), torch.from_numpy(c), g)
-        r_gpu = _compat.pop_ranks_lifo2d(torch.from_numpy(T).cuda(), torch.from_numpy(c).cuda(), g).cpu()
+        r_cpu = ranks_ref.pop_ranks_lifo2d(torch.from_numpy(T), torch.from_numpy(c), g)
+        r_gpu = _compat.pop_ranks2d(torch.from_numpy(T).cuda(), torch.from_numpy(c).cuda(), g).cpu()
+        st = _compat.ranks_status(torch.device("cuda", torch.cuda.current_device()))
+        assert st[0] == 1 and st[1] > 1 and st[2] == 0 and st[3] == 0          # ties seen, no wait at the limit, no oversized group
         assert torch.equal(r_cpu, r_gpu)                  # iterated torch form == one-pass device sweep
         Td, cd = torch.from_numpy(T).cuda(), torch.from_numpy(c).cuda()
         flat = Td.reshape(-1)
@@ -498,7 +502,7 @@ def test_tie_order_kernel_matches_torch_reference_and_oracle_order():
         group[order0] = grp.to(torch.int32)
         rank0 = torch.empty(flat.numel(), dtype=torch.int32, device="cuda")
         rank0[order0] = torch.arange(flat.numel(), dtype=torch.int32, device="cuda")
-        r_it = _compat._pop_ranks_lifo2d_sort(Td, cd, g[1] * T.shape[1] + g[0], 96, group, rank0).cpu()
+        r_it = ranks_ref.pop_ranks_lifo2d_sort(Td, cd, g[1] * T.shape[1] + g[0], 96, group, rank0).cpu()
         assert torch.equal(r_it, r_gpu)                   # and == the iterated device fallback (huge tie groups)
         mine = np.argsort(r_gpu.numpy().ravel(), kind="stable")[1:1 + len(order)]
         assert int((mine != order).sum()) <= max_bad
@@ -893,3 +897,50 @@ def test_one_host_thread_two_devices_timing_events():
             T = engine.solve2d(torch.from_numpy(c).to(f"cuda:{dev}"), [[60, 60]])[0].cpu().numpy()
             assert engine.last_stats()["solve_kernel_ms"] > 0
         assert rel_err(T, ref) < TOL64
+
+
+def test_c_abi_alone_reproduces_bicomputetmap_and_the_3d_early_exit():
+    """What INTEGRATION.md promises a C / C++ host: the reference's RETURN VALUES from include/fm_b200.h alone.  torch
+    only provides device memory here -- no torch op runs between the library calls: fmb_bisolve2d_f64 (KAT-3b: join
+    node, both partial fields), fmb_solve2d_until_f64, fmb_solve3d_until_f64 (KAT-4 truncated field), each bitwise
+    (2D) / 1e-9 (3D) against the oracle's early-exit loops."""
+    import ctypes as C
+    import torch
+    from oracle import oracle as O
+    from planning_motion_planning_b200 import _capi
+    L = _capi.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    i32 = lambda v: (C.c_int32 * len(v))(*v)
+    c = rand_map((100, 100), 0)
+    g, s = [10, 10], [90, 90]
+    cd = torch.from_numpy(c).cuda()
+    ws = torch.empty(L.fmb_workspace_bytes_bisolve2d(100, 100), dtype=torch.uint8, device="cuda")
+    out = torch.empty((2, 100, 100), dtype=torch.float64, device="cuda")
+    info = torch.empty(16, dtype=torch.int32, device="cuda")
+    _capi.check(L.fmb_bisolve2d_f64(cd.data_ptr(), 100, 100, i32(g), i32(s), 0, out[0].data_ptr(), out[1].data_ptr(), info.data_ptr(),
+                                    ws.data_ptr(), ws.numel(), st, None))
+    _capi.check(L.fmb_finish(ws.data_ptr(), ws.numel(), st, None))
+    TG, TS, j = O.biComputeTmap(c, g, s)
+    inf = info.tolist()
+    assert [inf[1] % 100, inf[1] // 100] == [int(j[0]), int(j[1])] == [64, 36]
+    assert inf[6] == 0 and inf[10] == 0 and inf[12] == 0 and inf[13] == 0
+    for a, ref in ((out[0], TG), (out[1], TS)):
+        assert rel_err(a.cpu().numpy(), ref) < TOL64
+    # single front, early exit when `start` is accepted
+    ws2 = torch.empty(L.fmb_workspace_bytes_until2d(100, 100), dtype=torch.uint8, device="cuda")
+    T2 = torch.empty((100, 100), dtype=torch.float64, device="cuda")
+    _capi.check(L.fmb_solve2d_until_f64(cd.data_ptr(), 100, 100, i32([25, 25]), i32([60, 70]), 0, T2.data_ptr(), info.data_ptr(),
+                                        ws2.data_ptr(), ws2.numel(), st))
+    _capi.check(L.fmb_finish(ws2.data_ptr(), ws2.numel(), st, None))
+    assert rel_err(T2.cpu().numpy(), O.computeTmap(c, [25, 25], [60, 70])) < TOL64
+    # 3D (KAT-4)
+    c3 = rand_map((24, 24, 24), 0)
+    g3, s3 = [5, 6, 7], [18, 17, 16]
+    c3d = torch.from_numpy(c3).cuda()
+    ws3 = torch.empty(L.fmb_workspace_bytes_until3d(24, 24, 24), dtype=torch.uint8, device="cuda")
+    T3 = torch.empty((24, 24, 24), dtype=torch.float64, device="cuda")
+    _capi.check(L.fmb_solve3d_until_f64(c3d.data_ptr(), 24, 24, 24, i32(g3), i32(s3), T3.data_ptr(), info.data_ptr(), ws3.data_ptr(),
+                                        ws3.numel(), st))
+    _capi.check(L.fmb_finish(ws3.data_ptr(), ws3.numel(), st, None))
+    ref3 = O.computeTmap3D(c3, g3, s3)
+    assert int(np.isfinite(ref3).sum()) == 9830 and rel_err(T3.cpu().numpy(), ref3) < TOL64

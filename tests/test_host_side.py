@@ -86,11 +86,11 @@ def test_product_never_imports_oracle():
 
 
 def test_lifo_pop_order_emulation_matches_reference_order():
-    """FastMarching._compat.pop_ranks_lifo2d (torch, runs on CPU tensors here) against the
+    """tests/ranks_ref.pop_ranks_lifo2d (torch on CPU tensors: the rule the device kernels implement) against the
     reference's true pop order (C oracle = bitwise restatement): exact ties pop LIFO."""
     import torch
     from conftest import plateau_map
-    from FastMarching import _compat
+    import ranks_ref as _compat
     uniform = np.pad(np.ones((40, 40)), 1, constant_values=np.inf)
     for c, g, max_bad in ((uniform, [20, 20], 0), (plateau_map(80, 1), [8, 8], 0), (plateau_map(80, 3), [8, 8], 0),
                           (plateau_map(80, 2), [8, 8], 0), (uniform, [12, 30], 0), (rand_map((60, 60), 2), [9, 40], 0)):
@@ -109,7 +109,7 @@ def test_bisolve_emulation_fuzz_is_bitwise_equal_to_the_heap_loop():
     import torch
     import emu
     from conftest import plateau_map
-    from FastMarching import _compat as _c
+    import ranks_ref as _c
     rng = np.random.default_rng(7)
     checked = 0
     for it in range(18):

@@ -273,7 +273,7 @@ def test_tie_order_of_a_transposed_field_follows_the_callers_orientation():
     """An F-ordered input is solved as its C-ordered transpose; the child order of updateNode
     (FastMarching.py:46-54) is not symmetric in x and y, so the tie order must be mapped back."""
     import torch
-    from FastMarching import _compat
+    import ranks_ref as _compat
     uniform = np.pad(np.full((60, 60), 3.0), 1, constant_values=np.inf)
     uniform[30, 8:25] = np.inf
     for c, s in ((uniform, [18, 40]), (plateau_map(96, 7), [70, 66])):

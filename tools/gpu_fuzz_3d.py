@@ -24,7 +24,7 @@ def case(rng):
 if __name__ == "__main__":
     N = int(sys.argv[1]) if len(sys.argv) > 1 else 100
     rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
-    _compat.EXACT_3D = bool(int(sys.argv[3])) if len(sys.argv) > 3 else True
+    EXACT_3D = True   # (the drop-in always solves in the exact arithmetic now: fmb_solve3d_until_f64)
     bad = 0; worst = 0.0; t0 = time.time()
     for it in range(N):
         c, g, s, uniform = case(rng)
@@ -38,4 +38,4 @@ if __name__ == "__main__":
             bad += 1
             print("MISMATCH case", it, "uniform" if uniform else "random", c.shape, g, s, "pattern differs in",
                   int((np.isfinite(got) != np.isfinite(ref)).sum()), "cells; err", e, flush=True)
-    print(f"exact={_compat.EXACT_3D} cases {N} bad {bad} worst rel err {worst:.2e} in {time.time() - t0:.1f} s")
+    print(f"exact={EXACT_3D} cases {N} bad {bad} worst rel err {worst:.2e} in {time.time() - t0:.1f} s")

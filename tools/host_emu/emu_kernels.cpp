@@ -9,6 +9,7 @@
 #include "../../planning_motion_planning_b200/csrc/eikonal2d.cuh"
 #include "../../planning_motion_planning_b200/csrc/eikonal2d_cta.cuh"
 #include "../../planning_motion_planning_b200/csrc/eikonal2d_sweep.cuh"
+#include "../../planning_motion_planning_b200/csrc/eikonal2d_wsweep.cuh"
 #include "../../planning_motion_planning_b200/csrc/eikonal3d_sweep.cuh"
 #include "../../planning_motion_planning_b200/csrc/eikonal3d.cuh"
 #include "../../planning_motion_planning_b200/csrc/pow2_glibc.cuh"
@@ -85,7 +86,14 @@ int run2d_cta(const real *cost, long long cost_qstride, real *T, int rows, int c
     double slack = 0.0; P.slack = &slack; P.slack_frac = getenv("FMB_EMU_SLACK") ? atof(getenv("FMB_EMU_SLACK")) : 0.0;
     emu::launch(2, 64, 0, [&] { fmb::init_fill2d_kernel<real>(P, (int)ring.size()); });
     emu::launch(1, 32 * ((nq + 31) / 32), 0, [&] { fmb::init_seed2d_kernel<real, TW>(P); });
-    if (R == 0) {          // sweep engine
+    if (R == 0 && getenv("FMB_EMU_WSWEEP") && atoi(getenv("FMB_EMU_WSWEEP"))) {          // warp-per-tile sweep engine (1: costs staged, 2: costs from global)
+        const bool stage = atoi(getenv("FMB_EMU_WSWEEP")) == 1;
+        using TL = fmb::Tile2D<real, 32>;
+        const size_t smem = sizeof(real) * (TL::T_ELEMS + (stage ? TL::C_ELEMS : 0)) * 4;
+        if (P.windowed == 1) P.windowed = 0;
+        if (best_first) { if (stage) emu::launch(nblocks, 128, smem, [&] { fmb::solve2d_wsweep_kernel<real, true, true>(P); }); else emu::launch(nblocks, 128, smem, [&] { fmb::solve2d_wsweep_kernel<real, true, false>(P); }); }
+        else { if (stage) emu::launch(nblocks, 128, smem, [&] { fmb::solve2d_wsweep_kernel<real, false, true>(P); }); else emu::launch(nblocks, 128, smem, [&] { fmb::solve2d_wsweep_kernel<real, false, false>(P); }); }
+    } else if (R == 0) {          // sweep engine
         const size_t smem = fmb::Tile2D<real, 32>::WARP_BYTES + 256;
         if (best_first) emu::launch(nblocks, 128, smem, [&] { fmb::solve2d_sweep_kernel<real, true>(P); });
         else emu::launch(nblocks, 128, smem, [&] { fmb::solve2d_sweep_kernel<real, false>(P); });
