@@ -30,6 +30,7 @@ def computeTmap(costMap, goal, start):
     dev = _c.device()
     cd = _c.to_device(c, dev)
     s = [int(np.int64(v)) for v in start]
+    s = [v if -2 ** 31 <= v < 2 ** 31 else -1 for v in s]          # (np.uint32(-1) and friends: outside the volume)
     # One library call (fmb_solve3d_until_f64): the solve in the reference's own arithmetic (libm pow for `**2` on
     # scalars, so exactly tied values are tied here too), pop ranks with the reference's LIFO order inside the tie
     # group of `start` (only that group decides which cells are accepted when it pops), replay of the first

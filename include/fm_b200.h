@@ -99,7 +99,11 @@ typedef struct fmb_options {
     int32_t precheck;     /* sweep engine: open every visit with a check pass (-1 auto, 0, 1) */
     int32_t causal_slack; /* sweep engines, local causal order: a tile only waits for a neighbour whose priority lies more than
                              this many percent of one tile crossing (at the seed's cost) below its own (0 = default, -1 = none) */
-    int32_t reserved[2];
+    int32_t tma;          /* 2D sweep engine: stage interior tiles with TMA tensor copies (-1 auto = on, 0 off, 1 on) */
+    int32_t ring2;        /* 2D sweep engine, local causal order: also wait for a queued / running tile of the SECOND ring whose priority
+                             lies more than this many percent of one tile crossing below mine (0 = default: 200 in 2D, off in 3D; -1 = off) */
+    int32_t variant;      /* sweep engines: bit 0 = straight-line sweep step (predication, no vote / branches), bit 1 (2D) = the cell's current value
+                             is re-read right before the store (0 = default: 3 in 2D, 1 in 3D; -1 = the branching step) */
 } fmb_options;
 void fmb_get_options(fmb_options *out);
 int fmb_set_options(const fmb_options *in);

@@ -45,6 +45,8 @@ struct Problem2D {
     int win_div;             // levels per tile crossing at the source's cost (1 in the warp engine)
     double *slack;           // local causal order: tolerance of the wait rule in T units, written by the seed kernel
     double slack_frac;       //   = slack_frac x (tile width x cost at the seed of query 0)
+    int variant;             // sweep engine: bit 0 = straight-line sweep step (predication instead of vote + branches)
+    double hop_frac;         // second-ring wait rule: slack[1] = hop_frac x the same scale (<= 0: rule off)
     int win_running;         // 1: a tile keeps its level count while it RUNS (released when it finishes), so the
                              //    window is measured from the lowest queued-or-running level
 };
@@ -159,7 +161,9 @@ __global__ void init_seed2d_kernel(Problem2D<real> P) {
     }
     if (P.windowed == 2 && q == 0) {
         const real c0 = P.cost[(long long)sy * P.cost_pitch + sx];
-        *P.slack = (c0 > (real)0 && c0 < num<real>::inf()) ? P.slack_frac * (double)TW * (double)c0 : 0.0;
+        const double scale = (c0 > (real)0 && c0 < num<real>::inf()) ? (double)TW * (double)c0 : 0.0;
+        P.slack[0] = P.slack_frac * scale;
+        P.slack[1] = P.hop_frac * scale;
     }
     int cand[5][2] = {{tx, ty}, {-1, -1}, {-1, -1}, {-1, -1}, {-1, -1}};
     if (sx % TW == 0 && tx > 0) { cand[1][0] = tx - 1; cand[1][1] = ty; }

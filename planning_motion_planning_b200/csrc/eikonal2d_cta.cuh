@@ -62,10 +62,18 @@ __device__ __forceinline__ int cta_acquire(const Problem2D<real> &P, int lane, i
             const unsigned long long mine = *reinterpret_cast<const volatile unsigned long long *>(&P.tile_prio[item]);
             const double slack = *reinterpret_cast<const volatile double *>(P.slack);
             bool blocked = false;
-            if (lane < 4) {
-                const bool ex = lane == 0 ? ttx > 0 : lane == 1 ? ttx < P.ntx - 1 : lane == 2 ? tty > 0 : tty < P.nty - 1;
-                if (ex) {
-                    const int n = item + (lane == 0 ? -1 : lane == 1 ? 1 : lane == 2 ? -P.ntx : P.ntx);
+            if (lane < 12) {
+                // lanes 0-3: the four face neighbours (wait rule above).  lanes 4-11: the second ring (diagonals and the
+                // tiles two steps away in a straight line): an upwind tile there has not activated the face neighbour
+                // between us yet -- that neighbour is still IDLE and invisible to the rule above -- but will, and the
+                // face neighbour will then lower my halo: running now would be repeated.  Such a tile only counts when
+                // its priority lies more than `hop` (one tile crossing, a fraction of it) below mine.
+                const int ddx[12] = {-1, 1, 0, 0, -1, 1, -1, 1, -2, 2, 0, 0};
+                const int ddy[12] = {0, 0, -1, 1, -1, -1, 1, 1, 0, 0, -2, 2};
+                const int nx = ttx + ddx[lane], ny = tty + ddy[lane];
+                const bool ring2 = lane >= 4;
+                if (nx >= 0 && nx < P.ntx && ny >= 0 && ny < P.nty && !(ring2 && P.hop_frac <= 0.0)) {
+                    const int n = item + ddy[lane] * P.ntx + ddx[lane];
                     const int st = ld_volatile(&P.tile_state[n]);
                     unsigned long long key = ~0ULL;
                     if (st == ST_QUEUED || st == ST_DIRTY) key = *reinterpret_cast<const volatile unsigned long long *>(&P.tile_prio[n]);
@@ -74,7 +82,8 @@ __device__ __forceinline__ int cta_acquire(const Problem2D<real> &P, int lane, i
                         key = rk < key ? rk : key;
                     }
                     // (~0 reads as NaN: never blocks)
-                    blocked = __longlong_as_double((long long)key) + slack < __longlong_as_double((long long)mine);
+                    const double tol = ring2 ? *reinterpret_cast<const volatile double *>(P.slack + 1) : slack;
+                    blocked = __longlong_as_double((long long)key) + tol < __longlong_as_double((long long)mine);
                 }
             }
             const bool any_blocked = __any_sync(FULL, blocked) && streak < 100000;

@@ -31,20 +31,81 @@
 //     inputs change?".
 // (Measured and dropped: streaming the halo through global memory while both tiles sweep, with activation of the
 // downwind tiles at step 34 -- twice the visits per tile, slower.)
+//
+// Staging (Blackwell data movement).  An interior tile is staged by TWO TMA tensor copies issued by one thread:
+// cp.async.bulk.tensor.3d of the 38 x 34 T box at (x0 - 2, y0 - 1) -- the halo columns and rows arrive with the tile,
+// which is why the shared T layout has a row pitch of 38 -- and of the 34 x 32 cost box at (x0, y0), both completing
+// on one mbarrier (complete_tx::bytes) that the CTA waits on by parity.  TMA fills out-of-bounds elements with zeros,
+// not +inf, so tiles that touch the map limits (and fp32 / unaligned fields) keep the cp.async / register paths.
 #pragma once
 #include "eikonal2d_cta.cuh"
+#ifndef FMB_HOST_EMU
+#include <cuda.h>          // CUtensorMap
+#endif
 
 namespace fmb {
 
+// shared-memory layout of one sweep-engine CTA (elements of `real` unless noted)
+struct Sweep2DSmem {
+    // T row pitch: [+1] left halo, [+2 .. +33] interior, [+34] right halo, [+35 .. +37] padding that the TMA box fills
+    // with the next columns.  38: PT - 1 odd keeps the skewed accesses of the sweeps (lane l, column d - l) free of
+    // bank conflicts, PT mod 16 = 6 keeps the column accesses of the check passes (lane = row) at two-way (36 is four-way:
+    // measured +3.5 % per sweep step), PT * 8 is a multiple of 16 bytes (TMA box rows, cp.async chunks).
+    static constexpr int PT = 38;
+    static constexpr int PC = 34;                        // cost row pitch
+    static constexpr int T_ELEMS = 1296;                 // 34 rows x 38, padded so that the cost box starts 128-byte aligned
+    static constexpr int C_ELEMS = TILE_H * PC;
+    template <typename real> static constexpr size_t bytes() { return sizeof(real) * (T_ELEMS + C_ELEMS) + 32 * 4 + 4 * 4 + 16; }
+};
+
+#ifndef FMB_HOST_EMU
+struct TmaMaps2D { CUtensorMap T, C; };
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MBAR_DONE;\n"
+        "bra MBAR_WAIT;\n"
+        "MBAR_DONE:\n"
+        "}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *map, int x, int y, int z, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(map), "r"(x), "r"(y), "r"(z),
+                 "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+#else
+struct TmaMaps2D { int unused; };
+#endif
+
+#ifndef FMB_HOST_EMU
+#define FMB_TMA_PARAM , const __grid_constant__ TmaMaps2D tmaps, int use_tma
+#else
+#define FMB_TMA_PARAM , TmaMaps2D tmaps = TmaMaps2D(), int use_tma = 0
+#endif
 template <typename real, bool BEST>
-__global__ void __launch_bounds__(128) solve2d_sweep_kernel(Problem2D<real> P) {
-    using TL = Tile2D<real, 32>;
-    constexpr int PT = TL::PT, TW = 32, NSTEP = TILE_H + TW - 1;
+__global__ void __launch_bounds__(128, 3) solve2d_sweep_kernel(Problem2D<real> P FMB_TMA_PARAM) {
+    constexpr int PT = Sweep2DSmem::PT, PC = Sweep2DSmem::PC, TW = 32, NSTEP = TILE_H + TW - 1;
+#ifndef FMB_HOST_EMU
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+#else
     FMB_DYN_SMEM(smem_raw);
+#endif
     real *sT = reinterpret_cast<real *>(smem_raw);
-    real *sC = sT + TL::T_ELEMS;
-    unsigned *sDirty = reinterpret_cast<unsigned *>(sC + TL::C_ELEMS);      // [32] changed cells per row since the last write-back
+    real *sC = sT + Sweep2DSmem::T_ELEMS;
+    unsigned *sDirty = reinterpret_cast<unsigned *>(sC + Sweep2DSmem::C_ELEMS);      // [32] changed cells per row since the last write-back
     int *sCtl = reinterpret_cast<int *>(sDirty + 32);                        // [0] tile, [1] stop, [2] level, [3] continue in place
+    unsigned long long *sBar = reinterpret_cast<unsigned long long *>(sCtl + 4);      // mbarrier of the TMA copies
+    unsigned bar_phase = 0;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const real INF = num<real>::inf();
     const int tiles_per_q = P.ntx * P.nty;
@@ -55,6 +116,10 @@ __global__ void __launch_bounds__(128) solve2d_sweep_kernel(Problem2D<real> P) {
     unsigned my_evals = 0, my_written = 0;
     int streak = 0;
     long long c_wait = 0, c_load = 0, c_relax = 0, c_store = 0, c_check = 0;
+#ifndef FMB_HOST_EMU
+    if (use_tma && tid == 0) { mbar_init(sBar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncthreads();
+#endif
 
     for (;;) {
         const long long tc0 = clock64();
@@ -82,6 +147,22 @@ __global__ void __launch_bounds__(128) solve2d_sweep_kernel(Problem2D<real> P) {
             const bool fast = sizeof(real) == 8 && y0 >= 1 && y0 + TILE_H < P.rows && x0 + TW <= P.cols &&
                               (P.T_pitch % EPC) == 0 && (P.cost_pitch % EPC) == 0 &&
                               ((size_t)Tq % 16) == 0 && ((size_t)cq % 16) == 0;
+            bool by_tma = false;
+#ifndef FMB_HOST_EMU
+            by_tma = use_tma && sizeof(real) == 8 && x0 >= 2 && x0 + PT - 2 <= P.cols && y0 >= 1 && y0 + TILE_H + 1 <= P.rows;
+            if (by_tma) {
+                // the previous visit's generic-proxy accesses to this shared memory are ordered before the async-proxy writes
+                fence_proxy_async();
+                __syncthreads();
+                if (tid == 0) {
+                    mbar_expect_tx(sBar, (unsigned)(sizeof(real) * ((TILE_H + 2) * PT + TILE_H * PC)));
+                    tma_load_3d(sT, &tmaps.T, x0 - 2, y0 - 1, q, sBar);
+                    tma_load_3d(sC, &tmaps.C, x0, y0, P.cost_qstride ? q : 0, sBar);
+                }
+                mbar_wait(sBar, bar_phase);
+                bar_phase ^= 1u;
+            } else
+#endif
             if (fast) {
                 for (int c = tid; c < (TILE_H + 2) * CPR; c += 128) {
                     const int row = c / CPR, col = (c % CPR) * EPC;
@@ -89,7 +170,7 @@ __global__ void __launch_bounds__(128) solve2d_sweep_kernel(Problem2D<real> P) {
                 }
                 for (int c = tid; c < TILE_H * CPR; c += 128) {
                     const int row = c / CPR, col = (c % CPR) * EPC;
-                    cp_async16_cg(&sC[row * PT + col], &cq[(long long)(y0 + row) * P.cost_pitch + x0 + col]);
+                    cp_async16_cg(&sC[row * PC + col], &cq[(long long)(y0 + row) * P.cost_pitch + x0 + col]);
                 }
                 if (tid < 64) {                                 // left / right halo columns
                     const int k = tid & 31, y = y0 + k;
@@ -112,7 +193,7 @@ __global__ void __launch_bounds__(128) solve2d_sweep_kernel(Problem2D<real> P) {
                     const int yy = y0 + j, xx = x0 + i;
                     real c = INF;
                     if (yy < P.rows && xx < P.cols) c = __ldg(&cq[(long long)yy * P.cost_pitch + xx]);
-                    sC[j * PT + i] = c;
+                    sC[j * PC + i] = c;
                 }
             }
         }
@@ -123,7 +204,7 @@ __global__ void __launch_bounds__(128) solve2d_sweep_kernel(Problem2D<real> P) {
         const int sx = (warp & 1) ? -1 : 1, sy = (warp & 2) ? -1 : 1;
         const int jrow = sy > 0 ? lane : TILE_H - 1 - lane;
         volatile real *rowT = sT + (jrow + 1) * PT + 2;
-        const real *rowC = sC + jrow * PT;
+        const real *rowC = sC + jrow * PC;
         const int dv = sy > 0 ? PT : -PT;              // towards the sweep-downwind row
         const int hcol = sx > 0 ? -1 : TW;             // my upwind halo column (tile coordinates)
         int steps = 0, round = 0;
@@ -143,7 +224,7 @@ __global__ void __launch_bounds__(128) solve2d_sweep_kernel(Problem2D<real> P) {
                 for (int pass = 0; pass < npass; ++pass) {
                     bool changed = false;
                     const real *rT = sT + (lane + 1) * PT + 2 + 8 * warp;
-                    const real *rC = sC + lane * PT + 8 * warp;
+                    const real *rC = sC + lane * PC + 8 * warp;
                     real m[10], u[8], dn[8], cc[8];
 #pragma unroll
                     for (int k = 0; k < 8; ++k) { m[k + 1] = rT[k]; u[k] = rT[k - PT]; dn[k] = rT[k + PT]; cc[k] = rC[k]; }
@@ -178,6 +259,31 @@ __global__ void __launch_bounds__(128) solve2d_sweep_kernel(Problem2D<real> P) {
                 bool hot = false;
                 int ic = min(max(i, 0), TW - 1);
                 real n_cur = rowT[ic], n_c = rowC[ic], n_dwh = rowT[ic + sx], n_dwv = rowT[ic + dv], n_up0 = rowT[ic - dv];
+                if (P.variant & 1) {
+                    // straight-line step: the update is evaluated in every step and its result applied by predication --
+                    // no vote, no branch, no reconvergence point between one step's result and the next step's shuffle;
+                    // the cell's value "as it is now" is loaded at the top of the step with the other operands
+                    for (int d = 0; d < NSTEP; ++d, i += sx) {
+                        const bool valid = (unsigned)i < (unsigned)TW;
+                        const real cur = n_cur, c = n_c, dwh = n_dwh, dwv = n_dwv, up0 = n_up0;
+                        const int iw = ic;
+                        real now = rowT[iw];
+                        ic = min(max(i + sx, 0), TW - 1);
+                        n_cur = rowT[ic]; n_c = rowC[ic]; n_dwh = rowT[ic + sx]; n_dwv = rowT[ic + dv];
+                        if (lane == 0) n_up0 = rowT[ic - dv];
+                        real up = __shfl_up_sync(FULL, res, 1);
+                        if (lane == 0) up = up0;
+                        const bool go = valid && (res < cur || up < cur) && c < INF;
+                        const real v = eikonal_update_sel<real>(res < dwh ? res : dwh, up < dwv ? up : dwv, c);
+                        const bool acc = go && v != cur && v <= num<real>::mul(cur, UP);
+                        if (P.variant & 2) now = rowT[iw];          // as late as possible: the window for a lost update shrinks
+                        const bool st = acc && v != now && v <= num<real>::mul(now, UP);
+                        if (st) rowT[iw] = v;
+                        dirty |= st ? 1u << iw : 0u;
+                        my_evals += go;
+                        res = valid ? (acc ? v : cur) : res;
+                    }
+                } else
                 for (int d = 0; d < NSTEP; ++d, i += sx) {
                     const bool valid = (unsigned)i < (unsigned)TW;
                     const real cur = n_cur, c = n_c, dwh = n_dwh, dwv = n_dwv, up0 = n_up0;

@@ -33,6 +33,8 @@ struct Problem3D {
     int check_passes;        // Jacobi check passes tried before another round of sweeps (>= 1)
     double *slack;           // tolerance of the causal wait rule in T units, written by the seed kernel:
     double slack_frac;       //   slack_frac x (T3Y cells x cost at the seed of query 0)
+    double hop_frac;         // second-ring wait rule: slack[1] = hop_frac x the same scale (<= 0: off)
+    int variant;             // bit 0: straight-line sweep step
 };
 
 // FastMarching3D.py:59-75 -- descending-dimension quadratic solver, in the
@@ -127,26 +129,27 @@ template <bool EXACT>
 __device__ __forceinline__ double solve3d_update_sel(double t0, double t1, double t2, double C, bool &slow) {
     using N = num<double>;
     const double C2 = EXACT ? pow2_glibc(C) : N::mul(C, C);
-    // n = 3: max() keeps the first maximum
+    // n = 3: max() keeps the first maximum.  (Tmax - Tmax)**2 is an exact zero and adding it is exact, so the sum of the
+    // three squares in the reference's order equals the sum of the squares of the two OTHER differences in their
+    // order: two squarings instead of three (and one instead of two at n = 2) -- what counts when a squaring is libm pow.
     const bool g1 = t1 > t0;
     const double m01 = g1 ? t1 : t0;
     const bool g2 = t2 > m01;
     const double mx3 = g2 ? t2 : m01;
-    const double e0 = N::sub(mx3, t0), e1 = N::sub(mx3, t1), e2 = N::sub(mx3, t2);
-    const double p0 = EXACT ? pow2_glibc(e0) : N::mul(e0, e0), p1 = EXACT ? pow2_glibc(e1) : N::mul(e1, e1),
-                 p2 = EXACT ? pow2_glibc(e2) : N::mul(e2, e2);
-    const bool ok3 = C2 > N::add(N::add(p0, p1), p2);
     // Tarray.remove(Tmax): the other two, in order
     const bool rm0 = !g1 && !g2, rm2 = g2;
     const double a = rm0 ? t1 : t0, b = rm2 ? t1 : t2;
+    const double ea = N::sub(mx3, a), eb = N::sub(mx3, b);
+    const double pa = EXACT ? pow2_glibc(ea) : N::mul(ea, ea), pb = EXACT ? pow2_glibc(eb) : N::mul(eb, eb);
+    // (inf - inf = NaN at the maximum itself when it is +inf: the reference's sum is NaN then and its test fails)
+    const bool ok3 = mx3 < N::inf() && C2 > N::add(pa, pb);
     const bool fmax = !(b > a);
     const double mx2 = fmax ? a : b;
-    const double f0 = N::sub(mx2, a), f1 = N::sub(mx2, b);
-    const double r0 = EXACT ? pow2_glibc(f0) : N::mul(f0, f0), r1 = EXACT ? pow2_glibc(f1) : N::mul(f1, f1);
-    const bool ok2 = C2 > N::add(r0, r1);
     const double c1 = fmax ? b : a;                      // the last one standing
-    const double h0 = N::sub(c1, c1);                    // NaN when it is +inf: the test fails like the reference's
-    const bool ok1 = C2 > (EXACT ? pow2_glibc(h0) : N::mul(h0, h0));
+    const double f1 = N::sub(mx2, c1);
+    const double r1 = EXACT ? pow2_glibc(f1) : N::mul(f1, f1);
+    const bool ok2 = mx2 < N::inf() && C2 > r1;
+    const bool ok1 = c1 < N::inf() && C2 > 0.0;          // (c1 - c1)**2 = 0, NaN when c1 is +inf
     const int n = ok3 ? 3 : ok2 ? 2 : ok1 ? 1 : 0;
     const double q0 = N::mul(t0, t0), q1 = N::mul(t1, t1), q2 = N::mul(t2, t2);
     const double qa = rm0 ? q1 : q0, qb = rm2 ? q1 : q2;
@@ -234,7 +237,9 @@ __global__ void init_seed3d_kernel(Problem3D<real> P) {
     const int base = q * P.nty * P.ntx * P.ntz;
     if (P.causal && q == 0) {
         const real c0 = P.cost[((long long)sy * P.nx + sx) * P.nz + sz];
-        *P.slack = (c0 > (real)0 && c0 < num<real>::inf()) ? P.slack_frac * (double)T3Y * (double)c0 : 0.0;
+        const double scale = (c0 > (real)0 && c0 < num<real>::inf()) ? (double)T3Y * (double)c0 : 0.0;
+        P.slack[0] = P.slack_frac * scale;
+        P.slack[1] = P.hop_frac * scale;
     }
     // the seed's own tile and every face-neighbour tile that sees it in its halo
     for (int k = 0; k < 7; ++k) {

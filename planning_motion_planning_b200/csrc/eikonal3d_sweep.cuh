@@ -40,11 +40,16 @@ __device__ __forceinline__ int cta_acquire3d(const Problem3D<real> &P, int lane,
         const unsigned long long mine = *reinterpret_cast<const volatile unsigned long long *>(&P.tile_prio[item]);
         const double slack = *reinterpret_cast<const volatile double *>(P.slack);
         bool blocked = false;
-        if (lane < 6) {
-            const bool ex = lane == 0 ? tz > 0 : lane == 1 ? tz < P.ntz - 1 : lane == 2 ? tx > 0 : lane == 3 ? tx < P.ntx - 1
-                            : lane == 4 ? ty > 0 : ty < P.nty - 1;
-            if (ex) {
-                const int n = item + nbr_off3d(lane, P.ntx, P.ntz);
+        if (lane < 24) {
+            // lanes 0-5: the six face neighbours.  lanes 6-23: the second ring (12 edge diagonals, 6 tiles two steps away
+            // in a straight line), counted only when more than `hop` below my priority (see eikonal2d_cta.cuh)
+            const int dz_[24] = {-1, 1, 0, 0, 0, 0, /*xz*/ -1, 1, -1, 1, /*yz*/ -1, 1, -1, 1, /*xy*/ 0, 0, 0, 0, -2, 2, 0, 0, 0, 0};
+            const int dx_[24] = {0, 0, -1, 1, 0, 0, -1, -1, 1, 1, 0, 0, 0, 0, -1, 1, -1, 1, 0, 0, -2, 2, 0, 0};
+            const int dy_[24] = {0, 0, 0, 0, -1, 1, 0, 0, 0, 0, -1, -1, 1, 1, -1, -1, 1, 1, 0, 0, 0, 0, -2, 2};
+            const int nz = tz + dz_[lane], nx = tx + dx_[lane], ny = ty + dy_[lane];
+            const bool ring2 = lane >= 6;
+            if (nz >= 0 && nz < P.ntz && nx >= 0 && nx < P.ntx && ny >= 0 && ny < P.nty && !(ring2 && P.hop_frac <= 0.0)) {
+                const int n = item + (dy_[lane] * P.ntx + dx_[lane]) * P.ntz + dz_[lane];
                 const int st = ld_volatile(&P.tile_state[n]);
                 unsigned long long key = ~0ULL;
                 if (st == ST_QUEUED || st == ST_DIRTY) key = *reinterpret_cast<const volatile unsigned long long *>(&P.tile_prio[n]);
@@ -53,7 +58,8 @@ __device__ __forceinline__ int cta_acquire3d(const Problem3D<real> &P, int lane,
                     key = rk < key ? rk : key;
                 }
                 // (~0 reads as NaN: never blocks)
-                blocked = __longlong_as_double((long long)key) + slack < __longlong_as_double((long long)mine);
+                const double tol = ring2 ? *reinterpret_cast<const volatile double *>(P.slack + 1) : slack;
+                blocked = __longlong_as_double((long long)key) + tol < __longlong_as_double((long long)mine);
             }
         }
         const bool any_blocked = __any_sync(FULL, blocked) && streak < 100000;
@@ -251,6 +257,32 @@ __global__ void __launch_bounds__(256) solve3d_sweep_kernel(Problem3D<real> P) {
                 int zc = sz > 0 ? min(max(kz, 0), TZ - 1) : TZ - 1 - min(max(kz, 0), TZ - 1);
                 real n_cur = colT[zc], n_c = colC[zc], n_dwz = colT[zc + sz], n_dwx = colT[zc + dvx], n_dwy = colT[zc + dvy];
                 real n_upx0 = colT[zc - dvx], n_upy0 = colT[zc - dvy];
+                if (!EXACT && (P.variant & 1)) {
+                    // straight-line step (see eikonal2d_sweep.cuh): the update is evaluated in every step and applied by
+                    // predication, the cell's value "as it is now" is read as late as possible
+                    for (int d = 0; d < NSTEP; ++d, ++kz) {
+                        const bool valid = (unsigned)kz < (unsigned)TZ;
+                        const int z = zc;
+                        const real cur = n_cur, c = n_c, dwz = n_dwz, dwx = n_dwx, dwy = n_dwy, upx0 = n_upx0, upy0 = n_upy0;
+                        zc = sz > 0 ? min(max(kz + 1, 0), TZ - 1) : TZ - 1 - min(max(kz + 1, 0), TZ - 1);
+                        n_cur = colT[zc]; n_c = colC[zc]; n_dwz = colT[zc + sz]; n_dwx = colT[zc + dvx]; n_dwy = colT[zc + dvy];
+                        if (lx == 0) n_upx0 = colT[zc - dvx];
+                        if (ly == 0) n_upy0 = colT[zc - dvy];
+                        real upx = __shfl_up_sync(FULL, res, 1);
+                        real upy = __shfl_up_sync(FULL, res, 8);
+                        if (lx == 0) upx = upx0;
+                        if (ly == 0) upy = upy0;
+                        const bool go = valid && (res < cur || upx < cur || upy < cur) && c < INF;
+                        const real v = solve3d_update_warp<real, EXACT>(upx < dwx ? upx : dwx, upy < dwy ? upy : dwy, res < dwz ? res : dwz, c, go);
+                        const bool acc = go && v != cur && v <= num<real>::mul(cur, UP);
+                        const real now = colT[z];
+                        const bool st = acc && v != now && v <= num<real>::mul(now, UP);
+                        if (st) colT[z] = v;
+                        dirty |= st ? 1u << z : 0u;
+                        my_evals += go;
+                        res = valid ? (acc ? v : cur) : res;
+                    }
+                } else
                 for (int d = 0; d < NSTEP; ++d, ++kz) {
                     const bool valid = (unsigned)kz < (unsigned)TZ;
                     const int z = zc;

@@ -3,6 +3,7 @@
 // Host side only launches kernels; no host-side numerics, no CPU fallback.
 #include "../../include/fm_b200.h"
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -104,6 +105,9 @@ void opt_defaults_locked() {
     g_opt.pipeline = env_int("FMB_PIPELINE", -1);
     g_opt.precheck = env_int("FMB_PRECHECK", -1);
     g_opt.causal_slack = env_int("FMB_CAUSAL_SLACK", 0);
+    g_opt.tma = env_int("FMB_TMA", -1);
+    g_opt.ring2 = env_int("FMB_RING2", 0);
+    g_opt.variant = env_int("FMB_VARIANT", 0);
     g_opt_init = true;
 }
 fmb_options opt() {
@@ -241,11 +245,50 @@ int launch_solve2d_cta(fmb::Problem2D<real> P, const WsLayout &L, cudaStream_t s
     return FMB_OK;
 }
 
-// Sweep engine (eikonal2d_cta.cuh): 4 warps per tile visit, one diagonal-wavefront sweep each
+// TMA tensor maps of a solve's T and cost arrays (3D: x, y, query), built per call on the host (cuTensorMapEncodeTiled is
+// reached through cudaGetDriverEntryPoint: the library does not link libcuda).  Returns false when the arrays cannot be
+// described (unaligned base / pitch, driver without the entry point): the kernel then stages with cp.async.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+        else cudaGetLastError();
+    }
+    return fn;
+}
+bool make_tmap3d(CUtensorMap *m, const void *base, int rows, int cols, long long pitch, long long qstride, int nq, int box_w, int box_h) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    if (((size_t)base % 16) != 0 || (pitch % 2) != 0 || (qstride % 2) != 0 || cols < box_w || rows < box_h) return false;
+    const bool per_q = qstride > 0 && nq > 1;
+    const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)(per_q ? nq : 1)};
+    const cuuint64_t strides[2] = {(cuuint64_t)pitch * 8, (cuuint64_t)(per_q ? qstride : (long long)rows * pitch) * 8};
+    const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// Sweep engine (eikonal2d_sweep.cuh): 4 warps per tile visit, one diagonal-wavefront sweep each
 template <typename real, bool BEST>
 int launch_solve2d_sweep(fmb::Problem2D<real> P, const WsLayout &L, cudaStream_t st, int resume_activate = -1) {
-    const size_t smem = fmb::Tile2D<real, 32>::WARP_BYTES + 256;
+    const size_t smem = fmb::Sweep2DSmem::bytes<real>();
     auto kern = fmb::solve2d_sweep_kernel<real, BEST>;
+    fmb::TmaMaps2D tm;
+    memset(&tm, 0, sizeof(tm));
+    const fmb_options O0 = opt();
+    int use_tma = 0;
+    if (sizeof(real) == 8 && O0.tma != 0)
+        use_tma = make_tmap3d(&tm.T, P.T, P.rows, P.cols, P.T_pitch, P.T_qstride, P.nq, fmb::Sweep2DSmem::PT, fmb::TILE_H + 2) &&
+                  make_tmap3d(&tm.C, P.cost, P.rows, P.cols, P.cost_pitch, P.cost_qstride, P.nq, fmb::Sweep2DSmem::PC, fmb::TILE_H);
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem), "occupancy(solve2d_sweep)");
     if (per_sm < 1) return fail(FMB_E_CUDA, "solve2d_sweep kernel does not fit on an SM%s");
@@ -258,12 +301,12 @@ int launch_solve2d_sweep(fmb::Problem2D<real> P, const WsLayout &L, cudaStream_t
     // One map in causal order is a chain of dependent visits: two CTAs per SM per query run it as fast as the whole
     // machine (measured 4096^2: 10.3 ms with 296 CTAs, 10.1 ms with 1036) and leave the other slots to concurrent
     // solves on other streams -- a persistent grid that fills every slot would serialise them.
-    if (!P.best_first && P.windowed == 2) {
+    if (!P.best_first && P.windowed == 2 && O.max_blocks <= 0) {
         const long long lean = (long long)2 * sm_count() * P.nq;
         if (blocks > lean) blocks = lean;
     }
     if (blocks < 1) blocks = 1;
-    if (O.max_blocks > 0 && blocks > O.max_blocks) blocks = O.max_blocks;
+    if (O.max_blocks > 0 && blocks > O.max_blocks) blocks = O.max_blocks;      // (an explicit cap also lifts the lean default)
     const long long cells = (long long)P.rows * P.cols * P.nq;
     long long fill_blocks = (cells + 256 * 8 - 1) / (256 * 8);
     if (fill_blocks > (long long)sm_count() * 16) fill_blocks = (long long)sm_count() * 16;
@@ -272,7 +315,7 @@ int launch_solve2d_sweep(fmb::Problem2D<real> P, const WsLayout &L, cudaStream_t
     timing_begin(st);
     launch_init2d<real, 32>(P, L, st, resume_activate, fill_blocks);
     timing_mid(st);
-    kern<<<(unsigned)blocks, 128, smem, st>>>(P);
+    kern<<<(unsigned)blocks, 128, smem, st>>>(P, tm, use_tma);
     cudaError_t le = cudaGetLastError();
     timing_end(st);
     CK(le, "launch solve2d_sweep");
@@ -359,7 +402,7 @@ int solve2d(const real *d_cost, int64_t cost_pitch, int64_t cost_qstride, real *
     if (engine >= 4 && P.windowed == 1) P.windowed = 0;       // (the warp-sweep engine has FIFO, causal and best-first orders)
     if (P.windowed == 1 && nq != 1) P.windowed = 0;           // the level window is kept per launch, not per query
     P.win_window = O.window >= 0 ? O.window : 2;
-    P.check_passes = O.check_passes > 0 ? O.check_passes : 4;
+    P.check_passes = O.check_passes > 0 ? O.check_passes : (engine == 3 ? 2 : 4);
     P.precheck = O.precheck >= 0 ? O.precheck : 0;
     P.pipeline = O.pipeline >= 0 ? O.pipeline : 0;      // early publish: measured slower (more rounds per visit)
     P.win_div = engine == 3 ? (O.level_div > 0 ? O.level_div : 1) : 1;
@@ -370,6 +413,10 @@ int solve2d(const real *d_cost, int64_t cost_pitch, int64_t cost_qstride, real *
     P.tile_level = (int *)(ws + L.level_off);
     P.run_prio = (unsigned long long *)(ws + L.runprio_off);
     P.slack = (double *)(ws + L.win_off + 16);
+    // measured 4096^2 (planner-like map): 10.7 ms without the second-ring rule, 9.3 with it (visits per tile 3.8 -> 2.1);
+    // 7.0 ms with the straight-line sweep step as well (510 -> 376 cycles per step) and two check passes instead of four
+    P.hop_frac = O.ring2 > 0 ? 0.01 * O.ring2 : (O.ring2 < 0 ? 0.0 : 2.0);
+    P.variant = O.variant > 0 ? O.variant : (O.variant < 0 ? 0 : 3);
     P.slack_frac = O.causal_slack > 0 ? 0.01 * O.causal_slack : 0.0;      // measured 4096^2: 10.4 / 10.6 / 11.9 / 15.9 ms at 0 / 25 / 50 / 100 %
     cudaStream_t st = (cudaStream_t)stream;
     if (engine >= 4 && resume_activate < 0) {

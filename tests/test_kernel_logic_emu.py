@@ -384,3 +384,41 @@ def test_update3d_branch_free_form_is_bitwise_the_branching_form():
             some = ~np.all(np.isinf(t[:5000, :3]), axis=1)           # all-inf: the reference raises, the device returns inf
             ref = np.array([O.solve3d(*row) for row in t[:5000]])
             assert np.array_equal(ref.view(np.uint64)[some], a[:5000].view(np.uint64)[some])
+
+
+# ------------------------------------------------------------------ 2D sweep engines (csrc/eikonal2d_sweep.cuh, eikonal2d_wsweep.cuh)
+@pytest.mark.parametrize("variant,ring2", [("0", "1.0"), ("1", "1.0"), ("0", "0"), ("1", "3.0")])
+def test_solve2d_sweep_engine_causal_order(variant, ring2, monkeypatch):
+    """The library's default 2D engine (four sweep warps per tile visit, local causal order with the second-ring wait
+    rule) under the emulator, both forms of the sweep step: == oracle on random, obstacle and plateau maps."""
+    monkeypatch.setenv("FMB_EMU_VARIANT", variant)
+    monkeypatch.setenv("FMB_EMU_RING2", ring2)
+    cases = [(rand_map((100, 100), 0), [25, 25]), (rand_map((70, 133), 2), [120, 5]), (plateau_map(128, 3), [100, 90])]
+    c = rand_map((130, 130), 1)
+    c[40:44, 10:100] = np.inf
+    c[80:84, 30:129] = np.inf
+    cases.append((c, [64, 64]))
+    for c, g in cases:
+        T, st = emu.solve2d_cta(c, [g], R=0, nblocks=3, best_first=0, windowed=2)
+        assert rel_err(T[0], O.computeTmap(c, g)) < TOL64
+        assert st["visits"] > 0
+    T, _ = emu.solve2d_cta(cases[2][0], [[10, 10], [100, 90], [64, 20]], R=0, nblocks=2, best_first=1)
+    for q, g in enumerate([[10, 10], [100, 90], [64, 20]]):
+        assert rel_err(T[q], O.computeTmap(cases[2][0], g)) < TOL64
+
+
+@pytest.mark.parametrize("mode", ["1", "2"])
+def test_solve2d_warp_sweep_engine_for_batches(mode, monkeypatch):
+    """Warp-per-tile sweep visits (engine2d = 4 / 5: costs staged in shared memory / read from global memory)."""
+    monkeypatch.setenv("FMB_EMU_WSWEEP", mode)
+    c = rand_map((100, 100), 0)
+    for bf in (0, 1):
+        T, _ = emu.solve2d_cta(c, [[25, 25], [70, 40]], R=0, nblocks=3, best_first=bf, windowed=0)
+        for q, g in enumerate([[25, 25], [70, 40]]):
+            assert rel_err(T[q], O.computeTmap(c, g)) < TOL64
+    c = plateau_map(96, 3)
+    c[30:34, 10:70] = np.inf
+    T, _ = emu.solve2d_cta(c, [[10, 10]], R=0, nblocks=2, best_first=0, windowed=0)
+    assert rel_err(T[0], O.computeTmap(c, [10, 10])) < TOL64
+    T32, _ = emu.solve2d_cta(c.astype(np.float32), [[10, 10]], R=0, nblocks=2, best_first=0)
+    assert rel_err(T32[0].astype(np.float64), O.computeTmap(c.astype(np.float32).astype(np.float64), [10, 10])) < TOL32

@@ -83,7 +83,9 @@ int run2d_cta(const real *cost, long long cost_qstride, real *T, int rows, int c
     P.lev_count = lev_count.data(); P.tile_level = tile_level.data(); P.win_hint = &win_hint; P.win_inv_delta = &win_inv_delta;
     std::vector<unsigned long long> run_prio(ntiles);
     P.run_prio = run_prio.data();
-    double slack = 0.0; P.slack = &slack; P.slack_frac = getenv("FMB_EMU_SLACK") ? atof(getenv("FMB_EMU_SLACK")) : 0.0;
+    double slack[2] = {0.0, 0.0}; P.slack = slack; P.slack_frac = getenv("FMB_EMU_SLACK") ? atof(getenv("FMB_EMU_SLACK")) : 0.0;
+    P.hop_frac = getenv("FMB_EMU_RING2") ? atof(getenv("FMB_EMU_RING2")) : 1.0;
+    P.variant = getenv("FMB_EMU_VARIANT") ? atoi(getenv("FMB_EMU_VARIANT")) : 0;
     emu::launch(2, 64, 0, [&] { fmb::init_fill2d_kernel<real>(P, (int)ring.size()); });
     emu::launch(1, 32 * ((nq + 31) / 32), 0, [&] { fmb::init_seed2d_kernel<real, TW>(P); });
     if (R == 0 && getenv("FMB_EMU_WSWEEP") && atoi(getenv("FMB_EMU_WSWEEP"))) {          // warp-per-tile sweep engine (1: costs staged, 2: costs from global)
@@ -94,7 +96,7 @@ int run2d_cta(const real *cost, long long cost_qstride, real *T, int rows, int c
         if (best_first) { if (stage) emu::launch(nblocks, 128, smem, [&] { fmb::solve2d_wsweep_kernel<real, true, true>(P); }); else emu::launch(nblocks, 128, smem, [&] { fmb::solve2d_wsweep_kernel<real, true, false>(P); }); }
         else { if (stage) emu::launch(nblocks, 128, smem, [&] { fmb::solve2d_wsweep_kernel<real, false, true>(P); }); else emu::launch(nblocks, 128, smem, [&] { fmb::solve2d_wsweep_kernel<real, false, false>(P); }); }
     } else if (R == 0) {          // sweep engine
-        const size_t smem = fmb::Tile2D<real, 32>::WARP_BYTES + 256;
+        const size_t smem = fmb::Sweep2DSmem::bytes<real>();
         if (best_first) emu::launch(nblocks, 128, smem, [&] { fmb::solve2d_sweep_kernel<real, true>(P); });
         else emu::launch(nblocks, 128, smem, [&] { fmb::solve2d_sweep_kernel<real, false>(P); });
     } else {
@@ -122,7 +124,9 @@ int run3d(const real *cost, long long cost_qstride, real *T, int ny, int nx, int
     P.q.watchdog_cycles = 1LL << 40; P.step_cap = 1 << 20;
     std::vector<unsigned long long> prio(ntiles), run_prio(ntiles);
     P.tile_prio = prio.data(); P.run_prio = run_prio.data(); P.causal = sweep ? 1 : 0; P.check_passes = 4; P.arm_all = 0;
-    double slack = 0.0; P.slack = &slack; P.slack_frac = getenv("FMB_EMU_SLACK") ? atof(getenv("FMB_EMU_SLACK")) : 0.0;
+    double slack[2] = {0.0, 0.0}; P.slack = slack; P.slack_frac = getenv("FMB_EMU_SLACK") ? atof(getenv("FMB_EMU_SLACK")) : 0.0;
+    P.hop_frac = getenv("FMB_EMU_RING2") ? atof(getenv("FMB_EMU_RING2")) : 1.0;
+    P.variant = getenv("FMB_EMU_VARIANT") ? atoi(getenv("FMB_EMU_VARIANT")) : 0;
     using TL16 = fmb::Tile3D<real, 16>;
     const size_t smem_sweep = sizeof(real) * (TL16::T_ELEMS + TL16::C_ELEMS + 8) + 32 * sizeof(unsigned) + 4 * sizeof(int);
     emu::launch(2, 64, 0, [&] { fmb::init_fill3d_kernel<real>(P, (int)ring.size()); });
