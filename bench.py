@@ -266,6 +266,36 @@ def reference_arm(args):
 
 
 # ------------------------------------------------------------------ own arm
+def bind_to_gpu_numa(local_rank):
+    """Pin this process (and with it the first-touch placement of its pinned host buffers) to the CPUs of the NUMA node
+    its GPU hangs off: at N = 8 every rank otherwise runs on node 0 and all H2D / D2H traffic crosses one memory
+    controller (round-1 SCALE record: e2e efficiency 0.58 at 8 GPUs).  Best effort; returns what was done."""
+    info = {"bound": False}
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id if hasattr(torch.cuda.get_device_properties(local_rank), "pci_bus_id") else None
+        dom = getattr(torch.cuda.get_device_properties(local_rank), "pci_domain_id", 0)
+        dvc = getattr(torch.cuda.get_device_properties(local_rank), "pci_device_id", 0)
+        if bus is None:
+            return info
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, dvc)
+        node = int(open(path).read().strip())
+        info["numa_node"] = node
+        if node < 0:
+            return info
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info.update(bound=True, cpus=len(allowed))
+    except Exception as e:          # no sysfs / no permission: measured as is
+        info["error"] = type(e).__name__
+    return info
+
+
 def own_arm(args):
     import torch
     import torch.distributed as dist
@@ -278,6 +308,7 @@ def own_arm(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    affinity = bind_to_gpu_numa(local) if world > 1 else {"bound": False, "note": "single rank: not bound"}
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -803,6 +834,7 @@ def own_arm(args):
             "evals_per_cell": stats["evals"] / cells,
             "roofline": roofline, "e2e": e2e, "e2e_pipelined": e2e_pipelined, "planner_call": bi, "cpu_baseline": cpu, "batch": batch, "batch_sharded": sharded, "volume3d": vol, "costmap2d": cmap, "costvolume3d": cvol,
             "gpu_launches": 4 * K, "clocks": clocks,
+            "host_affinity": affinity, "solver_options": _capi.get_options(),
         }
         print(json.dumps(line), flush=True)
     if world > 1:
