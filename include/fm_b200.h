@@ -306,6 +306,12 @@ int fmb_costvolume_f64(const fmb_costvolume_desc *desc, double *d_cmap, double *
  *   interp1d(range(n), .)(np.linspace(0, n - 1, m)) (np.interp semantics).  d_out [npaths][m][3];
  *   d_status[p] = 1 when the path has fewer than 11 rows (scipy raises ValueError; the rows are NaN then).
  *   d_ws: fmb_workspace_bytes_pathpost() bytes. */
+/* fmb_path_pack_f64: the written rows of npaths tracer slabs ([npaths][cap][dim], d_count rows each) packed into one dense
+ * array, path p at row d_offsets[p] (int64, e.g. the exclusive prefix sum of d_count): d_out[row] = scale * (waypoint + shift)
+ * (scale = 1, shift = 0 copies the waypoints as traced; scale = resolution, shift = 1 gives the planner's metres, :1234).
+ * Lets a batch hand K x dim waypoints to the host instead of cap-row slabs. */
+int fmb_path_pack_f64(const double *d_paths, const int32_t *d_count, const int64_t *d_offsets, int64_t cap, int npaths, int dim,
+                      double scale, double shift, double *d_out, void *stream);
 size_t fmb_workspace_bytes_pathpost(void);
 int fmb_path_stitch2d_f64(const double *d_pathS, const int32_t *d_countS, const double *d_pathG, const int32_t *d_countG,
                           int64_t cap, int npairs, double resolution, double *d_out, int32_t *d_count_out, void *stream);

@@ -84,6 +84,7 @@ SIGNATURES = {
     "fmb_workspace_bytes_costmap2d": (_sz, [_i32]),
     "fmb_costmap2d_f64": (C.c_int, [_vp, _vp, _i32, _dbl, _dbl, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "fmb_costmap2d_finish": (C.c_int, [_vp, _sz, _vp, C.POINTER(C.c_int32)]),
+    "fmb_path_pack_f64": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _dbl, _dbl, _vp, _vp]),
     "fmb_workspace_bytes_pathpost": (_sz, []),
     "fmb_path_stitch2d_f64": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _dbl, _vp, _vp, _vp]),
     "fmb_path_post3d_f64": (C.c_int, [_vp, _vp, _i64, _i32, C.POINTER(C.c_double), C.POINTER(C.c_double), _vp, _i32, _vp, _vp, _vp, _sz, _vp]),

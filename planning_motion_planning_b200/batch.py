@@ -33,11 +33,29 @@ def _dist_info():
     return 0, 1, None
 
 
+class PackedPaths:
+    """Paths of a chunk of queries as three arrays: ``flat`` (K, D) all waypoints back to back, ``counts`` (n,) rows per
+    query, ``status`` (n,) tracer status.  ``unpack()`` gives the ``[(path, status), ...]`` list (views into ``flat``)."""
+    __slots__ = ("flat", "counts", "status")
+
+    def __init__(self, flat, counts, status):
+        self.flat, self.counts, self.status = flat, counts, status
+
+    def __len__(self):
+        return len(self.counts)
+
+    def unpack(self):
+        ends = np.cumsum(self.counts)
+        return [(self.flat[ends[i] - self.counts[i]:ends[i]], int(self.status[i])) for i in range(len(self.counts))]
+
+
 def solve_chunk_gpu(cost, goals, starts, tau: float = 0.5):
     """Default per-chunk worker: full-field solve + one path per query on the current CUDA
-    device.  ``cost`` is one shared (rows, cols) map or (n, rows, cols) maps (numpy or torch)."""
+    device.  ``cost`` is one shared (rows, cols) map or (n, rows, cols) maps (numpy or torch).
+    Only the rows that were written travel to the host: the tracer's slab is (n, 30002, 2) fp64 = 480 KB per query; the
+    written rows are packed on the device (fmb_path_pack_f64) and copied in one piece."""
     import torch
-    from . import engine
+    from . import _capi, engine
     dev = torch.device("cuda", torch.cuda.current_device())
     c = cost if isinstance(cost, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(cost))
     c = c.to(dev, non_blocking=True)
@@ -45,12 +63,13 @@ def solve_chunk_gpu(cost, goals, starts, tau: float = 0.5):
     T = engine.solve2d(c, np.asarray(goals, dtype=np.int32), nq=n, sync=False)
     out, cnt, st = engine.trace2d(T, np.asarray(starts, dtype=np.float64), np.asarray(goals, dtype=np.float64), tau)
     engine.finish(dev)
-    # only the rows that were written travel to the host: the path slab is (n, 30002, 2) fp64 = 480 KB per query
-    keep = torch.arange(out.shape[1], device=dev)[None, :] < cnt[:, None]
-    flat = out[keep].cpu().numpy()
-    cnt, st = cnt.cpu().numpy(), st.cpu().numpy()
-    ends = np.cumsum(cnt)
-    return [(flat[ends[i] - cnt[i]:ends[i]].copy(), int(st[i])) for i in range(n)]
+    off = torch.cumsum(cnt.to(torch.int64), 0) - cnt.to(torch.int64)
+    cnt_h = cnt.cpu().numpy()
+    total = int(cnt_h.sum())
+    packed = torch.empty((max(total, 1), 2), dtype=torch.float64, device=dev)
+    _capi.check(_capi.lib().fmb_path_pack_f64(out.data_ptr(), cnt.data_ptr(), off.data_ptr(), out.shape[1], n, 2, 1.0, 0.0,
+                                              packed.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    return PackedPaths(packed[:total].cpu().numpy(), cnt_h, st.cpu().numpy())
 
 
 def solve_queries(cost, goals: Sequence, starts: Sequence, tau: float = 0.5, chunk: int = 64,
@@ -73,18 +92,34 @@ def solve_queries(cost, goals: Sequence, starts: Sequence, tau: float = 0.5, chu
         raise ValueError("per-query costmaps must have one map per query")
     lo, hi = shard_bounds(Q, rank, world)
     fn = solve_fn or solve_chunk_gpu
-    results: List = []
+    parts: List = []                      # per chunk: a PackedPaths or a plain [(path, status), ...] list (custom solve_fn)
     for a in range(lo, hi, max(1, chunk)):
         b = min(hi, a + max(1, chunk))
         cc = cost[a:b] if per_query else cost
-        results.extend(fn(cc, [list(g) for g in goals[a:b]], [list(s) for s in starts[a:b]], tau))
+        parts.append(fn(cc, [list(g) for g in goals[a:b]], [list(s) for s in starts[a:b]], tau))
+
+    def as_packed(ps):
+        """all chunks of one rank as ONE PackedPaths (three arrays pickle / travel much faster than thousands of small ones)"""
+        if not ps:
+            return PackedPaths(np.zeros((0, 2)), np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.int32))
+        if all(isinstance(p, PackedPaths) for p in ps):
+            return PackedPaths(np.concatenate([p.flat for p in ps]), np.concatenate([p.counts for p in ps]),
+                               np.concatenate([p.status for p in ps]))
+        lst = [r for p in ps for r in (p.unpack() if isinstance(p, PackedPaths) else p)]
+        D = lst[0][0].shape[1] if lst and lst[0][0].ndim == 2 else 2
+        return PackedPaths(np.concatenate([np.asarray(r[0], dtype=np.float64).reshape(-1, D) for r in lst]) if lst else np.zeros((0, D)),
+                           np.array([len(r[0]) for r in lst], dtype=np.int32), np.array([r[1] for r in lst], dtype=np.int32))
+    mine = as_packed(parts)
     if gather and dist is not None and world > 1:
         bucket = [None] * world if rank == 0 else None
-        dist.gather_object((lo, results), bucket, dst=0)
+        dist.gather_object((lo, mine.flat, mine.counts, mine.status), bucket, dst=0)
         if rank == 0:
-            merged: List = []
-            for part_lo, part in sorted(bucket, key=lambda t: t[0]):
-                assert part_lo == len(merged)
-                merged.extend(part)
-            return 0, merged
-    return lo, results
+            bucket.sort(key=lambda t: t[0])
+            pos = 0
+            for part_lo, _, cts, _ in bucket:
+                assert part_lo == pos
+                pos += len(cts)
+            merged = PackedPaths(np.concatenate([t[1] for t in bucket]), np.concatenate([t[2] for t in bucket]),
+                                 np.concatenate([t[3] for t in bucket]))
+            return 0, merged.unpack()
+    return lo, mine.unpack()

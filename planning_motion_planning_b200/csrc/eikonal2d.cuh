@@ -137,8 +137,7 @@ __global__ void init_fill2d_kernel(Problem2D<real> P, int ring_slots) {
     if (P.windowed == 1)
         for (long long i = tid; i < WIN_LEVELS; i += nth) P.lev_count[i] = 0;
     if (tid == 0) {
-        QueueCtl z = {};
-        *P.q.ctl = z;
+        ctl_reset(P.q.ctl);
         if (P.windowed == 1) *P.win_hint = WIN_LEVELS - 1;
     }
 }
@@ -192,7 +191,7 @@ __global__ void init_resume2d_kernel(Problem2D<real> P, int ring_slots) {
     const long long ntiles = (long long)P.nq * P.ntx * P.nty;
     for (long long i = tid; i < ntiles; i += nth) { P.tile_state[i] = ST_IDLE; P.tile_prio[i] = 0x7ff0000000000000ULL; }
     for (long long i = tid; i < ring_slots; i += nth) P.q.ring[i] = -1;
-    if (tid == 0) { QueueCtl z = {}; *P.q.ctl = z; }
+    if (tid == 0) ctl_reset(P.q.ctl);
 }
 template <typename real>
 __global__ void activate_rows2d_kernel(Problem2D<real> P, int activate) {

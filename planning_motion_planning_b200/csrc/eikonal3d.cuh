@@ -223,7 +223,7 @@ __global__ void init_fill3d_kernel(Problem3D<real> P, int ring_slots) {
         if (P.causal) { P.tile_prio[i] = 0x7ff0000000000000ULL; P.run_prio[i] = 0x7ff0000000000000ULL; }
     }
     for (long long i = tid; i < ring_slots; i += nth) P.q.ring[i] = -1;
-    if (tid == 0) { QueueCtl z = {}; *P.q.ctl = z; }
+    if (tid == 0) ctl_reset(P.q.ctl);
 }
 
 template <typename real, int TZ>
@@ -275,7 +275,7 @@ __global__ void init_resume3d_kernel(Problem3D<real> P, int ring_slots) {
         if (P.causal) { P.tile_prio[i] = 0x7ff0000000000000ULL; P.run_prio[i] = 0x7ff0000000000000ULL; }
     }
     for (long long i = tid; i < ring_slots; i += nth) P.q.ring[i] = -1;
-    if (tid == 0) { QueueCtl z = {}; *P.q.ctl = z; }
+    if (tid == 0) ctl_reset(P.q.ctl);
 }
 template <typename real>
 __global__ void activate_all3d_kernel(Problem3D<real> P) {

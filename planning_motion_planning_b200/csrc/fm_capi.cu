@@ -531,6 +531,14 @@ int fmb_finish(void *d_ws, size_t ws_bytes, void *stream, fmb_stats *stats) {
             } else cudaGetLastError();
         }
     }
+    // a failure is reported ONCE: by this call for the solve it finishes, or -- carried over by the init kernels of later
+    // solves (QueueCtl::sticky) -- for an earlier solve that was queued on this workspace and never finished
+    if (!h.abort && h.sticky_magic == fmb::STICKY_MAGIC && h.sticky) h.abort = h.sticky;
+    if (h.abort) {
+        const int zero = 0;
+        CK(cudaMemcpy((char *)d_ws + offsetof(fmb::QueueCtl, abort), &zero, sizeof(int), cudaMemcpyHostToDevice), "cudaMemcpy(abort)");
+        CK(cudaMemcpy((char *)d_ws + offsetof(fmb::QueueCtl, sticky), &zero, sizeof(int), cudaMemcpyHostToDevice), "cudaMemcpy(sticky)");
+    }
     if (h.abort == fmb::DEV_WATCHDOG) return fail(FMB_E_WATCHDOG, "device watchdog fired: a queue wait exceeded FMB_WATCHDOG_MS%s");
     if (h.abort == fmb::DEV_COSTRANGE) return fail(FMB_E_INVALID, "a finite cost lies outside the supported range [1e-140, 1e140] (fp32: [1e-15, 1e15])%s");
     if (h.abort == fmb::DEV_STEPCAP) return fail(FMB_E_STEPCAP, "in-tile iteration cap (FMB_STEP_CAP) exceeded%s");

@@ -96,6 +96,15 @@ __global__ void __launch_bounds__(WARPS * 32) trace2d_kernel(TraceArgs2D<real> A
     K = 1;
     int ci = -1, cj = -1;                                   // cell whose node gradients are cached
     double x00 = 0, x01 = 0, x10 = 0, x11 = 0, y00 = 0, y01 = 0, y10 = 0, y11 = 0;
+    // Node gradients are a pure function of T and of the node, and the path moves at most tau per step: the warp keeps
+    // the normalised gradients of a BLOCK of BW x BH nodes in registers (lane = node), recomputed -- all lanes at once,
+    // one round of loads -- only when the path leaves the block; entering another cell inside the block costs eight
+    // shuffles and no load.  Same values as the reference's per-step recomputation (FastMarching.py:255-297).
+    constexpr int BW = 6, BH = 5;                           // 30 nodes = 5 x 4 cells
+    const bool blocked = n >= BW && m >= BH;
+    int bx = 0, by = -1000000;                              // origin node of the block (none yet)
+    double gbx = 0.0, gby = 0.0;                            // my node's gradient
+    double lnx = 0.0, lny = 0.0;                            // last step direction (block placement)
 
     for (int step = 0; step < A.max_steps; ++step) {
         if (isnan(px) || isnan(py)) { status = TR_VALUEERROR; append_end = false; break; }   // int(nan) at :250
@@ -106,21 +115,32 @@ __global__ void __launch_bounds__(WARPS * 32) trace2d_kernel(TraceArgs2D<real> A
         }
         const int i = (int)fi, j = (int)fj;
         const double a = __dsub_rn(px, (double)i), b = __dsub_rn(py, (double)j);
-        // The four node gradients are a pure function of T and of the cell (i, j); the path moves
-        // at most tau per step, so they are recomputed only when it enters another cell
-        // (same values as the reference's per-step recomputation, shorter dependent chain).
         if (i != ci || j != cj) {
             ci = i; cj = j;
-            if (lane >= 8) {      // idle lanes pull the rows the path is about to enter into L1
-                const int pj = min(max(j - 20 + lane, 0), m - 1);
-                prefetch_l1(&T[(long long)pj * A.T_pitch + i]);
+            if (blocked) {
+                if (i < bx || i > bx + BW - 2 || j < by || j > by + BH - 2) {
+                    // the path walks DOWN the gradient: p -= tau * n, so it heads towards -lnx, -lny
+                    bx = min(max(i - (lnx > 0.0 ? 3 : (lnx < 0.0 ? 1 : 2)), 0), n - BW);
+                    by = min(max(j - (lny > 0.0 ? 2 : 1), 0), m - BH);
+                    if (lane < BW * BH) grad_node2d<real>(T, A.T_pitch, m, n, bx + lane % BW, by + lane / BW, gbx, gby);
+                    else {                                  // the two idle lanes pull the rows ahead into L1
+                        const int pj = min(max(lny > 0.0 ? by - 3 - (lane & 1) : by + BH + 2 + (lane & 1), 0), m - 1);
+                        prefetch_l1(&T[(long long)pj * A.T_pitch + i]);
+                    }
+                }
+                const int l00 = (j - by) * BW + (i - bx);
+                x00 = __shfl_sync(FULL, gbx, l00); x01 = __shfl_sync(FULL, gbx, l00 + 1);
+                x10 = __shfl_sync(FULL, gbx, l00 + BW); x11 = __shfl_sync(FULL, gbx, l00 + BW + 1);
+                y00 = __shfl_sync(FULL, gby, l00); y01 = __shfl_sync(FULL, gby, l00 + 1);
+                y10 = __shfl_sync(FULL, gby, l00 + BW); y11 = __shfl_sync(FULL, gby, l00 + BW + 1);
+            } else {
+                double gx, gy;
+                grad_node2d<real>(T, A.T_pitch, m, n, i + (lane & 1), j + ((lane >> 1) & 1), gx, gy);
+                x00 = __shfl_sync(FULL, gx, 0); x01 = __shfl_sync(FULL, gx, 1);
+                x10 = __shfl_sync(FULL, gx, 2); x11 = __shfl_sync(FULL, gx, 3);
+                y00 = __shfl_sync(FULL, gy, 0); y01 = __shfl_sync(FULL, gy, 1);
+                y10 = __shfl_sync(FULL, gy, 2); y11 = __shfl_sync(FULL, gy, 3);
             }
-            double gx, gy;
-            grad_node2d<real>(T, A.T_pitch, m, n, i + (lane & 1), j + ((lane >> 1) & 1), gx, gy);
-            x00 = __shfl_sync(FULL, gx, 0); x01 = __shfl_sync(FULL, gx, 1);
-            x10 = __shfl_sync(FULL, gx, 2); x11 = __shfl_sync(FULL, gx, 3);
-            y00 = __shfl_sync(FULL, gy, 0); y01 = __shfl_sync(FULL, gy, 1);
-            y10 = __shfl_sync(FULL, gy, 2); y11 = __shfl_sync(FULL, gy, 3);
         }
         const double dx = bilinear_ref(x00, x01, x10, x11, a, b);
         const double dy = bilinear_ref(y00, y01, y10, y11, a, b);
@@ -160,6 +180,7 @@ __global__ void __launch_bounds__(WARPS * 32) trace2d_kernel(TraceArgs2D<real> A
             nx = __ddiv_rn(dx, dhyp2(dx, dy));
             ny = __ddiv_rn(dy, dhyp2(nx, dy));          // sic (:226-227)
         }
+        lnx = nx; lny = ny;
         px = __dsub_rn(px, __dmul_rn(A.tau, nx));
         py = __dsub_rn(py, __dmul_rn(A.tau, ny));
         if (lane == 0) { out[2 * K] = px; out[2 * K + 1] = py; }

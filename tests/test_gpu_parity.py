@@ -474,6 +474,17 @@ def test_device_side_failure_is_reported_not_hidden(eng, fmb_opts):
     assert rel_err(T, O.computeTmap(c, [60, 60])) < TOL64
     with pytest.raises(_capi.FmbError):           # bad arguments are rejected by the C ABI
         _capi.check(_capi.lib().fmb_solve2d_f64(cd.data_ptr(), 10, 0, cd.data_ptr(), 120, 0, 120, 120, 1, None, None, 0, None))
+    # a failure of a solve that was QUEUED (sync=False) is not erased by the next solve's init kernels: it is reported by
+    # the next finish(), once
+    fmb_opts(step_cap=3)
+    eng.solve2d(cd, [[60, 60]], sync=False)
+    fmb_opts(step_cap=1 << 20)
+    eng.solve2d(cd, [[60, 60]], sync=False)
+    with pytest.raises(_capi.FmbError) as ei:
+        eng.finish()
+    assert ei.value.code == _capi.FMB_E_STEPCAP
+    T = eng.solve2d(cd, [[60, 60]])[0].cpu().numpy()          # ... and the workspace is clean again
+    assert rel_err(T, O.computeTmap(c, [60, 60])) < TOL64
 
 
 def test_tie_order_kernel_matches_torch_reference_and_oracle_order():

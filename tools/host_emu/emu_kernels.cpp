@@ -36,7 +36,7 @@ int run2d(const real *cost, long long cost_qstride, real *T, int rows, int cols,
     P.seeds = seeds;
     const long long ntiles = (long long)nq * P.ntx * P.nty;
     std::vector<int> state(ntiles), ring(pow2_at_least(ntiles));
-    fmb::QueueCtl ctl;
+    fmb::QueueCtl ctl = {};
     P.tile_state = state.data(); P.q.ctl = &ctl; P.q.ring = ring.data(); P.q.ring_mask = (unsigned)ring.size() - 1;
     P.q.watchdog_cycles = 1LL << 40; P.step_cap = 1 << 20;
     std::vector<unsigned long long> prio(ntiles);
@@ -69,7 +69,7 @@ int run2d_cta(const real *cost, long long cost_qstride, real *T, int rows, int c
     P.seeds = seeds;
     const long long ntiles = (long long)nq * P.ntx * P.nty;
     std::vector<int> state(ntiles), ring(pow2_at_least(ntiles));
-    fmb::QueueCtl ctl;
+    fmb::QueueCtl ctl = {};
     P.tile_state = state.data(); P.q.ctl = &ctl; P.q.ring = ring.data(); P.q.ring_mask = (unsigned)ring.size() - 1;
     P.q.watchdog_cycles = 1LL << 40; P.step_cap = 1 << 20;
     std::vector<unsigned long long> prio(ntiles);
@@ -119,7 +119,7 @@ int run3d(const real *cost, long long cost_qstride, real *T, int ny, int nx, int
     P.seeds = seeds;
     const long long ntiles = (long long)nq * P.nty * P.ntx * P.ntz;
     std::vector<int> state(ntiles), ring(pow2_at_least(ntiles));
-    fmb::QueueCtl ctl;
+    fmb::QueueCtl ctl = {};
     P.tile_state = state.data(); P.q.ctl = &ctl; P.q.ring = ring.data(); P.q.ring_mask = (unsigned)ring.size() - 1;
     P.q.watchdog_cycles = 1LL << 40; P.step_cap = 1 << 20;
     std::vector<unsigned long long> prio(ntiles), run_prio(ntiles);
@@ -257,7 +257,7 @@ int emu_resolve2d_f64(const double *cost, double *T, int rows, int cols, const i
     const long long ntiles = (long long)P.ntx * P.nty;
     std::vector<int> state(ntiles), ring(pow2_at_least(ntiles));
     std::vector<unsigned long long> prio(ntiles);
-    fmb::QueueCtl ctl;
+    fmb::QueueCtl ctl = {};
     P.tile_state = state.data(); P.q.ctl = &ctl; P.q.ring = ring.data(); P.q.ring_mask = (unsigned)ring.size() - 1;
     P.q.watchdog_cycles = 1LL << 40; P.step_cap = 1 << 20; P.tile_prio = prio.data(); P.best_first = 0; P.arm_rows = halo_rows; P.windowed = 0; P.win_window = 0; P.win_div = 1; P.win_running = 0; P.check_passes = 1; P.precheck = 0; P.pipeline = getenv("FMB_PIPELINE") ? atoi(getenv("FMB_PIPELINE")) : 1;
     P.lev_count = nullptr; P.tile_level = nullptr; P.win_hint = nullptr; P.win_inv_delta = nullptr;
