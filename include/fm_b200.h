@@ -350,8 +350,12 @@ int fmb_bisolve2d_f64(const double *d_cost, int rows, int cols, const int32_t *g
                       double *d_TG, double *d_TS, int32_t *d_join, void *d_ws, size_t ws_bytes, void *stream, void *stream2);
 /* Single front with the reference's early exit in ONE call: FastMarching.py:92-112 (as intended) / FastMarching3D.py:126-145.
  * The partial field after `start` is accepted; the full field when start is outside the array, unreached, or == goal
- * (closed before the loop, never popped).  3D: solved in the reference's own arithmetic (fmb_solve3d_exact_f64).
- * d_info: device int32[16], [0] = k (INT32_MAX = no truncation), [4..7] rank status, [12] replay waits at the limit. */
+ * (closed before the loop, never popped).  3D: the fast solve decides where it can -- the field in the reference's own
+ * arithmetic (fmb_solve3d_exact_f64; 4-8x dearer) differs from it by ~3e-12, so only a (near-)tie of T[start] with
+ * another cell can make the accepted set depend on it; that second solve is launched behind a device flag and its
+ * kernels return at once when no cell lies within 1e-9 of T[start].
+ * d_info: device int32[16], [0] = k (INT32_MAX = no truncation), [4..7] rank status, [12] replay waits at the limit,
+ * [14] (3D) = 1 when the exact solve ran. */
 size_t fmb_workspace_bytes_until2d(int rows, int cols);
 size_t fmb_workspace_bytes_until3d(int ny, int nx, int nz);
 int fmb_solve2d_until_f64(const double *d_cost, int rows, int cols, const int32_t *goal_xy, const int32_t *start_xy, int32_t transposed,

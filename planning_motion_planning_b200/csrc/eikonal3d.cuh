@@ -35,6 +35,8 @@ struct Problem3D {
     double slack_frac;       //   slack_frac x (T3Y cells x cost at the seed of query 0)
     double hop_frac;         // second-ring wait rule: slack[1] = hop_frac x the same scale (<= 0: off)
     int variant;             // bit 0: straight-line sweep step
+    const int *enable;       // device flag or nullptr: when it reads 0 the init and solve kernels of this launch return at once
+                             // (a solve that a preceding kernel found unnecessary: fmb_solve3d_until_f64)
 };
 
 // FastMarching3D.py:59-75 -- descending-dimension quadratic solver, in the
@@ -209,6 +211,7 @@ struct Tile3D {
 
 template <typename real>
 __global__ void init_fill3d_kernel(Problem3D<real> P, int ring_slots) {
+    if (P.enable && !*P.enable) return;
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long nth = (long long)gridDim.x * blockDim.x;
     const real INF = num<real>::inf();
@@ -228,6 +231,7 @@ __global__ void init_fill3d_kernel(Problem3D<real> P, int ring_slots) {
 
 template <typename real, int TZ>
 __global__ void init_seed3d_kernel(Problem3D<real> P) {
+    if (P.enable && !*P.enable) return;
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= P.nq) return;
     const int sx = P.seeds[3 * q], sy = P.seeds[3 * q + 1], sz = P.seeds[3 * q + 2];
@@ -286,6 +290,7 @@ __global__ void activate_all3d_kernel(Problem3D<real> P) {
 
 template <typename real, int TZ, int WARPS, bool EXACT = false>
 __global__ void __launch_bounds__(WARPS * 32) solve3d_kernel(Problem3D<real> P) {
+    if (P.enable && !*P.enable) return;
     using TL = Tile3D<real, TZ>;
     constexpr int PZ = TL::PZ, PS = TL::PS;
     FMB_DYN_SMEM(smem_raw);

@@ -105,6 +105,7 @@ __device__ __forceinline__ real solve3d_update_warp(real tx, real ty, real tz, r
 
 template <typename real, bool EXACT>
 __global__ void __launch_bounds__(256) solve3d_sweep_kernel(Problem3D<real> P) {
+    if (P.enable && !*P.enable) return;
     constexpr int TZ = 16;
     using TL = Tile3D<real, TZ>;
     constexpr int PZ = TL::PZ, PS = TL::PS, NSTEP = T3Y + T3X + TZ - 2;

@@ -204,6 +204,7 @@ inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v)
 inline int atomicMin(int *p, int v) { int o = *p; if (v < o) *p = v; return o; }
 inline int atomicMax(int *p, int v) { int o = *p; if (v > o) *p = v; return o; }
 inline unsigned atomicOr(unsigned *p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned atomicAnd(unsigned *p, unsigned v) { return __atomic_fetch_and(p, v, __ATOMIC_SEQ_CST); }
 inline int atomicExch(int *p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
 inline unsigned long long atomicMin(unsigned long long *p, unsigned long long v) {
     unsigned long long old = __atomic_load_n(p, __ATOMIC_SEQ_CST);

@@ -127,6 +127,7 @@ int run3d(const real *cost, long long cost_qstride, real *T, int ny, int nx, int
     double slack[2] = {0.0, 0.0}; P.slack = slack; P.slack_frac = getenv("FMB_EMU_SLACK") ? atof(getenv("FMB_EMU_SLACK")) : 0.0;
     P.hop_frac = getenv("FMB_EMU_RING2") ? atof(getenv("FMB_EMU_RING2")) : 1.0;
     P.variant = getenv("FMB_EMU_VARIANT") ? atoi(getenv("FMB_EMU_VARIANT")) : 0;
+    P.enable = nullptr;
     using TL16 = fmb::Tile3D<real, 16>;
     const size_t smem_sweep = sizeof(real) * (TL16::T_ELEMS + TL16::C_ELEMS + 8) + 32 * sizeof(unsigned) + 4 * sizeof(int);
     emu::launch(2, 64, 0, [&] { fmb::init_fill3d_kernel<real>(P, (int)ring.size()); });
