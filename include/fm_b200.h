@@ -103,7 +103,9 @@ typedef struct fmb_options {
     int32_t ring2;        /* 2D sweep engine, local causal order: also wait for a queued / running tile of the SECOND ring whose priority
                              lies more than this many percent of one tile crossing below mine (0 = default: 200 in 2D, off in 3D; -1 = off) */
     int32_t variant;      /* sweep engines: bit 0 = straight-line sweep step (predication, no vote / branches), bit 1 (2D) = the cell's current value
-                             is re-read right before the store (0 = default: 3 in 2D, 1 in 3D; -1 = the branching step) */
+                             is re-read right before the store, bit 3 (3D) = octant rule: a cell is evaluated only by the sweep whose upwind side carries
+                             its lower neighbour on every axis, sweeps without such a cell skip the round (36 -> 12 evaluations per cell, +10 % time)
+                             (0 = default: 3 in 2D, 1 in 3D; -1 = the branching step) */
 } fmb_options;
 void fmb_get_options(fmb_options *out);
 int fmb_set_options(const fmb_options *in);

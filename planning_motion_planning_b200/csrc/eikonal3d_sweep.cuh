@@ -204,6 +204,14 @@ __global__ void __launch_bounds__(256) solve3d_sweep_kernel(Problem3D<real> P) {
         const int dvx = sx > 0 ? PZ : -PZ, dvy = sy > 0 ? PS : -PS;      // towards the sweep-downwind column
         int steps = 0, round = 0;
         long long t_rounds = 0;
+        // Octant rule (variant bit 3).  With the loose rule "a sweep-upwind neighbour lies below me" seven of the eight
+        // sweeps re-evaluate nearly every cell to no effect, and with four sweep warps per scheduler those evaluations are
+        // what a step costs.  A sweep is the right one for a cell when, on EVERY axis, the lower of the cell's two
+        // neighbours lies on the sweep's upwind side (ties, incl. two +inf neighbours, go to the positive orientation):
+        // then the sweep's own chain carries every input of the cell's update.  Each cell is evaluated by one sweep per
+        // round; the others skip the step after one vote.  (The check passes ignore the rule: it costs rounds at worst.)
+        const bool octant = (P.variant & 8) != 0;
+        auto ax_ok = [](real up, real dw, int sgn) -> bool { return up < dw || (up == dw && sgn > 0); };
         for (;;) {      // continuation loop: one pass per (re-)activation served in place
             const long long tr0 = clock64();
             for (;; ++round) {
@@ -250,6 +258,31 @@ __global__ void __launch_bounds__(256) solve3d_sweep_kernel(Problem3D<real> P) {
                 if (steps > P.step_cap) break;
                 ++n_rounds;
 
+                // ---- octant gate: which of the eight sweeps have any cell to evaluate?  One pass of compares (no update):
+                // a cell belongs to the sweep whose upwind side carries the lower neighbour on every axis, if any neighbour
+                // lies below it.  A tile far from the source holds one to three octants; the other sweep warps skip the
+                // round instead of competing for issue slots (eight warps x ~200 instructions per step otherwise).
+                if (octant) {
+                    if (tid == 0) sCtl[2] = 0;
+                    __syncthreads();
+                    const int col = tid >> 3, zb = 2 * (tid & 7);
+                    const real *p = sT + TL::at(col >> 3, col & 7, zb);
+                    const real *pc = sC + col * PZ + zb;
+                    unsigned om = 0;
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const real cur = p[k], zm = p[k - 1], zp = p[k + 1], xm = p[k - PZ], xp = p[k + PZ], ym = p[k - PS], yp = p[k + PS];
+                        const real lz = zm < zp ? zm : zp, lxv = xm < xp ? xm : xp, lyv = ym < yp ? ym : yp;
+                        if ((lz < cur || lxv < cur || lyv < cur) && pc[k] < INF)
+                            om |= 1u << ((zp < zm ? 1 : 0) | (xp < xm ? 2 : 0) | (yp < ym ? 4 : 0));
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) om |= __shfl_xor_sync(FULL, om, o);
+                    if (lane == 0 && om) atomicOr(reinterpret_cast<unsigned *>(&sCtl[2]), om);
+                    __syncthreads();
+                    if (!((sCtl[2] >> warp) & 1)) { __syncthreads(); steps += NSTEP; continue; }
+                }
+
                 // ---- one sweep per warp.  Lane (ly, lx) relaxes cell kz = d - ly - lx of its column at step d.
                 int kz = -ly - lx;
                 real res = colT[sz > 0 ? -1 : TZ];             // before my first cell: the z halo
@@ -273,7 +306,8 @@ __global__ void __launch_bounds__(256) solve3d_sweep_kernel(Problem3D<real> P) {
                         real upy = __shfl_up_sync(FULL, res, 8);
                         if (lx == 0) upx = upx0;
                         if (ly == 0) upy = upy0;
-                        const bool go = valid && (res < cur || upx < cur || upy < cur) && c < INF;
+                        const bool go = valid && (res < cur || upx < cur || upy < cur) && c < INF &&
+                                        (!octant || (ax_ok(res, dwz, sz) && ax_ok(upx, dwx, sx) && ax_ok(upy, dwy, sy)));
                         const real v = solve3d_update_warp<real, EXACT>(upx < dwx ? upx : dwx, upy < dwy ? upy : dwy, res < dwz ? res : dwz, c, go);
                         const bool acc = go && v != cur && v <= num<real>::mul(cur, UP);
                         const real now = colT[z];
@@ -296,9 +330,10 @@ __global__ void __launch_bounds__(256) solve3d_sweep_kernel(Problem3D<real> P) {
                     real upy = __shfl_up_sync(FULL, res, 8);
                     if (lx == 0) upx = upx0;
                     if (ly == 0) upy = upy0;
-                    const bool go = valid && (res < cur || upx < cur || upy < cur) && c < INF;
+                    const bool go = valid && (res < cur || upx < cur || upy < cur) && c < INF &&
+                                    (!octant || (ax_ok(res, dwz, sz) && ax_ok(upx, dwx, sx) && ax_ok(upy, dwy, sy)));
                     real out = cur;
-                    if (hot || __any_sync(FULL, go)) {
+                    if ((hot && !octant) || __any_sync(FULL, go)) {
                         const real v = solve3d_update_warp<real, EXACT>(upx < dwx ? upx : dwx, upy < dwy ? upy : dwy, res < dwz ? res : dwz, c, go);
                         if (go) {
                             ++my_evals;

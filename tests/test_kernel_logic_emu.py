@@ -380,7 +380,7 @@ def test_update3d_branch_free_form_is_bitwise_the_branching_form():
                        sl.ctypes.data_as(emu.ip))
         assert np.array_equal(a.view(np.uint64)[sl == 0], b.view(np.uint64)[sl == 0])
         assert sl.sum() == 0
-        if exact:
+        if exact == 1:
             some = ~np.all(np.isinf(t[:5000, :3]), axis=1)           # all-inf: the reference raises, the device returns inf
             ref = np.array([O.solve3d(*row) for row in t[:5000]])
             assert np.array_equal(ref.view(np.uint64)[some], a[:5000].view(np.uint64)[some])
@@ -422,3 +422,13 @@ def test_solve2d_warp_sweep_engine_for_batches(mode, monkeypatch):
     assert rel_err(T[0], O.computeTmap(c, [10, 10])) < TOL64
     T32, _ = emu.solve2d_cta(c.astype(np.float32), [[10, 10]], R=0, nblocks=2, best_first=0)
     assert rel_err(T32[0].astype(np.float64), O.computeTmap(c.astype(np.float32).astype(np.float64), [10, 10])) < TOL32
+
+
+def test_solve3d_sweep_engine_octant_rule(monkeypatch):
+    """variant bit 3: every cell is evaluated by the one sweep whose upwind side carries its lower neighbours, sweeps without
+    such a cell skip the round (12 instead of 36 evaluations per cell on the bench volume): same field."""
+    monkeypatch.setenv("FMB_EMU_VARIANT", "9")
+    c = rand_map((20, 20, 20), 5)
+    c[8:10, 3:15, 3:15] = np.inf
+    T, st = emu.solve3d(c, [[4, 4, 4]], tz=0, nblocks=3)
+    assert rel_err(T[0], O.computeTmap3D(c, [4, 4, 4])) < TOL64

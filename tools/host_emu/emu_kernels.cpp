@@ -239,7 +239,7 @@ void emu_update3d(const double *t, long long n, int exact, double *out_sel, doub
     for (long long i = 0; i < n; ++i) {
         bool sl = false;
         const double *a = t + 4 * i;
-        if (exact) { out_sel[i] = fmb::solve3d_update_sel<true>(a[0], a[1], a[2], a[3], sl); out_ref[i] = fmb::solve3d_update_exact(a[0], a[1], a[2], a[3]); }
+        if (exact == 1) { out_sel[i] = fmb::solve3d_update_sel<true>(a[0], a[1], a[2], a[3], sl); out_ref[i] = fmb::solve3d_update_exact(a[0], a[1], a[2], a[3]); }
         else { out_sel[i] = fmb::solve3d_update_sel<false>(a[0], a[1], a[2], a[3], sl); out_ref[i] = fmb::solve3d_update<double>(a[0], a[1], a[2], a[3]); }
         slow[i] = sl;
     }
