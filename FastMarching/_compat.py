@@ -2,6 +2,8 @@
 emulation of the reference's early-exit ("partial field") semantics."""
 from __future__ import annotations
 
+import weakref
+
 import numpy as np
 import torch
 
@@ -28,7 +30,8 @@ def device() -> torch.device:
 # that came from here is recognised as pinned on its way back in (getPathGDM on a field biComputeTmap returned) and
 # uploaded with one DMA.
 _STAGE = {}
-_STAGE_ELEMS = 4 << 20            # 32 MiB of float64 per staging buffer
+_STAGE_ELEMS = 2 << 20            # 16 MiB of float64 per staging buffer
+_STAGE_BUFS = 4
 
 
 def to_device(a: np.ndarray, dev: torch.device) -> torch.Tensor:
@@ -36,24 +39,21 @@ def to_device(a: np.ndarray, dev: torch.device) -> torch.Tensor:
     t = torch.from_numpy(a)
     if a.size < (1 << 18):
         return t.to(dev)
-    try:
-        if t.is_pinned():
-            return t.to(dev, non_blocking=True)
-    except RuntimeError:
-        pass
+    if _is_ours(a):                                     # a field this module returned: page-locked, one DMA
+        return t.to(dev, non_blocking=True)
     out = torch.empty(a.shape, dtype=torch.float64, device=dev)
     flat_src, flat_dst = t.reshape(-1), out.reshape(-1)
     key = dev.index
     if key not in _STAGE:
-        _STAGE[key] = ([torch.empty(_STAGE_ELEMS, dtype=torch.float64).pin_memory() for _ in range(2)],
-                       [torch.cuda.Event(), torch.cuda.Event()])
+        _STAGE[key] = ([torch.empty(_STAGE_ELEMS, dtype=torch.float64).pin_memory() for _ in range(_STAGE_BUFS)],
+                       [torch.cuda.Event() for _ in range(_STAGE_BUFS)])
     bufs, evs = _STAGE[key]
     n = flat_src.numel()
     stream = torch.cuda.current_stream(dev)
     for k, lo in enumerate(range(0, n, _STAGE_ELEMS)):
         hi = min(n, lo + _STAGE_ELEMS)
-        b = k & 1
-        if k >= 2:
+        b = k % len(bufs)
+        if k >= len(bufs):
             evs[b].synchronize()                       # the DMA that last read this staging buffer is done
         bufs[b][:hi - lo].copy_(flat_src[lo:hi])
         flat_dst[lo:hi].copy_(bufs[b][:hi - lo], non_blocking=True)
@@ -61,15 +61,44 @@ def to_device(a: np.ndarray, dev: torch.device) -> torch.Tensor:
     return out
 
 
+# Result arrays: page-locked memory from a small pool.  cudaHostAlloc of a 128 MiB field costs ~18 ms, more than the
+# solve; a buffer goes back to the pool when the NumPy array handed to the caller (and with it every view of it) is
+# garbage-collected, so a planner that calls in a loop allocates once.
+_POOL = {}                         # nbytes -> [pinned uint8 tensors]
+_POOL_KEEP = 4
+_OURS = {}                         # id(array handed out) -> weakref to it
+
+
+def _is_ours(a: np.ndarray) -> bool:
+    base = a
+    while isinstance(base.base, np.ndarray):
+        base = base.base
+    r = _OURS.get(id(base))
+    return r is not None and r() is base
+
+
+def _give_back(key: int, nbytes: int, buf: torch.Tensor):
+    _OURS.pop(key, None)
+    free = _POOL.setdefault(nbytes, [])
+    if len(free) < _POOL_KEEP:
+        free.append(buf)
+
+
 def to_host(t: torch.Tensor) -> np.ndarray:
     """Device tensor -> fresh NumPy array (page-locked memory for large fields, see above)."""
     t = t.contiguous()
     if t.numel() < (1 << 18):
         return t.cpu().numpy()
-    h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    nbytes = t.numel() * t.element_size()
+    free = _POOL.get(nbytes)
+    buf = free.pop() if free else torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    h = buf.view(t.dtype).view(t.shape)
     h.copy_(t, non_blocking=True)
     torch.cuda.current_stream(t.device).synchronize()
-    return h.numpy()
+    a = h.numpy()
+    _OURS[id(a)] = weakref.ref(a)
+    weakref.finalize(a, _give_back, id(a), nbytes, buf)
+    return a
 
 
 def as_c_field(a):

@@ -53,7 +53,7 @@ def parse():
     ap.add_argument("--batch-queries", type=int, default=4096, help="512^2 queries per GPU in the batched section")
     ap.add_argument("--no-3d", action="store_true", help="skip the 3D (arm-workspace volume) section")
     ap.add_argument("--no-costmap", action="store_true", help="skip the cost-map construction section")
-    ap.add_argument("--inflight", type=int, default=3, help="independent queries solved concurrently per GPU (own stream each)")
+    ap.add_argument("--inflight", type=int, default=4, help="independent queries solved concurrently per GPU (own stream each)")
     ap.add_argument("--size3d", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -385,6 +385,8 @@ def own_arm(args):
     for _ in range(max(W, 3)):
         out, cnt, st = step_resident()
         stats = engine.finish(dev)
+    # NF solves share the GPU: each persistent grid takes 1/NF of the resident CTA slots (fmb_options.concurrent_solves)
+    _capi.set_options(concurrent_solves=NF)
     run_resident(2 * NF)
     torch.cuda.synchronize()
     for f in range(NF):
@@ -411,6 +413,7 @@ def own_arm(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t_ms = float(tt[0])
     value = world * cells * K / (t_ms * 1e-3)
+    _capi.set_options(concurrent_solves=0)                 # one solve alone from here on: the default grid
 
     # ---- per-kernel durations (library CUDA events around the persistent kernel), K more steps
     k_ms, i_ms, tr_ms = [], [], []
@@ -510,6 +513,7 @@ def own_arm(args):
             st_all = st_all or r
         return st_all
 
+    _capi.set_options(concurrent_solves=NF)
     run_e2e(2 * NF)
     finish_lanes()
     sampler2 = ClockSampler(local if os.environ.get("CUDA_VISIBLE_DEVICES") is None else 0)
@@ -526,6 +530,7 @@ def own_arm(args):
                   "reasons": sorted(set(clocks["reasons"]) | set(clocks2["reasons"])), "samples": len(allm),
                   "samples_resident_region": clocks["samples"], "samples_e2e_region": clocks2["samples"]}
     finish_lanes()
+    _capi.set_options(concurrent_solves=0)
     if world > 1:
         tt = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)

@@ -80,7 +80,8 @@ typedef struct fmb_stats {
  * environment variables only give the INITIAL values, read once at first use).  0 / -1 = automatic. */
 typedef struct fmb_options {
     int32_t engine2d;     /* 0 auto, 1 warp-per-tile armed-cell visits (round 1), 2 CTA-per-tile Jacobi visits, 3 four-warp sweep visits,
-                             4 / 5 warp-per-tile sweep visits for batches (costs staged in shared memory / read from global) */
+                             4 / 5 warp-per-tile sweep visits for batches (costs staged in shared memory / read from global),
+                             6 = 1 without the shared-memory cost tile (best-first batches: more resident warps; their default) */
     int32_t cta_cells;    /* cells per thread of the CTA engine: 0 auto, 1, 2 or 4 */
     int32_t tile_w2d;     /* tile width of the warp engine: 16 or 32 */
     int32_t tile_z3d;     /* 3D tile depth: 16 or 32 */
@@ -106,6 +107,10 @@ typedef struct fmb_options {
                              is re-read right before the store, bit 3 (3D) = octant rule: a cell is evaluated only by the sweep whose upwind side carries
                              its lower neighbour on every axis, sweeps without such a cell skip the round (36 -> 12 evaluations per cell, +10 % time)
                              (0 = default: 3 in 2D, 1 in 3D; -1 = the branching step) */
+    int32_t concurrent_solves; /* 2D sweep engine, one map per solve: how many solves the caller keeps in flight on this GPU (one stream
+                             each).  A solve in causal order is a chain of dependent visits that leaves most issue slots idle; its
+                             persistent grid then takes 1/n of the resident CTA slots, so all n solves are resident at once
+                             (0 / 1 = default: two CTAs per SM, the fastest grid for one solve alone) */
 } fmb_options;
 void fmb_get_options(fmb_options *out);
 int fmb_set_options(const fmb_options *in);

@@ -13,6 +13,8 @@ from typing import Callable, List, Optional, Sequence, Tuple
 
 import numpy as np
 
+FIRST_PASS_CROSSINGS = 4      # path slab of the first tracing pass, in crossings of the map (solve_chunk_gpu)
+
 
 def shard_bounds(n_items: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous block partition: ranks < n % world get one extra item."""
@@ -61,14 +63,41 @@ def solve_chunk_gpu(cost, goals, starts, tau: float = 0.5):
     c = c.to(dev, non_blocking=True)
     n = len(goals)
     T = engine.solve2d(c, np.asarray(goals, dtype=np.int32), nq=n, sync=False)
-    out, cnt, st = engine.trace2d(T, np.asarray(starts, dtype=np.float64), np.asarray(goals, dtype=np.float64), tau)
+    # Path slabs: the reference's step cap (round(15000 / tau) = 30000 steps) would make every query's slab 480 KB -- 2 GB
+    # for 4096 queries.  The first pass gives every path room for four crossings of the map; the few paths that use up
+    # that room (they ran into the smaller cap, not into the goal) are traced again with the reference's own cap.
+    full_steps = int(round(15000 / tau))
+    rows, cols = T.shape[-2:]
+    first_steps = min(full_steps, int(FIRST_PASS_CROSSINGS * (rows + cols) / tau) + 64)
+    init_h, end_h = np.asarray(starts, dtype=np.float64), np.asarray(goals, dtype=np.float64)
+    out, cnt, st = engine.trace2d(T, init_h, end_h, tau, max_steps=first_steps)
     engine.finish(dev)
-    off = torch.cumsum(cnt.to(torch.int64), 0) - cnt.to(torch.int64)
     cnt_h = cnt.cpu().numpy()
+    redo = np.nonzero(cnt_h >= first_steps + 2)[0] if first_steps < full_steps else np.zeros(0, dtype=np.int64)
+    extra = None
+    if len(redo):
+        extra = engine.trace2d(T, init_h[redo], end_h[redo], tau, field_of_path=redo.astype(np.int32), max_steps=full_steps)
+        cnt[torch.from_numpy(redo).to(dev)] = 0                   # packed separately below
+        cnt_h = cnt.cpu().numpy()
+    off = torch.cumsum(cnt.to(torch.int64), 0) - cnt.to(torch.int64)
     total = int(cnt_h.sum())
     packed = torch.empty((max(total, 1), 2), dtype=torch.float64, device=dev)
     _capi.check(_capi.lib().fmb_path_pack_f64(out.data_ptr(), cnt.data_ptr(), off.data_ptr(), out.shape[1], n, 2, 1.0, 0.0,
                                               packed.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    if extra is not None:
+        # splice the re-traced paths back in, in query order
+        flat, st_h = packed[:total].cpu().numpy(), st.cpu().numpy()
+        e_out, e_cnt, e_st = (t.cpu().numpy() for t in extra)
+        ends = np.cumsum(cnt_h)
+        pieces, counts = [], cnt_h.copy()
+        where = {int(q): k for k, q in enumerate(redo)}
+        for q in range(n):
+            if q in where:
+                k = where[q]
+                pieces.append(e_out[k, :e_cnt[k]]); counts[q] = e_cnt[k]; st_h[q] = e_st[k]
+            else:
+                pieces.append(flat[ends[q] - cnt_h[q]:ends[q]])
+        return PackedPaths(np.concatenate(pieces) if pieces else np.zeros((0, 2)), counts, st_h)
     return PackedPaths(packed[:total].cpu().numpy(), cnt_h, st.cpu().numpy())
 
 

@@ -215,8 +215,14 @@ __global__ void activate_rows2d_kernel(Problem2D<real> P, int activate) {
 //               the QUEUED tile of q with the lowest priority (smallest value that activated
 //               it).  Per-query best-first order cuts re-visits several-fold when many
 //               independent queries share the GPU (batched planning).
-template <typename real, int TW, int WARPS, bool BEST>
-__global__ void __launch_bounds__(WARPS * 32) solve2d_kernel(Problem2D<real> P) {
+#ifndef FMB_CG_MINB
+#define FMB_CG_MINB 5
+#endif
+// CG = true : the cost tile is NOT staged in shared memory; the relaxation reads the cost of its cell from global memory
+//              (L1-cached, the tile is touched once while its finite-cost masks are built).  Halves the shared memory
+//              of a tile in flight, i.e. more resident warps for the latency-bound batch regime.
+template <typename real, int TW, int WARPS, bool BEST, bool CG = false>
+__global__ void __launch_bounds__(WARPS * 32, CG ? FMB_CG_MINB : 0) solve2d_kernel(Problem2D<real> P) {
     using TL = Tile2D<real, TW>;
     constexpr int PT = TL::PT;
     constexpr unsigned ROWMASK = (TW == 32) ? 0xffffffffu : ((1u << TW) - 1u);
@@ -225,8 +231,8 @@ __global__ void __launch_bounds__(WARPS * 32) solve2d_kernel(Problem2D<real> P) 
     constexpr int NIT_C = TILE_H * TW / 32;
     FMB_DYN_SMEM(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    real *sT = reinterpret_cast<real *>(smem_raw) + (size_t)warp * TL::WARP_ELEMS;
-    real *sC = sT + TL::T_ELEMS;
+    real *sT = reinterpret_cast<real *>(smem_raw) + (size_t)warp * (CG ? TL::T_ELEMS : TL::WARP_ELEMS);
+    real *sC = sT + TL::T_ELEMS;            // (unused when CG)
     const real INF = num<real>::inf();
     const int tiles_per_q = P.ntx * P.nty;
     const unsigned long long PRIO_INF = 0x7ff0000000000000ULL;
@@ -354,17 +360,35 @@ __global__ void __launch_bounds__(WARPS * 32) solve2d_kernel(Problem2D<real> P) 
                     const int row = c / CPR, col = (c % CPR) * EPC;
                     cp_async16_cg(&sT[row * PT + 2 + col], &Tq[(long long)(y0 - 1 + row) * P.T_pitch + x0 + col]);
                 }
+                if (!CG) {
 #pragma unroll
-                for (int c = lane; c < TILE_H * CPR; c += 32) {
-                    const int row = c / CPR, col = (c % CPR) * EPC;
-                    cp_async16_cg(&sC[row * PT + col], &cq[(long long)(y0 + row) * P.cost_pitch + x0 + col]);
-                }
-                cp_async_wait_all();
-                __syncwarp();
+                    for (int c = lane; c < TILE_H * CPR; c += 32) {
+                        const int row = c / CPR, col = (c % CPR) * EPC;
+                        cp_async16_cg(&sC[row * PT + col], &cq[(long long)(y0 + row) * P.cost_pitch + x0 + col]);
+                    }
+                    cp_async_wait_all();
+                    __syncwarp();
 #pragma unroll 4
-                for (int j = 0; j < TILE_H; ++j) {
-                    const unsigned bal = __ballot_sync(FULL, lane < TW && sC[j * PT + (lane < TW ? lane : 0)] < INF);
-                    if (lane == j) cmask = bal;
+                    for (int j = 0; j < TILE_H; ++j) {
+                        const unsigned bal = __ballot_sync(FULL, lane < TW && sC[j * PT + (lane < TW ? lane : 0)] < INF);
+                        if (lane == j) cmask = bal;
+                    }
+                } else {
+                    // one coalesced row per load, eight rows in flight; the lines stay in L1 for the relaxation
+#pragma unroll
+                    for (int j0 = 0; j0 < TILE_H; j0 += 8) {
+                        real cv[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+                            cv[u] = lane < TW ? __ldg(&cq[(long long)(y0 + j0 + u) * P.cost_pitch + x0 + lane]) : INF;
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const unsigned bal = __ballot_sync(FULL, cv[u] < INF);
+                            if (lane == j0 + u) cmask = bal;
+                        }
+                    }
+                    cp_async_wait_all();
+                    __syncwarp();
                 }
             } else {
                 constexpr int BT = 9;
@@ -400,7 +424,7 @@ __global__ void __launch_bounds__(WARPS * 32) solve2d_kernel(Problem2D<real> P) 
 #pragma unroll
                     for (int u = 0; u < BC; ++u) {
                         const int idx = (b0 + u) * 32 + lane;
-                        sC[(idx / TW) * PT + idx % TW] = c[u];
+                        if (!CG) sC[(idx / TW) * PT + idx % TW] = c[u];
                         const unsigned bal = __ballot_sync(FULL, c[u] < INF);
 #pragma unroll
                         for (int sft = 0; sft < ROWS_PER_IT; ++sft)
@@ -415,7 +439,7 @@ __global__ void __launch_bounds__(WARPS * 32) solve2d_kernel(Problem2D<real> P) 
 
         // ---- arm the cells next to a lower halo value -------------------------
         real *rowT = sT + (lane + 1) * PT + 2;      // rowT[k] = T(row lane, col k); rowT[-1], rowT[TW] halos
-        const real *rowC = sC + lane * PT;
+        const real *rowC = CG ? cq + (long long)(y0 + lane) * P.cost_pitch + x0 : sC + lane * PT;   // only cells of cmask are read
         unsigned mask = 0;
         if (rowT[-1] < rowT[0]) mask |= 1u;
         if (rowT[TW] < rowT[TW - 1]) mask |= 1u << (TW - 1);
@@ -461,8 +485,9 @@ __global__ void __launch_bounds__(WARPS * 32) solve2d_kernel(Problem2D<real> P) 
                 const unsigned bit = 1u << k;
                 mask &= ~bit;
                 real *p = rowT + k;
+                const real ck = CG ? __ldg(rowC + k) : rowC[k];
                 const real l = p[-1], r = p[1], u = p[-PT], d = p[PT], cur = p[0];
-                const real v = eikonal_update<real>(l < r ? l : r, u < d ? u : d, rowC[k]);
+                const real v = eikonal_update<real>(l < r ? l : r, u < d ? u : d, ck);
                 // Lower values always win.  A value up to a few ulp HIGHER also replaces the stored one: a cell
                 // keeps the minimum over its history of updates, rounding is not monotone, and without this a
                 // cell can stay an ulp below update(final neighbours) -- the reference's field is an exact fixed

@@ -92,8 +92,12 @@ struct TmaMaps2D { int unused; };
 #else
 #define FMB_TMA_PARAM , TmaMaps2D tmaps = TmaMaps2D(), int use_tma = 0
 #endif
+// resident CTAs per SM the register allocation is held to (3: 168 registers, 4: 128)
+#ifndef FMB_SWEEP2D_MINB
+#define FMB_SWEEP2D_MINB 3
+#endif
 template <typename real, bool BEST>
-__global__ void __launch_bounds__(128, 3) solve2d_sweep_kernel(Problem2D<real> P FMB_TMA_PARAM) {
+__global__ void __launch_bounds__(128, FMB_SWEEP2D_MINB) solve2d_sweep_kernel(Problem2D<real> P FMB_TMA_PARAM) {
     constexpr int PT = Sweep2DSmem::PT, PC = Sweep2DSmem::PC, TW = 32, NSTEP = TILE_H + TW - 1;
 #ifndef FMB_HOST_EMU
     extern __shared__ __align__(1024) unsigned char smem_raw[];

@@ -108,6 +108,7 @@ void opt_defaults_locked() {
     g_opt.tma = env_int("FMB_TMA", -1);
     g_opt.ring2 = env_int("FMB_RING2", 0);
     g_opt.variant = env_int("FMB_VARIANT", 0);
+    g_opt.concurrent_solves = env_int("FMB_CONCURRENT_SOLVES", 0);
     g_opt_init = true;
 }
 fmb_options opt() {
@@ -174,11 +175,11 @@ void launch_init2d(const fmb::Problem2D<real> &P, const WsLayout &L, cudaStream_
     fmb::init_seed2d_kernel<real, TW><<<(P.nq + 127) / 128, 128, 0, st>>>(P);     // out-of-range seed = no seed
 }
 
-template <typename real, int TW, bool BEST>
+template <typename real, int TW, bool BEST, bool CG = false>
 int launch_solve2d(fmb::Problem2D<real> P, const WsLayout &L, cudaStream_t st, int resume_activate = -1) {
     using TL = fmb::Tile2D<real, TW>;
-    const size_t smem = TL::WARP_BYTES * WARPS;
-    auto kern = fmb::solve2d_kernel<real, TW, WARPS, BEST>;
+    const size_t smem = (CG ? sizeof(real) * TL::T_ELEMS : TL::WARP_BYTES) * WARPS;
+    auto kern = fmb::solve2d_kernel<real, TW, WARPS, BEST, CG>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(solve2d)");
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem), "occupancy(solve2d)");
@@ -302,7 +303,14 @@ int launch_solve2d_sweep(fmb::Problem2D<real> P, const WsLayout &L, cudaStream_t
     // machine (measured 4096^2: 10.3 ms with 296 CTAs, 10.1 ms with 1036) and leave the other slots to concurrent
     // solves on other streams -- a persistent grid that fills every slot would serialise them.
     if (!P.best_first && P.windowed == 2 && O.max_blocks <= 0) {
-        const long long lean = (long long)2 * sm_count() * P.nq;
+        long long lean = (long long)2 * sm_count() * P.nq;
+        // n solves in flight on n streams (fmb_options.concurrent_solves): 1/n of the resident slots each, so that no
+        // solve waits for another one's persistent CTAs to retire (4096^2, 444 slots: 3 x 296 CTAs 5.2 ms per solve,
+        // 3 x 148 3.9 ms, 4 x 111 3.5 ms; one solve alone: 7.3 ms with 296 CTAs, 7.6 ms with 148)
+        if (O.concurrent_solves > 1) {
+            const long long share = (long long)per_sm * sm_count() / O.concurrent_solves;
+            if (share >= 1 && share < lean) lean = share;
+        }
         if (blocks > lean) blocks = lean;
     }
     if (blocks < 1) blocks = 1;
@@ -369,9 +377,13 @@ int solve2d(const real *d_cost, int64_t cost_pitch, int64_t cost_qstride, real *
     const int best_first = resume_activate >= 0 ? 0 : (O.best_first >= 0 ? O.best_first : ((nq >= 8 && tiles_per_q32 <= 1024) ? 1 : 0));
     // Engine: the four-warp sweep visit (eikonal2d_sweep.cuh) where the solve is a chain of dependent visits (one map,
     // a few maps); the warp-per-tile visit (eikonal2d.cuh) for batches, where throughput per warp counts (measured
-    // 4096 x 512^2: 64 ms against 142 ms).
-    const int engine = O.engine2d > 0 ? O.engine2d : (best_first ? 1 : 3);
-    int tw = engine >= 2 ? 32 : O.tile_w2d;       // engines 2-5 use 32 x 32 tiles
+    // 4096 x 512^2: 64 ms against 142 ms), without the shared-memory cost tile (engine 6: 20 resident warps per SM
+    // instead of 12, 55 ms).
+    int engine = O.engine2d > 0 ? O.engine2d : (best_first ? 6 : 3);
+    // engine 6 = engine 1 with the cost read from global memory instead of a shared-memory tile (best-first batches)
+    const bool cost_global = engine == 6 && best_first;
+    if (engine == 6) engine = 1;
+    int tw = (engine >= 2 || cost_global) ? 32 : O.tile_w2d;       // engines 2-6 use 32 x 32 tiles
     if (tw != 16 && tw != 32) return fail(FMB_E_INVALID, "tile_w2d must be 16 or 32%s");
     const long long ntiles = tiles2d(rows, cols, tw) * nq;
     if (ntiles >= (1LL << 30)) return fail(FMB_E_INVALID, "too many tiles for one launch%s");
@@ -441,6 +453,7 @@ int solve2d(const real *d_cost, int64_t cost_pitch, int64_t cost_qstride, real *
     }
     if (P.best_first) {
         if (tw == 16) return launch_solve2d<real, 16, true>(P, L, st);
+        if (cost_global) return launch_solve2d<real, 32, true, true>(P, L, st);
         return launch_solve2d<real, 32, true>(P, L, st);
     }
     if (tw == 16) return launch_solve2d<real, 16, false>(P, L, st, resume_activate);

@@ -74,4 +74,5 @@ def fmb_opts():
 
 # 2D engines of the library: name -> fmb_options fields
 ENGINES_2D = {"sweep": dict(engine2d=3), "cta1": dict(engine2d=2, cta_cells=1), "cta2": dict(engine2d=2, cta_cells=2),
-              "cta4": dict(engine2d=2, cta_cells=4), "warp32": dict(engine2d=1, tile_w2d=32), "warp16": dict(engine2d=1, tile_w2d=16)}
+              "cta4": dict(engine2d=2, cta_cells=4), "warp32": dict(engine2d=1, tile_w2d=32), "warp16": dict(engine2d=1, tile_w2d=16),
+              "warp32g": dict(engine2d=6)}

@@ -182,7 +182,7 @@ def test_solve2d_differential_random_obstacles(eng, seed):
     assert rel_err(T, O.computeTmap(c, [int(gx), int(gy)])) < TOL64
 
 
-@pytest.mark.parametrize("engine", ["sweep", "cta2", "warp32"])
+@pytest.mark.parametrize("engine", ["sweep", "cta2", "warp32", "warp32g"])
 def test_best_first_and_fifo_agree(eng, engine, fmb_opts):
     """The two work orders of the persistent kernel reach the same fixed point."""
     import torch
@@ -955,3 +955,56 @@ def test_c_abi_alone_reproduces_bicomputetmap_and_the_3d_early_exit():
     _capi.check(L.fmb_finish(ws3.data_ptr(), ws3.numel(), st, None))
     ref3 = O.computeTmap3D(c3, g3, s3)
     assert int(np.isfinite(ref3).sum()) == 9830 and rel_err(T3.cpu().numpy(), ref3) < TOL64
+
+
+def test_batch_long_paths_are_retraced_with_the_reference_cap(eng, monkeypatch):
+    """batch.solve_chunk_gpu gives every path room for a few crossings of the map and re-traces the ones that use it up
+    with the reference's own 30000-step cap: a serpentine map with a long path next to short ones (room cut to one
+    crossing here so that the long path needs the second pass)."""
+    from oracle import oracle as O
+    from planning_motion_planning_b200 import batch
+    monkeypatch.setattr(batch, "FIRST_PASS_CROSSINGS", 1)
+    n = 64
+    c = np.ones((n, n))
+    c[0, :] = c[-1, :] = c[:, 0] = c[:, -1] = np.inf
+    for k, y in enumerate(range(4, n - 4, 4)):                    # walls with a gap alternating left / right
+        c[y, 1:n - 1] = np.inf
+        c[y, (n - 4) if k % 2 == 0 else 2:(n - 2) if k % 2 == 0 else 4] = 1.0
+    goals = [[2, 2], [2, 2], [40, 2]]
+    starts = [[n - 3, n - 3], [10, 2], [3, n - 3]]
+    lo, res = batch.solve_queries(c, goals, starts, chunk=8)
+    assert lo == 0 and len(res) == 3
+    long_rows = 0
+    for (p, st), g, s in zip(res, goals, starts):
+        T = O.computeTmap(c, g)
+        ref, rst = O.getPathGDM(T, np.array(s, dtype=np.float64), np.array(g, dtype=np.float64), 0.5, return_status=True)
+        assert st == rst and p.shape == ref.shape and np.abs(p - ref).max() < TOLP
+        long_rows = max(long_rows, len(p))
+    assert long_rows > 2 * (n + n) + 66          # at least one path exceeded the first-pass room
+
+
+def test_batch_default_engine_reads_costs_from_global_memory(eng, fmb_opts):
+    """Best-first batches run the armed-cell visit WITHOUT the shared-memory cost tile by default (engine2d = 6, 20 resident
+    warps per SM): ragged map with obstacles, per-query cost maps, fp64 against the oracle and fp32 within 1e-4."""
+    import torch
+    from oracle import oracle as O
+    from planning_motion_planning_b200 import _capi
+    assert _capi.get_options()["engine2d"] == 0
+    rng = np.random.default_rng(21)
+    shape = (257, 300)
+    cs = 1.0 + 4.0 * rng.random((12,) + shape)
+    cs[rng.random(cs.shape) < 0.06] = np.inf
+    goals = [[int(rng.integers(1, shape[1] - 1)), int(rng.integers(1, shape[0] - 1))] for _ in range(12)]
+    for q, g in enumerate(goals):
+        cs[q, g[1], g[0]] = 1.0
+    T = eng.solve2d(torch.from_numpy(cs).cuda(), goals).cpu().numpy()           # (nq, rows, cols) costs: one map per query
+    for q in (0, 5, 11):
+        assert rel_err(T[q], O.computeTmap(cs[q], goals[q])) < TOL64
+    Ts = eng.solve2d(torch.from_numpy(cs[0]).cuda(), goals).cpu().numpy()        # one shared map
+    for q in (1, 7):
+        c0 = cs[0].copy()
+        ref = O.computeTmap(c0, goals[q])
+        if np.isfinite(c0[goals[q][1], goals[q][0]]):
+            assert rel_err(Ts[q], ref) < TOL64
+    T32 = eng.solve2d(torch.from_numpy(cs[0].astype(np.float32)).cuda(), goals).cpu().numpy()
+    assert rel_err(T32[0].astype(np.float64), O.computeTmap(cs[0].astype(np.float32).astype(np.float64), goals[0])) < 1e-4

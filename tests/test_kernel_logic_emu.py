@@ -432,3 +432,21 @@ def test_solve3d_sweep_engine_octant_rule(monkeypatch):
     c[8:10, 3:15, 3:15] = np.inf
     T, st = emu.solve3d(c, [[4, 4, 4]], tz=0, nblocks=3)
     assert rel_err(T[0], O.computeTmap3D(c, [4, 4, 4])) < TOL64
+
+
+def test_warp_engine_with_costs_from_global_memory(monkeypatch):
+    """engine2d = 6 (the default of best-first batches): the armed-cell visit without the shared-memory cost tile -- same
+    fields as the oracle on interior, edge and ragged tiles, fp64 and fp32."""
+    monkeypatch.setenv("FMB_BEST_FIRST", "1")
+    monkeypatch.setenv("FMB_COST_GLOBAL", "1")
+    rng = np.random.default_rng(11)
+    for shape, goals in (((100, 130), [[25, 25], [120, 90], [64, 3]]), ((97, 65), [[1, 1], [60, 90]]), ((33, 31), [[15, 16]])):
+        c = 1.0 + 4.0 * rng.random(shape)
+        c[rng.random(shape) < 0.08] = np.inf
+        for g in goals:
+            c[g[1], g[0]] = 1.0
+        T, st = emu.solve2d(c, goals, nblocks=3)
+        for q, g in enumerate(goals):
+            assert rel_err(T[q], O.computeTmap(c, g)) < 1e-12
+        T32, _ = emu.solve2d(c.astype(np.float32), goals[:1], nblocks=2)
+        assert rel_err(T32[0].astype(np.float64), O.computeTmap(c.astype(np.float32).astype(np.float64), goals[0])) < 1e-4

@@ -50,7 +50,9 @@ int run2d(const real *cost, long long cost_qstride, real *T, int rows, int cols,
     P.lev_count = lev_count.data(); P.tile_level = tile_level.data(); P.win_hint = &win_hint; P.win_inv_delta = &win_inv_delta;
     emu::launch(2, 64, 0, [&] { fmb::init_fill2d_kernel<real>(P, (int)ring.size()); });
     emu::launch(1, 32 * ((nq + 31) / 32), 0, [&] { fmb::init_seed2d_kernel<real, TW>(P); });
-    if (P.best_first) emu::launch(nblocks, WARPS * 32, fmb::Tile2D<real, TW>::WARP_BYTES * WARPS, [&] { fmb::solve2d_kernel<real, TW, WARPS, true>(P); });
+    const bool cg = getenv("FMB_COST_GLOBAL") && atoi(getenv("FMB_COST_GLOBAL"));     // engine2d = 6: cost read from global memory
+    if (P.best_first && cg) emu::launch(nblocks, WARPS * 32, sizeof(real) * fmb::Tile2D<real, TW>::T_ELEMS * WARPS, [&] { fmb::solve2d_kernel<real, TW, WARPS, true, true>(P); });
+    else if (P.best_first) emu::launch(nblocks, WARPS * 32, fmb::Tile2D<real, TW>::WARP_BYTES * WARPS, [&] { fmb::solve2d_kernel<real, TW, WARPS, true>(P); });
     else emu::launch(nblocks, WARPS * 32, fmb::Tile2D<real, TW>::WARP_BYTES * WARPS, [&] { fmb::solve2d_kernel<real, TW, WARPS, false>(P); });
     if (stats) { stats[0] = ctl.visits; stats[1] = ctl.steps; stats[2] = ctl.evals; stats[3] = ctl.pushes; stats[4] = ctl.cells_written; }
     return ctl.abort ? ctl.abort : (ctl.pending != 0 ? -1 : 0);
