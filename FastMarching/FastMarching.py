@@ -49,7 +49,7 @@ def _device_map(costMap, nodes):
 
 
 def _to_numpy_field(Tt: torch.Tensor, swap: bool) -> np.ndarray:
-    a = _c.to_host(Tt)
+    a = _c.to_host(Tt, keep_device=True)
     return a.T if swap else a          # .T of a C array is F-ordered, like zeros_like() of the planner's view
 
 
@@ -97,13 +97,13 @@ def getPathGDM(totalCostMap, initWaypoint, endWaypoint, tau):
     init = np.asarray(initWaypoint, dtype=np.float64).reshape(-1)[:2]
     end = np.asarray(endWaypoint, dtype=np.float64).reshape(-1)[:2]
     dev = _c.device()
-    Td = _c.to_device(np.ascontiguousarray(c), dev)
-    if swap:
+
+    def run(Td):
         # unlike the solver, the tracer is NOT symmetric in x and y (the reference normalises dx
         # first and reuses it for dy, FastMarching.py:226-227), so an F-ordered field is put back
         # into [y, x] order on the device instead of tracing in swapped coordinates
-        Td = Td.T.contiguous()
-    out, count, status = engine.trace2d(Td, init[None, :], end[None, :], tau)
+        return engine.trace2d(Td.T.contiguous() if swap else Td, init[None, :], end[None, :], tau)
+    out, count, status = _c.trace_field(np.ascontiguousarray(c), dev, run)
     n, st = int(count[0]), int(status[0])
     _c.raise_trace(st)
     return out[0, :n].cpu().numpy()

@@ -36,7 +36,7 @@ def computeTmap(costMap, goal, start):
     # group of `start` (only that group decides which cells are accepted when it pops), replay of the first
     # rank[start] pops.  start == goal / outside / unreached: the full field (the goal is closed before the loop).
     T, info, ws = _c.solve3d_until(cd, g, s)
-    out = _c.to_host(T)                                 # synchronises
+    out = _c.to_host(T, keep_device=True)               # synchronises
     _c.finish(ws, dev)
     _c.check_info(info.tolist())
     return out
@@ -50,8 +50,7 @@ def getPathGDM(totalCostMap, initWaypoint, endWaypoint, tau):
     init = np.asarray(initWaypoint, dtype=np.float64).reshape(-1)[:3]
     end = np.asarray(endWaypoint, dtype=np.float64).reshape(-1)[:3]
     dev = _c.device()
-    Td = _c.to_device(Tn, dev)
-    out, count, status = engine.trace3d(Td, init[None, :], end[None, :], tau)
+    out, count, status = _c.trace_field(Tn, dev, lambda Td: engine.trace3d(Td, init[None, :], end[None, :], tau))
     n, st = int(count[0]), int(status[0])
     _c.raise_trace(st)
     return out[0, :n].cpu().numpy()

@@ -320,6 +320,10 @@ int fmb_costvolume_f64(const fmb_costvolume_desc *desc, double *d_cmap, double *
 int fmb_path_pack_f64(const double *d_paths, const int32_t *d_count, const int64_t *d_offsets, int64_t cap, int npaths, int dim,
                       double scale, double shift, double *d_out, void *stream);
 size_t fmb_workspace_bytes_pathpost(void);
+/* *d_flag = 1 when the two device arrays differ in any bit, else 0 (asynchronous).  The drop-in keeps the device copy
+ * of a field it returned; when the caller hands that array to getPathGDM (Coupled_motion_planner.py:1229-1230) the tracer
+ * starts on the copy while the array is uploaded again, and this check decides whether the path may be used. */
+int fmb_fields_differ_f64(const double *d_a, const double *d_b, int64_t n, int32_t *d_flag, void *stream);
 int fmb_path_stitch2d_f64(const double *d_pathS, const int32_t *d_countS, const double *d_pathG, const int32_t *d_countG,
                           int64_t cap, int npairs, double resolution, double *d_out, int32_t *d_count_out, void *stream);
 int fmb_path_post3d_f64(const double *d_paths, const int32_t *d_count, int64_t cap, int npaths, const double *scale3,

@@ -101,6 +101,7 @@ SIGNATURES = {
     "fmb_plan_batch2d_host": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _i32, _dbl, _i32, _dbl, _i32,
                                         C.POINTER(C.POINTER(FmbPlan2DResult))]),
     "fmb_plan2d_free": (None, [C.POINTER(FmbPlan2DResult)]),
+    "fmb_fields_differ_f64": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "fmb_workspace_bytes_costvolume": (_sz, [_i32, _i32, _i32]),
     "fmb_costvolume_f64": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _sz, _vp]),
 }

@@ -1008,3 +1008,81 @@ def test_batch_default_engine_reads_costs_from_global_memory(eng, fmb_opts):
             assert rel_err(Ts[q], ref) < TOL64
     T32 = eng.solve2d(torch.from_numpy(cs[0].astype(np.float32)).cuda(), goals).cpu().numpy()
     assert rel_err(T32[0].astype(np.float64), O.computeTmap(cs[0].astype(np.float32).astype(np.float64), goals[0])) < 1e-4
+
+
+@pytest.mark.parametrize("order", ["C", "F"])
+def test_dropin_tracer_reuses_the_device_field_only_if_unchanged(order):
+    """getPathGDM on an array computeTmap / biComputeTmap returned starts on the device copy the drop-in kept while the
+    array is uploaded again; the bitwise comparison of the two decides (fmb_fields_differ_f64).  Unchanged array: the
+    oracle's path.  Array changed in place by the caller (a wall of +inf across the old path, one value nudged by an
+    ulp): the oracle's path over the CHANGED array."""
+    import gc
+    import FastMarching.FastMarching as FM
+    from FastMarching import _compat as C
+    from oracle import oracle as O
+    from planning_motion_planning_b200 import synth
+    n = 640
+    c = synth.mars_costmap(n, 6)
+    goal = list(synth.free_cell_near(c, 80, 90)); start = list(synth.free_cell_near(c, 560, 500))
+    cm = np.asfortranarray(c.T).T if order == "C" else np.asfortranarray(c)       # same values, C- or F-ordered storage
+    T = FM.computeTmap(cm, goal, [-1, -1])
+    assert C._device_copy_of(T.T if order == "F" else T) is not None
+    Tref = O.computeTmap(c, goal)
+    assert rel_err(np.ascontiguousarray(T), Tref) < TOL64
+    s = np.array(start, dtype=np.float64)
+    before = dict(C.TRACE_STATS)
+    p = FM.getPathGDM(T, s, goal, 0.5)
+    ref = O.getPathGDM(np.ascontiguousarray(T), s, np.array(goal, dtype=np.float64), 0.5)
+    assert p.shape == ref.shape and np.abs(p - ref).max() < TOLP
+    assert C.TRACE_STATS["reused"] == before["reused"] + 1 and C.TRACE_STATS["retraced"] == before["retraced"]
+    # the caller edits the array in place: a wall with one gap far from the old path
+    mid = int(p[len(p) // 2, 1])
+    T[mid, :] = np.inf
+    T[mid, 5:8] = Tref[mid, 5:8]
+    p2 = FM.getPathGDM(T, s, goal, 0.5)
+    ref2, st2 = O.getPathGDM(np.ascontiguousarray(T), s, np.array(goal, dtype=np.float64), 0.5, return_status=True)
+    assert p2.shape == ref2.shape and (len(ref2) == 0 or np.abs(p2 - ref2).max() < TOLP)
+    assert p2.shape != p.shape or np.abs(p2 - p).max() > 1.0
+    assert C.TRACE_STATS["retraced"] == before["retraced"] + 1
+    # a one-ulp change anywhere is seen as well
+    T2 = FM.computeTmap(cm, goal, [-1, -1])
+    j, i = int(p[3, 1]), int(p[3, 0])
+    T2[j, i] = np.nextafter(T2[j, i], np.inf)
+    flag_before = C._device_copy_of(T2.T if order == "F" else T2)
+    assert flag_before is not None
+    p3 = FM.getPathGDM(T2, s, goal, 0.5)
+    ref3 = O.getPathGDM(np.ascontiguousarray(T2), s, np.array(goal, dtype=np.float64), 0.5)
+    assert p3.shape == ref3.shape and np.abs(p3 - ref3).max() < 1e-9
+    assert C.TRACE_STATS["retraced"] == before["retraced"] + 2
+    # the kept device copies are released with the host arrays
+    del T, T2, flag_before
+    gc.collect()
+    assert len(C._DEVCOPY) == 0
+
+
+def test_dropin_pagelocks_a_callers_array_on_reuse():
+    """A cost map that comes in a second time is page-locked in place and uploaded by one DMA from then on; every call
+    still uploads the CURRENT contents (an in-place edit between calls is seen); the registration ends with the array."""
+    import gc
+    import FastMarching.FastMarching as FM
+    from FastMarching import _compat as C
+    from oracle import oracle as O
+    from planning_motion_planning_b200 import synth
+    n = 640
+    c = synth.mars_costmap(n, 8)
+    goal = list(synth.free_cell_near(c, 500, 120))
+    n0 = len(C._REGISTERED)
+    T1 = FM.computeTmap(c, goal, [-1, -1])
+    assert len(C._REGISTERED) == n0
+    T2 = FM.computeTmap(c, goal, [-1, -1])                  # second sighting: registered
+    assert len(C._REGISTERED) == n0 + 1
+    ref = O.computeTmap(c, goal)
+    assert rel_err(T1, ref) < TOL64 and rel_err(T2, ref) < TOL64
+    c[300:340, 100:500] = np.inf                            # the caller edits its map in place
+    T3 = FM.computeTmap(c, goal, [-1, -1])
+    assert rel_err(T3, O.computeTmap(c, goal)) < TOL64 and not np.array_equal(np.isfinite(T3), np.isfinite(T2))
+    TG, TS, jn = FM.biComputeTmap(c, goal, list(synth.free_cell_near(c, 100, 560)))
+    assert np.isfinite(TG[jn[1], jn[0]]) and np.isfinite(TS[jn[1], jn[0]])
+    del c
+    gc.collect()
+    assert len(C._REGISTERED) == n0
