@@ -118,6 +118,9 @@ int fmb_set_options(const fmb_options *in);
 /* Self-test: counts (into *d_bad, zeroed by the caller) the inputs of d_x[0..n) inside the range of the library's
  * branch-free fp64 square root whose result differs in any bit from sqrt.rn.f64.  Must stay 0. */
 int fmb_debug_sqrt_check(const double *d_x, int64_t n, uint64_t *d_bad, void *stream);
+/* The same for the branch-free fp64 division of the tracer's fast step: d_bad2[0] += pairs (a, b) the fast form accepts
+ * whose quotient differs in any bit from div.rn.f64 (must stay 0), d_bad2[1] += accepted pairs (both zeroed by the caller). */
+int fmb_debug_div_check(const double *d_a, const double *d_b, int64_t n, uint64_t *d_bad2, void *stream);
 
 int fmb_version(void);
 const char *fmb_last_error(void);

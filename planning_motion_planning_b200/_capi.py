@@ -61,6 +61,7 @@ SIGNATURES = {
     "fmb_last_error": (C.c_char_p, []),
     "fmb_sm_count": (C.c_int, []),
     "fmb_debug_sqrt_check": (C.c_int, [_vp, _i64, _vp, _vp]),
+    "fmb_debug_div_check": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "fmb_get_options": (None, [C.POINTER(FmbOptions)]),
     "fmb_set_options": (C.c_int, [C.POINTER(FmbOptions)]),
     "fmb_workspace_bytes_2d": (_sz, [_i32, _i32, _i32]),

@@ -473,9 +473,29 @@ __global__ void sqrt_check_kernel(const double *x, long long n, unsigned long lo
     }
     if (mine) atomicAdd(bad, mine);
 }
+// bitwise comparison of the branch-free division with div.rn.f64; d_bad[1] counts the pairs the fast form accepts
+__global__ void div_check_kernel(const double *a, const double *b, long long n, unsigned long long *bad) {
+    unsigned long long mine = 0, accepted = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        bool ok = true;
+        const double q = fmb::ddiv_rn_fast(a[i], b[i], ok);
+        if (!ok) continue;
+        ++accepted;
+        if (__double_as_longlong(q) != __double_as_longlong(__ddiv_rn(a[i], b[i]))) ++mine;
+    }
+    if (mine) atomicAdd(bad, mine);
+    if (accepted) atomicAdd(bad + 1, accepted);
+}
 }  // namespace
 
 extern "C" {
+
+int fmb_debug_div_check(const double *d_a, const double *d_b, int64_t n, uint64_t *d_bad2, void *stream) {
+    if (!d_a || !d_b || !d_bad2 || n < 1) return fail(FMB_E_INVALID, "bad argument%s");
+    div_check_kernel<<<1184, 256, 0, (cudaStream_t)stream>>>(d_a, d_b, n, (unsigned long long *)d_bad2);
+    CK(cudaGetLastError(), "launch div_check");
+    return FMB_OK;
+}
 
 int fmb_debug_sqrt_check(const double *d_x, int64_t n, uint64_t *d_bad, void *stream) {
     if (!d_x || !d_bad || n < 1) return fail(FMB_E_INVALID, "bad argument%s");
@@ -571,7 +591,7 @@ int fmb_trace2d_f64(const double *d_T, int64_t T_pitch, int64_t T_qstride, int r
     A.field_of_path = d_field_of_path; A.init = d_init; A.end = d_end; A.tau = tau; A.max_steps = max_steps;
     A.out = d_out; A.cap = cap; A.count = d_count; A.status = d_status;
     constexpr int TW_ = 4;
-    fmb::trace2d_kernel<double, TW_><<<(npaths + TW_ - 1) / TW_, TW_ * 32, 0, (cudaStream_t)stream>>>(A);
+    fmb::trace2d_kernel<double, TW_><<<(npaths + TW_ - 1) / TW_, TW_ * 32, TW_ * fmb::TRACE2D_SMEM_PER_WARP, (cudaStream_t)stream>>>(A);
     CK(cudaGetLastError(), "launch trace2d");
     return FMB_OK;
 }

@@ -1086,3 +1086,35 @@ def test_dropin_pagelocks_a_callers_array_on_reuse():
     del c
     gc.collect()
     assert len(C._REGISTERED) == n0
+
+
+def test_branch_free_division_is_correctly_rounded(eng):
+    """ddiv_rn_fast (csrc/fm_common.cuh, the tracer's fast step) == div.rn.f64 bit for bit wherever it accepts its
+    operands: random mantissas over the accepted exponent range and beyond it, quotients next to 1 and to powers of two,
+    the tracer's own operand shapes (a gradient component over a hypotenuse), zeros, infinities and NaNs."""
+    import torch
+    from planning_motion_planning_b200 import _capi
+    g = torch.Generator(device="cuda").manual_seed(2)
+    n = 10_000_000
+    def rnd(lo, hi):
+        m = (torch.rand(n, dtype=torch.float64, device="cuda", generator=g) + 1.0)
+        e = torch.randint(lo, hi, (n,), device="cuda", generator=g).to(torch.float64)
+        sgn = torch.where(torch.rand(n, device="cuda", generator=g) < 0.5, -1.0, 1.0).to(torch.float64)
+        return sgn * m * torch.exp2(e)
+    cases = [(rnd(-520, 520), rnd(-520, 520)), (rnd(-1070, 1023), rnd(-1070, 1023)), (rnd(-3, 3), rnd(-3, 3))]
+    b = rnd(-2, 2).abs()
+    k = torch.randint(-3, 4, (n,), device="cuda", generator=g).to(torch.float64)
+    cases.append((b * (1.0 + k * 2.0 ** -52), b))                             # quotients within a few ulp of 1
+    dx, dy = rnd(-30, 1), rnd(-30, 1)
+    cases.append((dx, torch.sqrt(dx * dx + dy * dy)))                          # the tracer's nx = dx / hypot(dx, dy)
+    sp = torch.tensor([0.0, -0.0, 1.0, -1.0, float("inf"), float("-inf"), float("nan"), 5e-324, 1e-310, 1e308, 3.0, 0.01],
+                      dtype=torch.float64, device="cuda")
+    cases.append((sp.repeat_interleave(len(sp)), sp.repeat(len(sp))))
+    accepted = 0
+    for a, b in cases:
+        bad = torch.zeros(2, dtype=torch.int64, device="cuda")
+        _capi.check(_capi.lib().fmb_debug_div_check(a.contiguous().data_ptr(), b.contiguous().data_ptr(), a.numel(), bad.data_ptr(), None))
+        torch.cuda.synchronize()
+        assert int(bad[0]) == 0
+        accepted += int(bad[1])
+    assert accepted > 25_000_000

@@ -228,6 +228,8 @@ inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline double __longlong_as_double(long long v) { return emu_unbits<double>((uint64_t)v); }
 inline float __int_as_float(int v) { float f; memcpy(&f, &v, 4); return f; }
 
+struct double2 { double x, y; };
+inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
 inline int __double2hiint(double v) { return (int)(emu_bits(v) >> 32); }
 inline int __double2loint(double v) { return (int)(emu_bits(v) & 0xffffffffu); }
 inline double __hiloint2double(int hi, int lo) { return emu_unbits<double>(((uint64_t)(unsigned)hi << 32) | (unsigned)lo); }

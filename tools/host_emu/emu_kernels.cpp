@@ -207,7 +207,7 @@ void emu_trace2d_f64(const double *T, int rows, int cols, int npaths, const int 
     A.T = T; A.T_pitch = cols; A.T_qstride = (long long)rows * cols; A.rows = rows; A.cols = cols; A.npaths = npaths;
     A.field_of_path = field_of_path; A.init = init; A.end = end; A.tau = tau; A.max_steps = max_steps;
     A.out = out; A.cap = cap; A.count = count; A.status = status;
-    emu::launch((npaths + 3) / 4, 128, 0, [&] { fmb::trace2d_kernel<double, 4>(A); });
+    emu::launch((npaths + 3) / 4, 128, 4 * fmb::TRACE2D_SMEM_PER_WARP, [&] { fmb::trace2d_kernel<double, 4>(A); });
 }
 void emu_trace3d_f64(const double *T, int ny, int nx, int nz, int npaths, const int *field_of_path, const double *init,
                      const double *end, double tau, int max_steps, double *out, long long cap, int *count, int *status) {
