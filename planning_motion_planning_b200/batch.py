@@ -13,6 +13,7 @@ from typing import Callable, List, Optional, Sequence, Tuple
 
 import numpy as np
 
+_LANE_STREAMS = {}            # (device, lanes) -> streams of solve_queries' lanes (kept: their memory pools stay warm)
 FIRST_PASS_CROSSINGS = 4      # path slab of the first tracing pass, in crossings of the map (solve_chunk_gpu)
 
 
@@ -102,7 +103,7 @@ def solve_chunk_gpu(cost, goals, starts, tau: float = 0.5):
 
 
 def solve_queries(cost, goals: Sequence, starts: Sequence, tau: float = 0.5, chunk: int = 64,
-                  gather: bool = False, solve_fn: Optional[Callable] = None):
+                  gather: bool = False, solve_fn: Optional[Callable] = None, lanes: int = 2):
     """Plan ``len(goals)`` independent queries (path from starts[q] to goals[q]).
 
     cost: (rows, cols) shared by all queries, or (Q, rows, cols) one map per query.
@@ -110,7 +111,9 @@ def solve_queries(cost, goals: Sequence, starts: Sequence, tau: float = 0.5, chu
     memory: chunk * rows * cols * 8 B of fields).  Returns ``(lo, results)`` with
     ``results[i] = (path ndarray (K,2), status)`` for global query ``lo + i``; with
     ``gather=True`` rank 0 instead gets ``(0, all results in query order)`` and the other
-    ranks ``(lo, their own)``.
+    ranks ``(lo, their own)``.  ``lanes``: chunks in flight per rank on the default GPU worker (each lane a host thread
+    with its own CUDA stream and workspace: the download and host-side unpacking of one chunk overlap the solve of the
+    next; device memory = lanes * chunk fields).
     """
     rank, world, dist = _dist_info()
     Q = len(goals)
@@ -122,10 +125,35 @@ def solve_queries(cost, goals: Sequence, starts: Sequence, tau: float = 0.5, chu
     lo, hi = shard_bounds(Q, rank, world)
     fn = solve_fn or solve_chunk_gpu
     parts: List = []                      # per chunk: a PackedPaths or a plain [(path, status), ...] list (custom solve_fn)
-    for a in range(lo, hi, max(1, chunk)):
-        b = min(hi, a + max(1, chunk))
+    spans = [(a, min(hi, a + max(1, chunk))) for a in range(lo, hi, max(1, chunk))]
+
+    def one(a, b):
         cc = cost[a:b] if per_query else cost
-        parts.append(fn(cc, [list(g) for g in goals[a:b]], [list(s) for s in starts[a:b]], tau))
+        return fn(cc, [list(g) for g in goals[a:b]], [list(s) for s in starts[a:b]], tau)
+    if solve_fn is None and lanes > 1 and len(spans) > 1:
+        import torch
+        from concurrent.futures import ThreadPoolExecutor
+        dev = torch.cuda.current_device()
+        if (dev, lanes) not in _LANE_STREAMS:
+            _LANE_STREAMS[(dev, lanes)] = [torch.cuda.Stream(device=dev) for _ in range(lanes)]
+        streams = _LANE_STREAMS[(dev, lanes)]
+        ready = torch.cuda.Event()
+        ready.record()                     # whatever the caller queued (the cost map's upload) comes first
+
+        import itertools
+        import threading
+        tls, next_lane = threading.local(), itertools.count()
+
+        def lane_job(k):
+            if not hasattr(tls, "stream"):             # one stream (hence one engine workspace) per worker thread
+                tls.stream = streams[next(next_lane)]
+                tls.stream.wait_event(ready)
+            with torch.cuda.device(dev), torch.cuda.stream(tls.stream):
+                return one(*spans[k])
+        with ThreadPoolExecutor(max_workers=lanes) as pool:
+            parts = list(pool.map(lane_job, range(len(spans))))
+    else:
+        parts = [one(a, b) for a, b in spans]
 
     def as_packed(ps):
         """all chunks of one rank as ONE PackedPaths (three arrays pickle / travel much faster than thousands of small ones)"""
