@@ -193,8 +193,8 @@ def cpu_port_run(c, goal, start, threads, sample_n):
 
 def reference_arm(args):
     """Reference arm: the CPU implementation of the SAME work (one full-size solve + path per
-    query) with the SAME concurrency the GPU arm is given: --gpus x --inflight independent queries at
-    a time, one host thread per query -- a heap FMM is sequential, a single query cannot use more.
+    query) on ALL the host threads of the box: one host thread per query (a heap FMM is sequential, a
+    single query cannot use more), as many queries at a time as there are threads.
     It is the C port of the reference (oracle): the reference itself is pure Python (~2e4 cells/s,
     one thread) and has nothing to compile."""
     rank = int(os.environ.get("RANK", "0"))
@@ -206,9 +206,11 @@ def reference_arm(args):
     cores = len(os.sched_getaffinity(0))
     n = args.size
     c = make_map(n, args.map)
-    nq = max(1, args.gpus)                      # one caller thread per GPU of the other arm (its e2e = single-threaded plugin calls)
-    threads = min(nq, cores)
-    goals, starts = goals_for(c, nq * max(1, args.inflight))
+    # Every host thread the box offers, one full-size query per thread at a time (a heap FMM is sequential: one query
+    # cannot use more than one thread, a job of many queries uses them all).  One step = `threads` queries.
+    threads = min(cores, 32)
+    nq = threads
+    goals, starts = goals_for(c, max(nq, max(1, args.gpus) * max(1, args.inflight)))
 
     def one(i):
         T = O.computeTmap(c, goals[i])
@@ -229,14 +231,10 @@ def reference_arm(args):
         step(nq, threads)
     total = time.perf_counter() - t0
     value = nq * n * n * args.steps / total
-    # context 1: the concurrency the other arm's device-resident loop runs with (--gpus x --inflight queries at a time)
-    nq2 = nq * max(1, args.inflight)
-    th2 = min(nq2, cores)
-    k2 = max(1, min(args.steps, 3))
+    # context 1: one query on one thread (the latency a single caller of the reference path sees)
     t0 = time.perf_counter()
-    for _ in range(k2):
-        step(nq2, th2)
-    inflight_value = nq2 * n * n * k2 / (time.perf_counter() - t0)
+    step(1, 1)
+    one_thread_value = n * n / (time.perf_counter() - t0)
     # context 2: every core busy on crops
     allc, _, _ = cpu_port_run(c, None, None, min(cores, 32), small)
     # context 3: the planner's own call, biComputeTmap (two fronts, real early exit) + the two half paths
@@ -246,7 +244,7 @@ def reference_arm(args):
     O.getPathGDM(TG, np.array(j, dtype=np.float64), goals[0], 0.5)
     O.getPathGDM(TS, np.array(j, dtype=np.float64), s_bi, 0.5)
     bi_s = time.perf_counter() - t0
-    sample = (f"{nq} full {n}x{n} solve(s) + path per step, one host thread per query "
+    sample = (f"{nq} full {n}x{n} solve(s) + path per step, one host thread per query, all at a time "
               f"({threads} of {cores} cores; C port of FastMarching.py heap FMM + tracer)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -254,10 +252,10 @@ def reference_arm(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": make_config(args),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
-                         "with_inflight_concurrency": {"value": inflight_value, "unit": UNIT, "cores": th2,
-                                                       "sample": f"{nq2} queries at a time (--gpus x --inflight), {k2} step(s)"},
-                         "throughput_all_cores": {"value": allc, "unit": UNIT, "cores": min(cores, 32),
-                                                  "sample": f"{min(cores, 32)} threads x one {small}x{small} crop each"},
+                         "one_query_one_thread": {"value": one_thread_value, "unit": UNIT, "cores": 1,
+                                                  "sample": "one full-size solve + path on one thread (latency of a single caller)"},
+                         "throughput_all_cores_crops": {"value": allc, "unit": UNIT, "cores": min(cores, 32),
+                                                        "sample": f"{min(cores, 32)} threads x one {small}x{small} crop each"},
                          "planner_call_bicompute_plus_2_paths_s": bi_s},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

@@ -95,6 +95,67 @@ __device__ __forceinline__ double bilinear_ref(double m00, double m01, double m1
 constexpr int TB = 16, TWIN = TB + 2;
 constexpr int TRACE2D_SMEM_PER_WARP = TB * TB * 16 + TWIN * TWIN * 8;
 
+// (Re)computes the gradient block whose origin node is (bx, by): the (TB + 2)^2 window of T into sW with every load in
+// flight before the first store, then eight nodes per lane, four at a time (the branch-free exact square root /
+// division let their chains interleave; a node outside their range -- zero or infinite gradient -- is redone by
+// grad_from5).  Not inlined: it runs once per ~30 steps and its registers must not weigh on the step loop.
+template <typename real>
+__device__ __noinline__ void load_gradient_block(const real *T, long long pitch, int m, int n, int bx, int by, double *sW,
+                                                 double2 *sG, int lane) {
+    __syncwarp();
+    {   // the window: every load in flight before the first store (one memory latency for all of it)
+        constexpr int NW = (TWIN * TWIN + 31) / 32;
+        double v[NW];
+#pragma unroll
+        for (int u = 0; u < NW; ++u) {
+            const int t = min(lane + 32 * u, TWIN * TWIN - 1);
+            const int wy = t / TWIN, wx = t - wy * TWIN;
+            const int gy = min(max(by - 1 + wy, 0), m - 1), gx = min(max(bx - 1 + wx, 0), n - 1);
+            v[u] = (double)T[(long long)gy * pitch + gx];
+        }
+#pragma unroll
+        for (int u = 0; u < NW; ++u) sW[min(lane + 32 * u, TWIN * TWIN - 1)] = v[u];
+    }
+    __syncwarp();
+    // eight nodes per lane, four at a time: the branch-free exact square root / division let their chains
+    // interleave; a node outside their range (zero or infinite gradient) is redone by grad_from5
+#pragma unroll
+    for (int t0 = 0; t0 < TB * TB; t0 += 128) {
+        double gxs[4], gys[4];
+        bool oks[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int t = t0 + 32 * u + lane;
+            const int ny_ = t / TB, nx_ = t - ny_ * TB;
+            const double *w = sW + (ny_ + 1) * TWIN + nx_ + 1;
+            const int i = bx + nx_, j = by + ny_;
+            const double c = w[0], cu = w[-TWIN], cd = w[TWIN], cl = w[-1], cr = w[1];
+            const bool iu = d_isinf(cu), id = d_isinf(cd), il = d_isinf(cl), ir = d_isinf(cr);
+            double Gy = id ? (iu ? 0.0 : __dsub_rn(c, cu)) : (iu ? __dsub_rn(cd, c) : __dmul_rn(__dsub_rn(cd, cu), 0.5));
+            Gy = j == 0 ? __dsub_rn(cd, c) : (j == m - 1 ? __dsub_rn(c, cu) : Gy);
+            double Gx = ir ? (il ? 0.0 : __dsub_rn(c, cl)) : (il ? __dsub_rn(cr, c) : __dmul_rn(__dsub_rn(cr, cl), 0.5));
+            Gx = i == 0 ? __dsub_rn(cr, c) : (i == n - 1 ? __dsub_rn(c, cl) : Gx);
+            const double s2 = __dadd_rn(dsq(Gx), dsq(Gy));
+            bool ok = sqrt_fast_ok(s2);
+            const double nrm = sqrt_rn_fast(ok ? s2 : 1.0);
+            gxs[u] = ddiv_rn_fast(Gx, nrm, ok);
+            gys[u] = ddiv_rn_fast(Gy, nrm, ok);
+            oks[u] = ok;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int t = t0 + 32 * u + lane;
+            if (!oks[u]) {
+                const int ny_ = t / TB, nx_ = t - ny_ * TB;
+                const double *w = sW + (ny_ + 1) * TWIN + nx_ + 1;
+                grad_from5(w[0], w[-TWIN], w[TWIN], w[-1], w[1], m, n, bx + nx_, by + ny_, gxs[u], gys[u]);
+            }
+            sG[t] = make_double2(gxs[u], gys[u]);
+        }
+    }
+    __syncwarp();
+}
+
 template <typename real, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) trace2d_kernel(TraceArgs2D<real> A) {
     FMB_DYN_SMEM(smem_raw);
@@ -138,6 +199,7 @@ __global__ void __launch_bounds__(WARPS * 32) trace2d_kernel(TraceArgs2D<real> A
         bool fast = false;
         if (blocked) {
             const double fi = trunc(px), fj = trunc(py);
+            bool have = true;
             if (fi != cfi || fj != cfj) {                   // another cell (or the first step, or NaN)
                 cfi = cfj = -1.0;
                 bool inb = fi >= bxlo && fi <= bxhi && fj >= bylo && fj <= byhi;          // NaN -> false
@@ -147,58 +209,7 @@ __global__ void __launch_bounds__(WARPS * 32) trace2d_kernel(TraceArgs2D<real> A
                     const int i = (int)fi, j = (int)fj;
                     bx = min(max(i - (lnx > 0.0 ? TB - 3 : (lnx < 0.0 ? 1 : TB / 2 - 1)), 0), n - TB);
                     by = min(max(j - (lny > 0.0 ? TB - 3 : (lny < 0.0 ? 1 : TB / 2 - 1)), 0), m - TB);
-                    __syncwarp();
-                    {   // the window: every load in flight before the first store (one memory latency for all of it)
-                        constexpr int NW = (TWIN * TWIN + 31) / 32;
-                        double v[NW];
-#pragma unroll
-                        for (int u = 0; u < NW; ++u) {
-                            const int t = min(lane + 32 * u, TWIN * TWIN - 1);
-                            const int wy = t / TWIN, wx = t - wy * TWIN;
-                            const int gy = min(max(by - 1 + wy, 0), m - 1), gx = min(max(bx - 1 + wx, 0), n - 1);
-                            v[u] = (double)T[(long long)gy * A.T_pitch + gx];
-                        }
-#pragma unroll
-                        for (int u = 0; u < NW; ++u) sW[min(lane + 32 * u, TWIN * TWIN - 1)] = v[u];
-                    }
-                    __syncwarp();
-                    // eight nodes per lane, four at a time: the branch-free exact square root / division let their chains
-                    // interleave; a node outside their range (zero or infinite gradient) is redone by grad_from5
-#pragma unroll
-                    for (int t0 = 0; t0 < TB * TB; t0 += 128) {
-                        double gxs[4], gys[4];
-                        bool oks[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int t = t0 + 32 * u + lane;
-                            const int ny_ = t / TB, nx_ = t - ny_ * TB;
-                            const double *w = sW + (ny_ + 1) * TWIN + nx_ + 1;
-                            const int i = bx + nx_, j = by + ny_;
-                            const double c = w[0], cu = w[-TWIN], cd = w[TWIN], cl = w[-1], cr = w[1];
-                            const bool iu = d_isinf(cu), id = d_isinf(cd), il = d_isinf(cl), ir = d_isinf(cr);
-                            double Gy = id ? (iu ? 0.0 : __dsub_rn(c, cu)) : (iu ? __dsub_rn(cd, c) : __dmul_rn(__dsub_rn(cd, cu), 0.5));
-                            Gy = j == 0 ? __dsub_rn(cd, c) : (j == m - 1 ? __dsub_rn(c, cu) : Gy);
-                            double Gx = ir ? (il ? 0.0 : __dsub_rn(c, cl)) : (il ? __dsub_rn(cr, c) : __dmul_rn(__dsub_rn(cr, cl), 0.5));
-                            Gx = i == 0 ? __dsub_rn(cr, c) : (i == n - 1 ? __dsub_rn(c, cl) : Gx);
-                            const double s2 = __dadd_rn(dsq(Gx), dsq(Gy));
-                            bool ok = sqrt_fast_ok(s2);
-                            const double nrm = sqrt_rn_fast(ok ? s2 : 1.0);
-                            gxs[u] = ddiv_rn_fast(Gx, nrm, ok);
-                            gys[u] = ddiv_rn_fast(Gy, nrm, ok);
-                            oks[u] = ok;
-                        }
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int t = t0 + 32 * u + lane;
-                            if (!oks[u]) {
-                                const int ny_ = t / TB, nx_ = t - ny_ * TB;
-                                const double *w = sW + (ny_ + 1) * TWIN + nx_ + 1;
-                                grad_from5(w[0], w[-TWIN], w[TWIN], w[-1], w[1], m, n, bx + nx_, by + ny_, gxs[u], gys[u]);
-                            }
-                            sG[t] = make_double2(gxs[u], gys[u]);
-                        }
-                    }
-                    __syncwarp();
+                    load_gradient_block<real>(T, A.T_pitch, m, n, bx, by, sW, sG, lane);
                     bxlo = (double)bx; bxhi = (double)(bx + TB - 2); bylo = (double)by; byhi = (double)(by + TB - 2);
                     inb = true;
                 }
@@ -211,8 +222,9 @@ __global__ void __launch_bounds__(WARPS * 32) trace2d_kernel(TraceArgs2D<real> A
                     fy3 = __dsub_rn(__dsub_rn(__dadd_rn(g11.y, g00.y), g01.y), g10.y);
                     cfi = fi; cfj = fj;
                 }
+                have = inb;
             }
-            if (fi == cfi && fj == cfj) {
+            if (have) {
                 const double a = __dsub_rn(px, fi), b = __dsub_rn(py, fj);
                 const double dx = __dadd_rn(__dadd_rn(__dadd_rn(fx0, __dmul_rn(fx1, a)), __dmul_rn(fx2, b)), __dmul_rn(__dmul_rn(fx3, a), b));
                 const double dy = __dadd_rn(__dadd_rn(__dadd_rn(fy0, __dmul_rn(fy1, a)), __dmul_rn(fy2, b)), __dmul_rn(__dmul_rn(fy3, a), b));
