@@ -39,10 +39,11 @@ def _dist_info():
 class PackedPaths:
     """Paths of a chunk of queries as three arrays: ``flat`` (K, D) all waypoints back to back, ``counts`` (n,) rows per
     query, ``status`` (n,) tracer status.  ``unpack()`` gives the ``[(path, status), ...]`` list (views into ``flat``)."""
-    __slots__ = ("flat", "counts", "status")
+    __slots__ = ("flat", "counts", "status", "dev")
 
-    def __init__(self, flat, counts, status):
+    def __init__(self, flat, counts, status, dev=None):
         self.flat, self.counts, self.status = flat, counts, status
+        self.dev = dev                 # the device tensor `flat` was downloaded from, when there is one (gather over NCCL)
 
     def __len__(self):
         return len(self.counts)
@@ -99,7 +100,7 @@ def solve_chunk_gpu(cost, goals, starts, tau: float = 0.5):
             else:
                 pieces.append(flat[ends[q] - cnt_h[q]:ends[q]])
         return PackedPaths(np.concatenate(pieces) if pieces else np.zeros((0, 2)), counts, st_h)
-    return PackedPaths(packed[:total].cpu().numpy(), cnt_h, st.cpu().numpy())
+    return PackedPaths(packed[:total].cpu().numpy(), cnt_h, st.cpu().numpy(), dev=packed[:total])
 
 
 def solve_queries(cost, goals: Sequence, starts: Sequence, tau: float = 0.5, chunk: int = 64,
@@ -160,23 +161,57 @@ def solve_queries(cost, goals: Sequence, starts: Sequence, tau: float = 0.5, chu
         if not ps:
             return PackedPaths(np.zeros((0, 2)), np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.int32))
         if all(isinstance(p, PackedPaths) for p in ps):
+            dev = None
+            if all(p.dev is not None for p in ps):
+                import torch
+                dev = ps[0].dev if len(ps) == 1 else torch.cat([p.dev for p in ps])
             return PackedPaths(np.concatenate([p.flat for p in ps]), np.concatenate([p.counts for p in ps]),
-                               np.concatenate([p.status for p in ps]))
+                               np.concatenate([p.status for p in ps]), dev=dev)
         lst = [r for p in ps for r in (p.unpack() if isinstance(p, PackedPaths) else p)]
         D = lst[0][0].shape[1] if lst and lst[0][0].ndim == 2 else 2
         return PackedPaths(np.concatenate([np.asarray(r[0], dtype=np.float64).reshape(-1, D) for r in lst]) if lst else np.zeros((0, D)),
                            np.array([len(r[0]) for r in lst], dtype=np.int32), np.array([r[1] for r in lst], dtype=np.int32))
     mine = as_packed(parts)
     if gather and dist is not None and world > 1:
-        bucket = [None] * world if rank == 0 else None
-        dist.gather_object((lo, mine.flat, mine.counts, mine.status), bucket, dst=0)
+        # Three arrays per rank travel as TENSORS through the process group's own transport (NCCL: device buffers over
+        # NVLink, the waypoints straight from the device copy the chunks kept; gloo: host buffers) -- no pickling of tens
+        # of megabytes of waypoints.  Shards are contiguous blocks in rank order, so rank order is query order.
+        import torch
+        on_gpu = dist.get_backend() == "nccl"
+        tdev = torch.device("cuda", torch.cuda.current_device()) if on_gpu else torch.device("cpu")
+        D = mine.flat.shape[1] if mine.flat.ndim == 2 else 2
+        meta = torch.tensor([lo, len(mine.counts), mine.flat.shape[0], D], dtype=torch.int64, device=tdev)
+        metas = [torch.zeros_like(meta) for _ in range(world)]
+        dist.all_gather(metas, meta)
+        metas = [[int(v) for v in m.tolist()] for m in metas]
         if rank == 0:
-            bucket.sort(key=lambda t: t[0])
-            pos = 0
-            for part_lo, _, cts, _ in bucket:
-                assert part_lo == pos
-                pos += len(cts)
-            merged = PackedPaths(np.concatenate([t[1] for t in bucket]), np.concatenate([t[2] for t in bucket]),
-                                 np.concatenate([t[3] for t in bucket]))
+            bufs, reqs = [], []
+            for r in range(1, world):
+                _, n_r, k_r, d_r = metas[r]
+                f = torch.empty((k_r, d_r), dtype=torch.float64, device=tdev)
+                cs = torch.empty((2, n_r), dtype=torch.int32, device=tdev)
+                if k_r:
+                    reqs.append(dist.irecv(f, src=r))
+                if n_r:
+                    reqs.append(dist.irecv(cs, src=r))
+                bufs.append((f, cs))
+            for q in reqs:
+                q.wait()
+            pos = len(mine.counts)
+            flats, cnts, sts = [mine.flat.reshape(-1, D)], [mine.counts], [mine.status]
+            for r, (f, cs) in enumerate(bufs, start=1):
+                assert metas[r][0] == pos
+                pos += metas[r][1]
+                cs_h = cs.cpu().numpy()
+                flats.append(f.cpu().numpy()); cnts.append(cs_h[0]); sts.append(cs_h[1])
+            merged = PackedPaths(np.concatenate(flats), np.concatenate(cnts), np.concatenate(sts))
             return 0, merged.unpack()
+        if len(mine.counts):
+            f = mine.dev if (on_gpu and mine.dev is not None) else torch.from_numpy(np.ascontiguousarray(mine.flat, dtype=np.float64)).to(tdev)
+            cs = torch.from_numpy(np.stack([np.asarray(mine.counts, dtype=np.int32), np.asarray(mine.status, dtype=np.int32)])).to(tdev)
+            if f.is_cuda:
+                f.record_stream(torch.cuda.current_stream())
+            if f.shape[0]:
+                dist.send(f.contiguous(), dst=0)
+            dist.send(cs.contiguous(), dst=0)
     return lo, mine.unpack()
