@@ -117,13 +117,59 @@ __device__ __forceinline__ real memo_wait(const real *memo, long long slot, real
     return fallback;
 }
 
-// pass 2: every relaxation of the first k pops, in pop order (see the header of this file)
+// one relaxation of the replay: ticket tk = r * NN + j = "pop r relaxes its j-th neighbour" (see the header of this file)
 template <typename real, int D>
-__global__ void truncate_sweep_kernel(Grid<D> g, const real *F, const real *cost, const int *rank, const int *order, int k,
-                                      real *out, real *memo, int *ticket, int *overflow, const int *k_dev = nullptr) {
+__device__ __forceinline__ void replay_ticket(long long tk, const Grid<D> &g, const real *F, const real *cost, const int *rank,
+                                              const int *order, int k, real *out, real *memo, int *overflow) {
     constexpr int NN = Grid<D>::NN;
     const real INF = num<real>::inf();
+    const int r = (int)(tk / NN), j = (int)(tk - (long long)r * NN);
+    const long long a = order[r];
+    const long long c = g.nbr(a, j);
+    if (c >= 0 && rank[c] > r && cost[c] < INF) {           // a free neighbour that is not accepted yet (:56, FastMarching3D.py:35)
+        real v[NN];
+        int newer = -1;                                      // a neighbour of c that pops in (r, k]: not c's last update
+#pragma unroll
+        for (int i = 0; i < NN; ++i) {
+            const long long m = g.nbr(c, i);
+            real val = INF;
+            if (m >= 0) {
+                const int rm = rank[m];
+                if (rm <= r) val = F[m];
+                else {
+                    if (rm <= k) newer = i;
+                    if (cost[m] < INF) {
+                        int wm = 0;
+                        const int tm = last_update_time<D>(g, rank, m, r, &wm);
+                        if (tm >= 0) val = memo_wait<real>(memo, m * NN + wm, F[m], overflow);
+                    }
+                }
+            }
+            v[i] = val;
+        }
+        real u = Grid<D>::template update<real>(v, cost[c]);
+        int wp = 0;
+        const int tprev = last_update_time<D>(g, rank, c, r - 1, &wp);
+        if (tprev >= 0) {
+            const real prev = memo_wait<real>(memo, c * NN + wp, u, overflow);
+            u = prev < u ? prev : u;
+        }
+        if (newer < 0 && rank[c] > k) out[c] = u;            // c's state when the reference stops
+        __threadfence();
+        *(reinterpret_cast<volatile unsigned long long *>(memo) + (c * NN + (j ^ 1))) =
+            (unsigned long long)__double_as_longlong((double)u);
+    }
+}
+
+// pass 2, dense form: every relaxation of the first k pops, in pop order.  run_if (optional): the kernel only runs when
+// *run_if != 0 -- the sparse form below failed (its frontier or ticket list overflowed, or its marking did not settle).
+template <typename real, int D>
+__global__ void truncate_sweep_kernel(Grid<D> g, const real *F, const real *cost, const int *rank, const int *order, int k,
+                                      real *out, real *memo, int *ticket, int *overflow, const int *k_dev = nullptr,
+                                      const int *run_if = nullptr) {
+    constexpr int NN = Grid<D>::NN;
     const int lane = threadIdx.x & 31;
+    if (run_if && *run_if == 0) return;
     if (k_dev) k = *k_dev;
     if (k >= g.size()) return;                     // every reached cell is accepted (no early exit): nothing to replay
     const long long n_tickets = ((long long)k + 1) * NN;
@@ -133,44 +179,129 @@ __global__ void truncate_sweep_kernel(Grid<D> g, const real *F, const real *cost
         base = __shfl_sync(FULL, base, 0);
         if (base >= n_tickets) break;
         const long long tk = (long long)base + lane;
-        if (tk < n_tickets) {
-            const int r = (int)(tk / NN), j = (int)(tk - (long long)r * NN);
-            const long long a = order[r];
-            const long long c = g.nbr(a, j);
-            if (c >= 0 && rank[c] > r && cost[c] < INF) {           // a free neighbour that is not accepted yet (:56, FastMarching3D.py:35)
-                real v[NN];
-                int newer = -1;                                      // a neighbour of c that pops in (r, k]: not c's last update
+        if (tk < n_tickets) replay_ticket<real, D>(tk, g, F, cost, rank, order, k, out, memo, overflow);
+        __syncwarp();
+    }
+}
+template <typename real>
+__global__ void memo_fill_kernel(real *memo, long long n, const int *run_if) {
+    if (run_if && *run_if == 0) return;
+    unsigned long long *p = reinterpret_cast<unsigned long long *>(memo);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = MEMO_UNKNOWN;
+}
+
+// ---------------------------------------------------------------------------
+// pass 2, sparse form: only the relaxations the narrow band of time k depends on.
+//
+// The partial field only shows the states of the narrow-band cells at time k.  A state reads (a) the earlier states of its
+// own cell and (b), for every neighbour that was not yet accepted at that moment, that neighbour's state after ITS last
+// relaxation before the moment -- which reads its own earlier states and its tentative neighbours, and so on backwards in
+// time along the front.  need_t[c] = the latest moment up to which the states of cell c are needed (-1: none); the
+// closure is computed by a frontier expansion (a cell whose bound rises is expanded again), a few rounds in practice
+// because every link steps back in time towards the moment a cell was first touched.  The needed relaxations are then
+// emitted as tickets from the cell side, sorted (the in-order hand-out is what makes the dependency waits deadlock
+// free) and replayed by the same code as the dense form: a few 10^5 tickets instead of 4 (k + 1).
+// counters (int[64], zeroed by the host): [0] dense ticket cursor, [1] waits at the limit, [4] tickets emitted,
+// [5] sparse form failed -> the dense form runs, [6] list cursor, [8 + i] size of the frontier of round i.
+constexpr int CONE_ROUNDS = 48;
+constexpr int CONE_TICKET_PAD = 0x7f7f7f7f;       // memset(0x7f) of the ticket list: above every valid ticket
+
+template <typename real, int D>
+__global__ void cone_seed_kernel(Grid<D> g, const real *cost, const int *rank, const int *k_dev, int *need_t, int *front,
+                                 int *counters, int cap) {
+    constexpr int NN = Grid<D>::NN;
+    const real INF = num<real>::inf();
+    const int k = *k_dev;
+    const long long total = g.size();
+    if (k >= total) return;
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < total; c += (long long)gridDim.x * blockDim.x) {
+        int t = -1;
+        if (rank[c] > k && cost[c] < INF) {
 #pragma unroll
-                for (int i = 0; i < NN; ++i) {
-                    const long long m = g.nbr(c, i);
-                    real val = INF;
-                    if (m >= 0) {
-                        const int rm = rank[m];
-                        if (rm <= r) val = F[m];
-                        else {
-                            if (rm <= k) newer = i;
-                            if (cost[m] < INF) {
-                                int wm = 0;
-                                const int tm = last_update_time<D>(g, rank, m, r, &wm);
-                                if (tm >= 0) val = memo_wait<real>(memo, m * NN + wm, F[m], overflow);
-                            }
-                        }
-                    }
-                    v[i] = val;
-                }
-                real u = Grid<D>::template update<real>(v, cost[c]);
-                int wp = 0;
-                const int tprev = last_update_time<D>(g, rank, c, r - 1, &wp);
-                if (tprev >= 0) {
-                    const real prev = memo_wait<real>(memo, c * NN + wp, u, overflow);
-                    u = prev < u ? prev : u;
-                }
-                if (newer < 0 && rank[c] > k) out[c] = u;            // c's state when the reference stops
-                __threadfence();
-                *(reinterpret_cast<volatile unsigned long long *>(memo) + (c * NN + (j ^ 1))) =
-                    (unsigned long long)__double_as_longlong((double)u);
+            for (int i = 0; i < NN; ++i) {
+                const long long n = g.nbr(c, i);
+                if (n >= 0 && rank[n] <= k) t = k;
             }
         }
+        need_t[c] = t;
+        if (t >= 0) {
+            const int pos = atomicAdd(&counters[8], 1);
+            if (pos < cap) front[pos] = (int)c; else counters[5] = 1;
+        }
+    }
+}
+
+template <typename real, int D>
+__global__ void cone_expand_kernel(Grid<D> g, const real *cost, const int *rank, const int *k_dev, int *need_t,
+                                   const int *fin, int *fout, int *counters, int round, int cap) {
+    constexpr int NN = Grid<D>::NN;
+    const real INF = num<real>::inf();
+    if (*k_dev >= g.size()) return;
+    const int n_in = min(counters[8 + round], cap);
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_in; idx += gridDim.x * blockDim.x) {
+        const long long c = fin[idx];
+        const int t = *reinterpret_cast<volatile int *>(&need_t[c]);
+#pragma unroll
+        for (int j = 0; j < NN; ++j) {
+            const long long a = g.nbr(c, j);
+            if (a < 0) continue;
+            const int r = rank[a];
+            if (r > t) continue;                                   // not a relaxation of c that is needed
+#pragma unroll
+            for (int i = 0; i < NN; ++i) {
+                const long long m = g.nbr(c, i);
+                if (m < 0 || rank[m] <= r || !(cost[m] < INF)) continue;      // accepted by then (final value) / obstacle
+                const int tm = last_update_time<D>(g, rank, m, r);
+                if (tm < 0) continue;                              // never touched before: +inf
+                if (atomicMax(&need_t[m], tm) < tm) {
+                    const int pos = atomicAdd(&counters[8 + round + 1], 1);
+                    if (pos < cap) fout[pos] = (int)m; else counters[5] = 1;
+                }
+            }
+        }
+    }
+}
+
+template <typename real, int D>
+__global__ void cone_emit_kernel(Grid<D> g, const int *rank, const int *k_dev, const int *need_t, int *tickets, real *memo,
+                                 int *counters, int cap_tickets) {
+    constexpr int NN = Grid<D>::NN;
+    const long long total = g.size();
+    if (*k_dev >= total) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && counters[8 + CONE_ROUNDS] > 0) counters[5] = 1;      // the marking did not settle
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < total; c += (long long)gridDim.x * blockDim.x) {
+        const int t = need_t[c];
+        if (t < 0) continue;
+#pragma unroll
+        for (int j = 0; j < NN; ++j) {
+            const long long a = g.nbr(c, j);
+            if (a < 0) continue;
+            const int r = rank[a];
+            if (r > t) continue;
+            const int pos = atomicAdd(&counters[4], 1);
+            if (pos < cap_tickets) {
+                tickets[pos] = r * NN + (j ^ 1);                   // seen from a: c is its neighbour j ^ 1
+                reinterpret_cast<unsigned long long *>(memo)[c * NN + j] = MEMO_UNKNOWN;
+            } else counters[5] = 1;
+        }
+    }
+}
+
+template <typename real, int D>
+__global__ void truncate_sweep_list_kernel(Grid<D> g, const real *F, const real *cost, const int *rank, const int *order,
+                                           real *out, real *memo, const int *tickets, int *counters, const int *k_dev, int cap_tickets) {
+    const int lane = threadIdx.x & 31;
+    if (counters[5]) return;                       // the dense form takes over
+    const int k = *k_dev;
+    if (k >= g.size()) return;
+    const int n_list = min(counters[4], cap_tickets);
+    for (;;) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&counters[6], 32);
+        base = __shfl_sync(FULL, base, 0);
+        if (base >= n_list) break;
+        const int idx = base + lane;
+        if (idx < n_list) replay_ticket<real, D>((long long)tickets[idx], g, F, cost, rank, order, k, out, memo, &counters[1]);
         __syncwarp();
     }
 }
