@@ -111,6 +111,8 @@ typedef struct fmb_options {
                              each).  A solve in causal order is a chain of dependent visits that leaves most issue slots idle; its
                              persistent grid then takes 1/n of the resident CTA slots, so all n solves are resident at once
                              (0 / 1 = default: two CTAs per SM, the fastest grid for one solve alone) */
+    int32_t replay_sparse; /* early-exit emulation: replay only the relaxations the narrow band depends on (-1 auto: from 2^21 cells on,
+                             0 always the dense replay, 1 always the sparse one; it falls back to the dense one on the device) */
 } fmb_options;
 void fmb_get_options(fmb_options *out);
 int fmb_set_options(const fmb_options *in);
@@ -356,7 +358,9 @@ int fmb_pop_ranks_status(const void *d_ws, void *stream, int32_t *out4);
  * d_TG / d_TS: out, the partial fields the reference returns; d_join: device int32[16], [0] = k (pops per front when
  * the loop breaks), [1] = flat index of nodeJoin, both INT32_MAX when the fronts never meet (reference: NameError);
  * [4..7] / [8..11] = fmb_pop_ranks_status of the G / S front, [12] / [13] = waits of the G / S replay that hit the
- * safety limit (must be 0).
+ * safety limit (must be 0), [14] = relaxations the replay of the G front ran in its sparse form (the dependency cone of
+ * the narrow band; the dense form replays all 4 (k + 1)), [15] = bit 0 / 1: the G / S front fell back to the dense form,
+ * bits 8..: rounds the G front's cone expansion took (diagnostics).
  * stream2: optional second stream for the S front (NULL = everything on `stream`); on return `stream` has joined it.
  * Asynchronous; fmb_finish(d_ws, ...) reports device-side failures of the solve. */
 size_t fmb_workspace_bytes_bisolve2d(int rows, int cols);

@@ -38,7 +38,7 @@ class FmbOptions(C.Structure):
     _fields_ = [(k, C.c_int32) for k in ("engine2d", "cta_cells", "tile_w2d", "tile_z3d", "best_first", "windowed",
                                          "window", "worker_div", "max_blocks", "watchdog_ms", "step_cap", "engine3d",
                                          "level_div", "win_running", "check_passes", "pipeline", "precheck",
-                                         "causal_slack", "tma", "ring2", "variant", "concurrent_solves")]
+                                         "causal_slack", "tma", "ring2", "variant", "concurrent_solves", "replay_sparse")]
 
 
 class FmbPlan2DResult(C.Structure):

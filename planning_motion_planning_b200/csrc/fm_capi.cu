@@ -109,6 +109,7 @@ void opt_defaults_locked() {
     g_opt.ring2 = env_int("FMB_RING2", 0);
     g_opt.variant = env_int("FMB_VARIANT", 0);
     g_opt.concurrent_solves = env_int("FMB_CONCURRENT_SOLVES", 0);
+    g_opt.replay_sparse = env_int("FMB_REPLAY_SPARSE", -1);
     g_opt_init = true;
 }
 fmb_options opt() {

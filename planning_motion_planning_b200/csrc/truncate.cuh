@@ -16,14 +16,21 @@
 // is the minimum of the update and the cell's previous state.
 //
 // Instead of recursing from the narrow band (deep, serial chains along uniform-cost fronts), the
-// kernel replays EVERY relaxation the reference performed during its first k pops, in the
+// kernels replay the relaxations the reference performed during its first k pops, in the
 // reference's own order, in parallel: ticket r*NN + j = "pop r relaxes its j-th neighbour".  Tickets
 // are handed out in order; a state waits (spin) for the few earlier states it reads -- they belong to
 // strictly earlier pops, i.e. to smaller tickets, which are held by running threads or finished, so
 // the wait cannot deadlock and the critical path is the longest dependency chain, not a walk.  The
 // states live in a dense memo of NN doubles per cell (slot c*NN + i = value of c after its neighbour i
 // popped; all-ones bits = not yet written).  The state of a narrow-band cell after its last update
-// <= k is its entry in the partial field.  Ranks come from a sort of F (host side).
+// <= k is its entry in the partial field.  Ranks come from a sort of F (fm_capi_ranks.inc).
+//
+// Two forms.  The DENSE form replays every relaxation: NN (k + 1) tickets (33.5 M for a 4096^2 bi-solve: 17 ms per
+// front).  The SPARSE form (round 2, the default behind fmb_bisolve2d_f64 / fmb_solve*_until_f64) first computes which
+// states the narrow band of time k depends on at all -- a backward closure over "reads the tentative state of" that
+// runs along the front for hundreds of rounds but touches only ~1.5 % of the relaxations (475 k tickets there) -- and
+// replays those, sorted, with the same code: 2.5 ms per front.  It reports failure on the device (a list overflowed,
+// the closure did not settle) and the dense form then runs instead, without a host round trip.
 #pragma once
 #include "eikonal2d.cuh"
 #include "eikonal3d.cuh"
@@ -202,8 +209,10 @@ __global__ void memo_fill_kernel(real *memo, long long n, const int *run_if) {
 // emitted as tickets from the cell side, sorted (the in-order hand-out is what makes the dependency waits deadlock
 // free) and replayed by the same code as the dense form: a few 10^5 tickets instead of 4 (k + 1).
 // counters (int[64], zeroed by the host): [0] dense ticket cursor, [1] waits at the limit, [4] tickets emitted,
-// [5] sparse form failed -> the dense form runs, [6] list cursor, [8 + i] size of the frontier of round i.
-constexpr int CONE_ROUNDS = 48;
+// [5] sparse form failed -> the dense form runs, [6] list cursor, [7] rounds of the expansion, [8 + i] size of the
+// frontier of grid-wide round i.
+constexpr int CONE_ROUNDS = 8;          // grid-wide rounds before the one-block tail
+constexpr int CONE_TAIL_ROUNDS = 1 << 16;
 constexpr int CONE_TICKET_PAD = 0x7f7f7f7f;       // memset(0x7f) of the ticket list: above every valid ticket
 
 template <typename real, int D>
@@ -231,34 +240,82 @@ __global__ void cone_seed_kernel(Grid<D> g, const real *cost, const int *rank, c
     }
 }
 
+// expands one frontier cell: every needed relaxation of c reads the tentative neighbours of that moment.  All ranks the
+// decisions need (the neighbours' and the neighbours' neighbours') are loaded up front -- one memory latency per cell
+// instead of one per decision: the tail of the expansion is a chain of hundreds of rounds of a few cells each.
+template <typename real, int D>
+__device__ __forceinline__ void cone_expand_cell(const Grid<D> &g, const real *cost, const int *rank, int *need_t, long long c,
+                                                 int *fout, int *n_out, int cap, int *fail) {
+    constexpr int NN = Grid<D>::NN;
+    const real INF = num<real>::inf();
+    const int t = *reinterpret_cast<volatile int *>(&need_t[c]);
+    long long nb[NN];
+    int rn[NN], r2[NN][NN];
+    bool open[NN];
+#pragma unroll
+    for (int i = 0; i < NN; ++i) {
+        nb[i] = g.nbr(c, i);
+        rn[i] = nb[i] >= 0 ? rank[nb[i]] : -1;
+        open[i] = nb[i] >= 0 && cost[nb[i]] < INF;
+#pragma unroll
+        for (int q = 0; q < NN; ++q) {
+            const long long m2 = nb[i] >= 0 ? g.nbr(nb[i], q) : -1;
+            r2[i][q] = m2 >= 0 ? rank[m2] : 0x7fffffff;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NN; ++j) {
+        if (nb[j] < 0) continue;
+        const int r = rn[j];
+        if (r > t) continue;                                   // not a relaxation of c that is needed
+#pragma unroll
+        for (int i = 0; i < NN; ++i) {
+            if (nb[i] < 0 || rn[i] <= r || !open[i]) continue;                 // accepted by then (final value) / obstacle
+            int tm = -1;                                       // the neighbour's last relaxation before that moment
+#pragma unroll
+            for (int q = 0; q < NN; ++q) tm = (r2[i][q] <= r && r2[i][q] > tm) ? r2[i][q] : tm;
+            if (tm < 0) continue;                              // never touched before: +inf
+            if (atomicMax(&need_t[nb[i]], tm) < tm) {
+                const int pos = atomicAdd(n_out, 1);
+                if (pos < cap) fout[pos] = (int)nb[i]; else *fail = 1;
+            }
+        }
+    }
+}
+
+// the first rounds of the expansion, grid-wide (thousands of cells per round) ...
 template <typename real, int D>
 __global__ void cone_expand_kernel(Grid<D> g, const real *cost, const int *rank, const int *k_dev, int *need_t,
                                    const int *fin, int *fout, int *counters, int round, int cap) {
-    constexpr int NN = Grid<D>::NN;
-    const real INF = num<real>::inf();
     if (*k_dev >= g.size()) return;
     const int n_in = min(counters[8 + round], cap);
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_in; idx += gridDim.x * blockDim.x) {
-        const long long c = fin[idx];
-        const int t = *reinterpret_cast<volatile int *>(&need_t[c]);
-#pragma unroll
-        for (int j = 0; j < NN; ++j) {
-            const long long a = g.nbr(c, j);
-            if (a < 0) continue;
-            const int r = rank[a];
-            if (r > t) continue;                                   // not a relaxation of c that is needed
-#pragma unroll
-            for (int i = 0; i < NN; ++i) {
-                const long long m = g.nbr(c, i);
-                if (m < 0 || rank[m] <= r || !(cost[m] < INF)) continue;      // accepted by then (final value) / obstacle
-                const int tm = last_update_time<D>(g, rank, m, r);
-                if (tm < 0) continue;                              // never touched before: +inf
-                if (atomicMax(&need_t[m], tm) < tm) {
-                    const int pos = atomicAdd(&counters[8 + round + 1], 1);
-                    if (pos < cap) fout[pos] = (int)m; else counters[5] = 1;
-                }
-            }
-        }
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_in; idx += gridDim.x * blockDim.x)
+        cone_expand_cell<real, D>(g, cost, rank, need_t, fin[idx], fout, &counters[8 + round + 1], cap, &counters[5]);
+}
+// ... and its long thin tail (tens of cells per round for hundreds of rounds: the chains that run along the front) in
+// ONE block that loops over the rounds with a block barrier instead of a launch per round
+template <typename real, int D>
+__global__ void __launch_bounds__(1024) cone_tail_kernel(Grid<D> g, const real *cost, const int *rank, const int *k_dev, int *need_t,
+                                 int *fa, int *fb, int *counters, int first_round, int cap, int max_rounds) {
+    __shared__ int s_in, s_out;
+    if (*k_dev >= g.size()) return;
+    int *fin = (first_round & 1) ? fb : fa, *fout = (first_round & 1) ? fa : fb;
+    if (threadIdx.x == 0) { s_in = min(counters[8 + first_round], cap); s_out = 0; }
+    __syncthreads();
+    int rounds = 0;
+    for (; rounds < max_rounds; ++rounds) {
+        const int n_in = s_in;
+        if (n_in == 0) break;
+        for (int idx = threadIdx.x; idx < n_in; idx += blockDim.x)
+            cone_expand_cell<real, D>(g, cost, rank, need_t, fin[idx], fout, &s_out, cap, &counters[5]);
+        __syncthreads();
+        if (threadIdx.x == 0) { s_in = min(s_out, cap); s_out = 0; }
+        int *tmp = fin; fin = fout; fout = tmp;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        if (s_in != 0) counters[5] = 1;              // did not settle within max_rounds
+        counters[7] = first_round + rounds;
     }
 }
 
@@ -268,7 +325,6 @@ __global__ void cone_emit_kernel(Grid<D> g, const int *rank, const int *k_dev, c
     constexpr int NN = Grid<D>::NN;
     const long long total = g.size();
     if (*k_dev >= total) return;
-    if (blockIdx.x == 0 && threadIdx.x == 0 && counters[8 + CONE_ROUNDS] > 0) counters[5] = 1;      // the marking did not settle
     for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < total; c += (long long)gridDim.x * blockDim.x) {
         const int t = need_t[c];
         if (t < 0) continue;

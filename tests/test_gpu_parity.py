@@ -424,7 +424,9 @@ def test_dropin_replays_planner_calls():
     assert p3.shape == g["path3d"].shape and np.abs(p3 - g["path3d"]).max() < TOLP
 
 
-def test_dropin_early_exit_fields_match_reference_bitwise_pattern():
+@pytest.mark.parametrize("replay", ["dense", "sparse"])
+def test_dropin_early_exit_fields_match_reference_bitwise_pattern(replay, fmb_opts):
+    fmb_opts(replay_sparse=1 if replay == "sparse" else 0)        # both forms of the replay (truncate.cuh)
     """Partial fields (accepted / narrow band / far) of the early-exit calls, SURVEY 8a a-5."""
     import FastMarching.FastMarching as FM
     import FastMarching.FastMarching3D as FM3D
@@ -519,7 +521,9 @@ def test_tie_order_kernel_matches_torch_reference_and_oracle_order():
         assert int((mine != order).sum()) <= max_bad
 
 
-def test_dropin_partial_fields_on_tie_heavy_maps():
+@pytest.mark.parametrize("replay", ["dense", "sparse"])
+def test_dropin_partial_fields_on_tie_heavy_maps(replay, fmb_opts):
+    fmb_opts(replay_sparse=1 if replay == "sparse" else 0)        # both forms of the replay (truncate.cuh)
     """Uniform-cost and block-plateau maps are full of exactly equal T values; the reference pops
     those LIFO, which decides the join node and which cells are accepted when the fronts meet."""
     import FastMarching.FastMarching as FM
@@ -535,7 +539,9 @@ def test_dropin_partial_fields_on_tie_heavy_maps():
         assert rel_err(T1, O.computeTmap(c, g, s)) < TOL64
 
 
-def test_dropin_bisolve_fuzz_join_and_patterns_exact():
+@pytest.mark.parametrize("replay", ["dense", "sparse"])
+def test_dropin_bisolve_fuzz_join_and_patterns_exact(replay, fmb_opts):
+    fmb_opts(replay_sparse=1 if replay == "sparse" else 0)        # both forms of the replay (truncate.cuh)
     """Seeded random / plateau / uniform maps with walls through the public drop-in API: the join
     node and the accepted / narrow-band / +inf pattern of both partial fields equal the heap
     loop's exactly, the values to 1e-9 (FastMarching.py:114-162)."""
@@ -870,7 +876,9 @@ def test_polish3d_reaches_the_fixed_point_of_the_reference_arithmetic(eng):
             # (exact equality for all but cells whose inputs are themselves within the acceptance threshold)
 
 
-def test_dropin_3d_early_exit_fuzz_slice():
+@pytest.mark.parametrize("replay", ["dense", "sparse"])
+def test_dropin_3d_early_exit_fuzz_slice(replay, fmb_opts):
+    fmb_opts(replay_sparse=1 if replay == "sparse" else 0)        # both forms of the replay (truncate.cuh)
     """120 volumes of tools/gpu_fuzz_3d.py (70 % uniform-cost with obstacles: the tie-heavy class the planner's real
     volume belongs to; 30 % random) through FM3D.computeTmap: the accepted / narrow-band / far pattern is the
     reference's in EVERY case and the values agree to 1e-9.  This needs the field to carry the reference's own rounding
@@ -910,7 +918,7 @@ def test_one_host_thread_two_devices_timing_events():
         assert rel_err(T, ref) < TOL64
 
 
-def test_c_abi_alone_reproduces_bicomputetmap_and_the_3d_early_exit():
+def test_c_abi_alone_reproduces_bicomputetmap_and_the_3d_early_exit(fmb_opts):
     """What INTEGRATION.md promises a C / C++ host: the reference's RETURN VALUES from include/fm_b200.h alone.  torch
     only provides device memory here -- no torch op runs between the library calls: fmb_bisolve2d_f64 (KAT-3b: join
     node, both partial fields), fmb_solve2d_until_f64, fmb_solve3d_until_f64 (KAT-4 truncated field), each bitwise
@@ -920,6 +928,7 @@ def test_c_abi_alone_reproduces_bicomputetmap_and_the_3d_early_exit():
     from oracle import oracle as O
     from planning_motion_planning_b200 import _capi
     L = _capi.lib()
+    fmb_opts(replay_sparse=1)               # (auto = dense below 2^21 cells; the sparse form is asserted on below)
     st = torch.cuda.current_stream().cuda_stream
     i32 = lambda v: (C.c_int32 * len(v))(*v)
     c = rand_map((100, 100), 0)
@@ -935,6 +944,8 @@ def test_c_abi_alone_reproduces_bicomputetmap_and_the_3d_early_exit():
     inf = info.tolist()
     assert [inf[1] % 100, inf[1] // 100] == [int(j[0]), int(j[1])] == [64, 36]
     assert inf[6] == 0 and inf[10] == 0 and inf[12] == 0 and inf[13] == 0
+    # the replay ran in its sparse form (the dependency cone of the narrow band) on both fronts
+    assert (inf[15] & 3) == 0 and 0 < inf[14] <= 4 * (inf[0] + 1), inf
     for a, ref in ((out[0], TG), (out[1], TS)):
         assert rel_err(a.cpu().numpy(), ref) < TOL64
     # single front, early exit when `start` is accepted
@@ -944,6 +955,7 @@ def test_c_abi_alone_reproduces_bicomputetmap_and_the_3d_early_exit():
                                         ws2.data_ptr(), ws2.numel(), st))
     _capi.check(L.fmb_finish(ws2.data_ptr(), ws2.numel(), st, None))
     assert rel_err(T2.cpu().numpy(), O.computeTmap(c, [25, 25], [60, 70])) < TOL64
+    assert (info.tolist()[15] & 3) == 0, info.tolist()
     # 3D (KAT-4)
     c3 = rand_map((24, 24, 24), 0)
     g3, s3 = [5, 6, 7], [18, 17, 16]
@@ -955,6 +967,7 @@ def test_c_abi_alone_reproduces_bicomputetmap_and_the_3d_early_exit():
     _capi.check(L.fmb_finish(ws3.data_ptr(), ws3.numel(), st, None))
     ref3 = O.computeTmap3D(c3, g3, s3)
     assert int(np.isfinite(ref3).sum()) == 9830 and rel_err(T3.cpu().numpy(), ref3) < TOL64
+    assert (info.tolist()[15] & 3) == 0 and (info.tolist()[15] >> 8) >= 1, info.tolist()      # ([14] = the exact solve ran, here)
 
 
 def test_batch_long_paths_are_retraced_with_the_reference_cap(eng, monkeypatch):

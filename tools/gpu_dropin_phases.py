@@ -19,7 +19,7 @@ def wrap(mod, name, tag):
         return r
     setattr(mod, name, g)
 wrap(engine, "solve2d", "solve2d"); wrap(engine, "solve3d", "solve3d")
-wrap(C, "pop_ranks_lifo2d", "ranks_lifo2d"); wrap(C, "pop_ranks", "ranks_plain"); wrap(C, "truncate", "truncate")
+wrap(C, "bisolve2d", "bisolve2d"); wrap(C, "solve3d_until", "solve3d_until"); wrap(C, "to_device", "to_device"); wrap(C, "to_host", "to_host")
 
 def run(label, f, reps=5):
     f(); acc.clear()
