@@ -297,7 +297,8 @@ __global__ void cone_expand_kernel(Grid<D> g, const real *cost, const int *rank,
 template <typename real, int D>
 __global__ void __launch_bounds__(1024) cone_tail_kernel(Grid<D> g, const real *cost, const int *rank, const int *k_dev, int *need_t,
                                  int *fa, int *fb, int *counters, int first_round, int cap, int max_rounds) {
-    __shared__ int s_in, s_out;
+    FMB_DYN_SMEM(smem_raw);                        // two ints: the sizes of the current and of the next frontier
+    int &s_in = reinterpret_cast<int *>(smem_raw)[0], &s_out = reinterpret_cast<int *>(smem_raw)[1];
     if (*k_dev >= g.size()) return;
     int *fin = (first_round & 1) ? fb : fa, *fout = (first_round & 1) ? fa : fb;
     if (threadIdx.x == 0) { s_in = min(counters[8 + first_round], cap); s_out = 0; }

@@ -121,9 +121,13 @@ def test_trace3d_matches_oracle_paths():
         assert np.abs(p[0] - g[f"kat4_path_{tag}"]).max() < TOLP
 
 
-def test_truncate_rebuilds_reference_partial_fields():
+@pytest.mark.parametrize("replay", ["dense", "sparse"])
+def test_truncate_rebuilds_reference_partial_fields(replay, monkeypatch):
     """csrc/truncate.cuh under the emulator: early-exit (2D/3D) and bidirectional partial fields
-    equal the reference's, including every narrow-band tentative value."""
+    equal the reference's, including every narrow-band tentative value -- with the dense replay (every relaxation of
+    the first k pops) and with the sparse one (only the dependency cone of the narrow band: cone_* kernels, sorted
+    tickets, list sweep; emu.truncate returns -1 if that form gave up)."""
+    monkeypatch.setenv("FMB_REPLAY_SPARSE", "1" if replay == "sparse" else "0")
     for c, g, s in ((rand_map((64, 64), 7), [40, 12], [57, 9]), (plateau_map(80, 3), [20, 60], [70, 71])):
         F, Tt = O.computeTmap(c, g), O.computeTmap(c, g, s)
         rank = emu._ranks(F)

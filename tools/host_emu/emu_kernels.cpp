@@ -4,6 +4,7 @@
 //
 //   g++ -O1 -g -std=c++17 -DFMB_HOST_EMU -ffp-contract=off -fPIC -shared \
 //       -I tools/host_emu -o tools/host_emu/libfm_emu.so tools/host_emu/emu_kernels.cpp
+#include <algorithm>
 #include "cuda_emu.h"
 
 #include "../../planning_motion_planning_b200/csrc/eikonal2d.cuh"
@@ -162,6 +163,34 @@ static int emu_tie_order(fmb::Grid<D> g, const double *T, const double *cost, co
     return scratch[2 * n + 1];
 }
 
+// dense replay (as fmb_truncate*_f64), or -- FMB_REPLAY_SPARSE=1 -- the sparse one as truncate_dk runs it: cone expansion (two
+// grid-wide rounds, then the one-block tail), tickets from the cell side, sorted, list sweep.  Returns the waits at the
+// limit, or -1 when the sparse form reported failure.
+template <int D>
+int emu_truncate(fmb::Grid<D> g, const double *F, const double *cost, const int *rank, int k, double *out) {
+    constexpr int NN = fmb::Grid<D>::NN;
+    const size_t n = (size_t)g.size();
+    std::vector<int> list(n); int counters[64] = {0};
+    std::vector<double> memo(n * NN);
+    emu::launch(4, 64, 0, [&] { fmb::truncate_mark_kernel<double, D>(g, F, rank, k, out, list.data()); });
+    if (!(getenv("FMB_REPLAY_SPARSE") && atoi(getenv("FMB_REPLAY_SPARSE")))) {
+        memset(memo.data(), 0xff, memo.size() * sizeof(double));   // as fmb_truncate2d_f64 does
+        emu::launch(4, 64, 0, [&] { fmb::truncate_sweep_kernel<double, D>(g, F, cost, rank, list.data(), k, out, memo.data(), counters, counters + 1); });
+        return counters[1];
+    }
+    std::vector<int> need(n), fa(n), fb(n), tickets(n * NN, fmb::CONE_TICKET_PAD);
+    const int cap = (int)n, grid_rounds = 2;
+    const int *kd = &k;
+    emu::launch(4, 64, 0, [&] { fmb::cone_seed_kernel<double, D>(g, cost, rank, kd, need.data(), fa.data(), counters, cap); });
+    for (int r = 0; r < grid_rounds; ++r)
+        emu::launch(4, 64, 0, [&] { fmb::cone_expand_kernel<double, D>(g, cost, rank, kd, need.data(), (r & 1) ? fb.data() : fa.data(), (r & 1) ? fa.data() : fb.data(), counters, r, cap); });
+    emu::launch(1, 128, 16, [&] { fmb::cone_tail_kernel<double, D>(g, cost, rank, kd, need.data(), fa.data(), fb.data(), counters, grid_rounds, cap, 1 << 16); });
+    emu::launch(4, 64, 0, [&] { fmb::cone_emit_kernel<double, D>(g, rank, kd, need.data(), tickets.data(), memo.data(), counters, (int)tickets.size()); });
+    std::sort(tickets.begin(), tickets.end());
+    emu::launch(4, 64, 0, [&] { fmb::truncate_sweep_list_kernel<double, D>(g, F, cost, rank, list.data(), out, memo.data(), tickets.data(), counters, kd, (int)tickets.size()); });
+    return counters[5] ? -1 : counters[1];
+}
+
 extern "C" {
 
 int emu_solve2d_f64(const double *cost, long long cost_qstride, double *T, int rows, int cols, int nq, const int *seeds,
@@ -220,19 +249,11 @@ void emu_trace3d_f64(const double *T, int ny, int nx, int nz, int npaths, const 
 
 int emu_truncate2d_f64(const double *F, const double *cost, const int *rank, int rows, int cols, int k, double *out) {
     fmb::Grid<2> g; g.rows = rows; g.cols = cols;
-    std::vector<int> list((size_t)rows * cols); int counters[2] = {0, 0};
-    std::vector<double> memo((size_t)rows * cols * 4); memset(memo.data(), 0xff, memo.size() * sizeof(double));   // as fmb_truncate2d_f64 does
-    emu::launch(4, 64, 0, [&] { fmb::truncate_mark_kernel<double, 2>(g, F, rank, k, out, list.data()); });
-    emu::launch(4, 64, 0, [&] { fmb::truncate_sweep_kernel<double, 2>(g, F, cost, rank, list.data(), k, out, memo.data(), counters, counters + 1); });
-    return counters[1];
+    return emu_truncate<2>(g, F, cost, rank, k, out);
 }
 int emu_truncate3d_f64(const double *F, const double *cost, const int *rank, int ny, int nx, int nz, int k, double *out) {
     fmb::Grid<3> g; g.ny = ny; g.nx = nx; g.nz = nz;
-    std::vector<int> list((size_t)ny * nx * nz); int counters[2] = {0, 0};
-    std::vector<double> memo((size_t)ny * nx * nz * 6); memset(memo.data(), 0xff, memo.size() * sizeof(double));
-    emu::launch(4, 64, 0, [&] { fmb::truncate_mark_kernel<double, 3>(g, F, rank, k, out, list.data()); });
-    emu::launch(4, 64, 0, [&] { fmb::truncate_sweep_kernel<double, 3>(g, F, cost, rank, list.data(), k, out, memo.data(), counters, counters + 1); });
-    return counters[1];
+    return emu_truncate<3>(g, F, cost, rank, k, out);
 }
 
 void emu_pow2(const double *x, double *out, long long n) { for (long long i = 0; i < n; ++i) out[i] = fmb::pow2_glibc(x[i]); }
