@@ -357,6 +357,8 @@ def own_arm(args):
                 ev_traced2[f][b].record(s_solve[f])
         for k in range(K_):
             f, b = k % NF, (k // NF) & 1
+            if f == 0:          # a wave of min(NF, what is left) solves shares the resident CTA slots
+                _capi.set_options(concurrent_solves=min(NF, K_ - k))
             with torch.cuda.stream(s_solve[f]):
                 s_solve[f].wait_event(ev_traced2[f][b])          # the trace that last read this buffer is done
                 engine.solve2d(cost_d, seeds_d, out=T_bufs[f][b], nq=1, sync=False)
@@ -482,6 +484,8 @@ def own_arm(args):
         for k in range(K_):
             f, j = k % NF, k // NF
             b = j & 1
+            if f == 0:
+                _capi.set_options(concurrent_solves=min(NF, K_ - k))
             with torch.cuda.stream(s_solve[f]):
                 s_solve[f].wait_event(ev_in[f][b])
                 s_solve[f].wait_event(ev_T_out[f][b])   # download and trace of this lane's step j-2 are done with the buffer

@@ -12,6 +12,7 @@ No CPU fallback: without CUDA or the library every call raises.
 from __future__ import annotations
 
 import ctypes as C
+import functools
 import math
 
 import numpy as np
@@ -43,9 +44,12 @@ def _frame(alpha, beta, gamma, p):
             -sb, cb * sg, cb * cg, p[2]]
 
 
-def _tables(rlim, rO, rm, gamma2D, resX, resZ, heading):
-    """Everything of TunnelCost that does not depend on the voxel grid, as the reference computes it
-    (numpy scalars from np.linspace, ``**2`` on scalars, math.sqrt / cos / sin)."""
+@functools.lru_cache(maxsize=8)
+def _static_tables(rlim, rO, rm, resX, resZ):
+    """The part of TunnelCost's tables that depends on the arm and the grid resolution only -- not on the base path --
+    as the reference computes it (numpy scalars from np.linspace, ``**2`` on scalars = libm pow, math.sqrt / cos / sin).
+    A pure function of five floats: cached, a planner that re-plans with the same arm pays the Python loops once
+    (2.7 ms of a 3.2 ms call at 256^3)."""
     tunnelRad = rlim + 2 * resX
     nX = int(round(2 * tunnelRad / resX) + 1)
     nZ = int(round(2 * tunnelRad / resZ) + 1)
@@ -61,16 +65,23 @@ def _tables(rlim, rO, rm, gamma2D, resX, resZ, heading):
             nr = math.sqrt(i2 + k2[b])
             norm[a, b] = nr
             val[a, b] = GRADIENT * (nr - (rO + rm) / 2) ** 2 + 2 + ramp
-    m = gamma2D.shape[0]
-    frames = [_frame(heading[j, 2] - math.pi / 2, heading[j, 1], heading[j, 0], gamma2D[j]) for j in range(m)]
-    frames.append(_frame(heading[m - 1, 2], heading[m - 1, 1], heading[m - 1, 0], gamma2D[m - 1]))      # :649 (no -pi/2)
     lr = np.linspace(0, tunnelRad, round(nZ / 2) + 1, endpoint=True)
     hval = np.array([GRADIENT * (k - (rO + rm) / 2) ** 2 + 2 for k in lr])
     th = [math.pi * i / 180 for i in range(-100, 100, 2)]
     sg = [math.pi * j / 180 for j in range(-90, 90, 2)]
     angles = np.array([math.cos(t) for t in th] + [math.sin(t) for t in th] + [math.cos(s) for s in sg] + [math.sin(s) for s in sg])
-    return dict(li=li, lk=lk, norm=norm, val=val, frames=np.array(frames, dtype=np.float64), lr=lr, hval=hval, angles=angles,
-                shell=rlim + 2 * resZ, nX=nX, nZ=nZ)
+    return dict(li=li, lk=lk, norm=norm, val=val, lr=lr, hval=hval, angles=angles, shell=rlim + 2 * resZ, nX=nX, nZ=nZ)
+
+
+def _tables(rlim, rO, rm, gamma2D, resX, resZ, heading):
+    """Everything of TunnelCost that does not depend on the voxel grid: the cached static tables plus the base frames of
+    this path (math.cos / math.sin per pose, as the reference)."""
+    t = dict(_static_tables(float(rlim), float(rO), float(rm), float(resX), float(resZ)))
+    m = gamma2D.shape[0]
+    frames = [_frame(heading[j, 2] - math.pi / 2, heading[j, 1], heading[j, 0], gamma2D[j]) for j in range(m)]
+    frames.append(_frame(heading[m - 1, 2], heading[m - 1, 1], heading[m - 1, 0], gamma2D[m - 1]))      # :649 (no -pi/2)
+    t["frames"] = np.array(frames, dtype=np.float64)
+    return t
 
 
 _WS = {}
