@@ -57,6 +57,14 @@ template <> struct Grid<2> {
     template <typename real> static __device__ __forceinline__ real update(const real *v, real cost) {
         return eikonal_update<real>(fmin(v[0], v[1]), fmin(v[2], v[3]), cost);
     }
+    // coordinate forms (32-bit, one division per cell): p = {x, y}; step = neighbour i of the cell at p: flat index or -1, q = its coordinates
+    __device__ __forceinline__ void split(int c, int *p) const { p[1] = c / cols; p[0] = c - p[1] * cols; }
+    __device__ __forceinline__ int step(const int *p, int i, int *q) const {
+        q[0] = p[0] + (i == 0 ? -1 : i == 1 ? 1 : 0);
+        q[1] = p[1] + (i == 2 ? -1 : i == 3 ? 1 : 0);
+        const bool in = (unsigned)q[0] < (unsigned)cols && (unsigned)q[1] < (unsigned)rows;
+        return in ? q[1] * cols + q[0] : -1;
+    }
 };
 template <> struct Grid<3> {
     int ny, nx, nz;
@@ -78,6 +86,18 @@ template <> struct Grid<3> {
     }
     template <typename real> static __device__ __forceinline__ real update(const real *v, real cost) {
         return solve3d_update<real>(v[0] < v[1] ? v[0] : v[1], v[2] < v[3] ? v[2] : v[3], v[4] < v[5] ? v[4] : v[5], cost);
+    }
+    // coordinate forms: p = {x, y, z}
+    __device__ __forceinline__ void split(int c, int *p) const {
+        const int r = c / nz;
+        p[2] = c - r * nz; p[1] = r / nx; p[0] = r - p[1] * nx;
+    }
+    __device__ __forceinline__ int step(const int *p, int i, int *q) const {
+        q[0] = p[0] + (i == 0 ? -1 : i == 1 ? 1 : 0);
+        q[1] = p[1] + (i == 2 ? -1 : i == 3 ? 1 : 0);
+        q[2] = p[2] + (i == 4 ? -1 : i == 5 ? 1 : 0);
+        const bool in = (unsigned)q[0] < (unsigned)nx && (unsigned)q[1] < (unsigned)ny && (unsigned)q[2] < (unsigned)nz;
+        return in ? (q[1] * nx + q[0]) * nz + q[2] : -1;
     }
 };
 
@@ -240,47 +260,52 @@ __global__ void cone_seed_kernel(Grid<D> g, const real *cost, const int *rank, c
     }
 }
 
-// expands one frontier cell: every needed relaxation of c reads the tentative neighbours of that moment.  All ranks the
-// decisions need (the neighbours' and the neighbours' neighbours') are loaded up front -- one memory latency per cell
-// instead of one per decision: the tail of the expansion is a chain of hundreds of rounds of a few cells each.
-template <typename real, int D>
-__device__ __forceinline__ void cone_expand_cell(const Grid<D> &g, const real *cost, const int *rank, int *need_t, long long c,
-                                                 int *fout, int *n_out, int cap, int *fail) {
+// expands one frontier cell: every needed relaxation of c (those up to moment t) reads the tentative neighbours of that
+// moment.  All ranks the decisions need (the neighbours' and the neighbours' neighbours') are loaded up front -- one
+// memory latency per cell instead of one per decision: the tail of the expansion is a chain of hundreds of rounds of a
+// few cells each.  push(cell, bound) receives every cell whose bound this call raised.
+template <typename real, int D, typename Push>
+__device__ __forceinline__ void cone_expand_cell(const Grid<D> &g, const real *cost, const int *rank, int *need_t, long long c, int t,
+                                                 Push push) {
     constexpr int NN = Grid<D>::NN;
     const real INF = num<real>::inf();
-    const int t = *reinterpret_cast<volatile int *>(&need_t[c]);
-    long long nb[NN];
-    int rn[NN], r2[NN][NN];
+    int nb[NN], rn[NN], r2[NN][NN];
     bool open[NN];
+    int pc[3], pn[3], pq[3];
+    g.split((int)c, pc);                           // (cells < 2^31: truncate_dk's guard) one division per cell, the rest by coordinates
 #pragma unroll
     for (int i = 0; i < NN; ++i) {
-        nb[i] = g.nbr(c, i);
+        nb[i] = g.step(pc, i, pn);
         rn[i] = nb[i] >= 0 ? rank[nb[i]] : -1;
         open[i] = nb[i] >= 0 && cost[nb[i]] < INF;
 #pragma unroll
         for (int q = 0; q < NN; ++q) {
-            const long long m2 = nb[i] >= 0 ? g.nbr(nb[i], q) : -1;
+            const int m2 = nb[i] >= 0 ? g.step(pn, q, pq) : -1;
             r2[i][q] = m2 >= 0 ? rank[m2] : 0x7fffffff;
         }
     }
+    // per neighbour the latest bound any needed relaxation of c asks of it (one atomic per neighbour, all of them in
+    // flight before the first result is looked at)
+    int want[NN], old[NN];
 #pragma unroll
-    for (int j = 0; j < NN; ++j) {
-        if (nb[j] < 0) continue;
-        const int r = rn[j];
-        if (r > t) continue;                                   // not a relaxation of c that is needed
+    for (int i = 0; i < NN; ++i) {
+        want[i] = -1;
 #pragma unroll
-        for (int i = 0; i < NN; ++i) {
-            if (nb[i] < 0 || rn[i] <= r || !open[i]) continue;                 // accepted by then (final value) / obstacle
+        for (int j = 0; j < NN; ++j) {
+            const int r = rn[j];
+            const bool event = nb[j] >= 0 && r <= t;           // a relaxation of c that is needed
+            const bool tentative = nb[i] >= 0 && rn[i] > r && open[i];         // not accepted by then, no obstacle
             int tm = -1;                                       // the neighbour's last relaxation before that moment
 #pragma unroll
             for (int q = 0; q < NN; ++q) tm = (r2[i][q] <= r && r2[i][q] > tm) ? r2[i][q] : tm;
-            if (tm < 0) continue;                              // never touched before: +inf
-            if (atomicMax(&need_t[nb[i]], tm) < tm) {
-                const int pos = atomicAdd(n_out, 1);
-                if (pos < cap) fout[pos] = (int)nb[i]; else *fail = 1;
-            }
+            want[i] = (event && tentative && tm > want[i]) ? tm : want[i];
         }
     }
+#pragma unroll
+    for (int i = 0; i < NN; ++i) old[i] = want[i] >= 0 ? atomicMax(&need_t[nb[i]], want[i]) : 0x7fffffff;
+#pragma unroll
+    for (int i = 0; i < NN; ++i)
+        if (old[i] < want[i]) push(nb[i], want[i]);
 }
 
 // the first rounds of the expansion, grid-wide (thousands of cells per round) ...
@@ -289,29 +314,52 @@ __global__ void cone_expand_kernel(Grid<D> g, const real *cost, const int *rank,
                                    const int *fin, int *fout, int *counters, int round, int cap) {
     if (*k_dev >= g.size()) return;
     const int n_in = min(counters[8 + round], cap);
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_in; idx += gridDim.x * blockDim.x)
-        cone_expand_cell<real, D>(g, cost, rank, need_t, fin[idx], fout, &counters[8 + round + 1], cap, &counters[5]);
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_in; idx += gridDim.x * blockDim.x) {
+        const long long c = fin[idx];
+        cone_expand_cell<real, D>(g, cost, rank, need_t, c, *reinterpret_cast<volatile int *>(&need_t[c]), [&](int m, int) {
+            const int pos = atomicAdd(&counters[8 + round + 1], 1);
+            if (pos < cap) fout[pos] = m; else counters[5] = 1;
+        });
+    }
 }
 // ... and its long thin tail (tens of cells per round for hundreds of rounds: the chains that run along the front) in
-// ONE block that loops over the rounds with a block barrier instead of a launch per round
+// ONE block that loops over the rounds with a block barrier instead of a launch per round.  The first CONE_SMEM_CAP
+// entries of a frontier (cell, bound) live in shared memory, the rest (cells only) spill to the global lists: a round
+// of the tail then costs two global round trips (the ranks, the atomic), not four.
+constexpr int CONE_SMEM_CAP = 2048;
+constexpr int CONE_TAIL_SMEM = 16 + 2 * CONE_SMEM_CAP * 8;
 template <typename real, int D>
 __global__ void __launch_bounds__(1024) cone_tail_kernel(Grid<D> g, const real *cost, const int *rank, const int *k_dev, int *need_t,
-                                 int *fa, int *fb, int *counters, int first_round, int cap, int max_rounds) {
-    FMB_DYN_SMEM(smem_raw);                        // two ints: the sizes of the current and of the next frontier
+                                                         int *fa, int *fb, int *counters, int first_round, int cap, int max_rounds) {
+    FMB_DYN_SMEM(smem_raw);
     int &s_in = reinterpret_cast<int *>(smem_raw)[0], &s_out = reinterpret_cast<int *>(smem_raw)[1];
+    int2 *sin_ = reinterpret_cast<int2 *>(smem_raw + 16), *sout = sin_ + CONE_SMEM_CAP;
     if (*k_dev >= g.size()) return;
-    int *fin = (first_round & 1) ? fb : fa, *fout = (first_round & 1) ? fa : fb;
+    int *gin = (first_round & 1) ? fb : fa, *gout = (first_round & 1) ? fa : fb;
     if (threadIdx.x == 0) { s_in = min(counters[8 + first_round], cap); s_out = 0; }
     __syncthreads();
-    int rounds = 0;
+    int rounds = 0, in_smem = 0;                   // entries of the input frontier that sit in shared memory
     for (; rounds < max_rounds; ++rounds) {
         const int n_in = s_in;
         if (n_in == 0) break;
-        for (int idx = threadIdx.x; idx < n_in; idx += blockDim.x)
-            cone_expand_cell<real, D>(g, cost, rank, need_t, fin[idx], fout, &s_out, cap, &counters[5]);
+        for (int idx = threadIdx.x; idx < n_in; idx += blockDim.x) {
+            int c, t;
+            if (idx < in_smem) { c = sin_[idx].x; t = sin_[idx].y; }
+            else { c = gin[idx - in_smem]; t = *reinterpret_cast<volatile int *>(&need_t[c]); }
+            cone_expand_cell<real, D>(g, cost, rank, need_t, c, t, [&](int m, int tm) {
+                const int pos = atomicAdd(&s_out, 1);
+                if (pos < CONE_SMEM_CAP) sout[pos] = make_int2(m, tm);
+                else if (pos - CONE_SMEM_CAP < cap) gout[pos - CONE_SMEM_CAP] = m;
+                else counters[5] = 1;
+            });
+        }
         __syncthreads();
-        if (threadIdx.x == 0) { s_in = min(s_out, cap); s_out = 0; }
-        int *tmp = fin; fin = fout; fout = tmp;
+        const int n_out = s_out;
+        __syncthreads();
+        if (threadIdx.x == 0) { s_in = min(n_out, cap); s_out = 0; }
+        in_smem = min(n_out, CONE_SMEM_CAP);
+        int2 *ts = sin_; sin_ = sout; sout = ts;
+        int *tg = gin; gin = gout; gout = tg;
         __syncthreads();
     }
     if (threadIdx.x == 0) {

@@ -229,6 +229,8 @@ inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline double __longlong_as_double(long long v) { return emu_unbits<double>((uint64_t)v); }
 inline float __int_as_float(int v) { float f; memcpy(&f, &v, 4); return f; }
 
+struct int2 { int x, y; };
+inline int2 make_int2(int x, int y) { int2 r; r.x = x; r.y = y; return r; }
 struct double2 { double x, y; };
 inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
 inline int __double2hiint(double v) { return (int)(emu_bits(v) >> 32); }

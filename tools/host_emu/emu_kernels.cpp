@@ -184,7 +184,7 @@ int emu_truncate(fmb::Grid<D> g, const double *F, const double *cost, const int 
     emu::launch(4, 64, 0, [&] { fmb::cone_seed_kernel<double, D>(g, cost, rank, kd, need.data(), fa.data(), counters, cap); });
     for (int r = 0; r < grid_rounds; ++r)
         emu::launch(4, 64, 0, [&] { fmb::cone_expand_kernel<double, D>(g, cost, rank, kd, need.data(), (r & 1) ? fb.data() : fa.data(), (r & 1) ? fa.data() : fb.data(), counters, r, cap); });
-    emu::launch(1, 128, 16, [&] { fmb::cone_tail_kernel<double, D>(g, cost, rank, kd, need.data(), fa.data(), fb.data(), counters, grid_rounds, cap, 1 << 16); });
+    emu::launch(1, 128, fmb::CONE_TAIL_SMEM, [&] { fmb::cone_tail_kernel<double, D>(g, cost, rank, kd, need.data(), fa.data(), fb.data(), counters, grid_rounds, cap, 1 << 16); });
     emu::launch(4, 64, 0, [&] { fmb::cone_emit_kernel<double, D>(g, rank, kd, need.data(), tickets.data(), memo.data(), counters, (int)tickets.size()); });
     std::sort(tickets.begin(), tickets.end());
     emu::launch(4, 64, 0, [&] { fmb::truncate_sweep_list_kernel<double, D>(g, F, cost, rank, list.data(), out, memo.data(), tickets.data(), counters, kd, (int)tickets.size()); });
