@@ -844,6 +844,10 @@ def own_arm(args):
                                                   "is traced while the next query of its lane solves"},
             "latency_ms_one_query": init_ms + solve_ms + trace_ms,
             "breakdown_ms": {"init_fill": init_ms, "solve_kernel": solve_ms, "trace_kernel": trace_ms},
+            "resident_loop": {"inflight": NF, "streams_per_lane": 2,
+                              "concurrent_solves": "fmb_options.concurrent_solves = min(inflight, queries left in the wave): each solve's persistent "
+                                                   "grid takes that share of the resident CTA slots; reset to 0 (one solve alone: two CTAs per SM) "
+                                                   "for solve_kernel_ms / latency_ms_one_query / the plugin-call e2e"},
             "solver_stats": {k: stats[k] for k in ("tile_visits", "steps", "evals", "pushes", "cells_written")},
             "evals_per_cell": stats["evals"] / cells,
             "roofline": roofline, "e2e": e2e, "e2e_pipelined": e2e_pipelined, "planner_call": bi, "cpu_baseline": cpu, "batch": batch, "batch_sharded": sharded, "volume3d": vol, "costmap2d": cmap, "costvolume3d": cvol,

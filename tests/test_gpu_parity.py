@@ -216,16 +216,19 @@ def test_windowed_order_reaches_the_same_field(eng, window, engine, fmb_opts):
     assert eng.last_stats()["deferrals"] >= 0
 
 
-def test_concurrent_solves_on_separate_streams(eng):
+@pytest.mark.parametrize("share", [0, 3])
+def test_concurrent_solves_on_separate_streams(eng, share, fmb_opts):
     """Three independent queries in flight on their own streams (what bench.py does): each lane has its
     own workspace, the results equal the one-at-a-time results bit for bit in their inf pattern and to
-    rounding in value (iteration order differs run to run)."""
+    rounding in value (iteration order differs run to run) -- with the default grid per solve and with
+    fmb_options.concurrent_solves = 3 (a third of the resident CTA slots each)."""
     import torch
     from planning_motion_planning_b200 import synth
     c = synth.mars_costmap(2048, 5)
     cd = torch.from_numpy(c).cuda()
     goals = [list(synth.free_cell_near(c, 300, 300)), list(synth.free_cell_near(c, 1700, 400)), list(synth.free_cell_near(c, 1000, 1800))]
     serial = [eng.solve2d(cd, [g]).clone() for g in goals]
+    fmb_opts(concurrent_solves=share)
     streams = [torch.cuda.Stream() for _ in goals]
     outs = [torch.empty((1, 2048, 2048), dtype=torch.float64, device="cuda") for _ in goals]
     torch.cuda.synchronize()
