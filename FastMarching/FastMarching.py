@@ -63,7 +63,21 @@ def computeTmap(costMap, goal, start):
     rank[start] pops.  start == goal, or an unreached / outside start: the FULL field (the goal is closed before the
     loop and never popped, FastMarching3D.py:127-142).
     """
-    cd, swap, (g, s), dev = _device_map(costMap, [goal, start])
+    c, swap = _c.as_c_field(costMap)
+    c = np.ascontiguousarray(c)
+    rows, cols = c.shape
+    g, s = _c.node2(goal, swap), _c.node2(start, swap)
+    _c.check_node2(g, rows, cols)
+    dev = _c.device()
+    pinned = _c.is_page_locked(c)
+    full = g == s or not (0 <= s[0] < cols and 0 <= s[1] < rows)          # known on the host: the loop never stops early
+    if full and pinned and _c.H2D_OVERLAP:
+        # the map's upload runs in bands behind the solve that already consumes it (fmb_solve2d_h2d_f64)
+        T, ws = _c.solve2d_h2d(c, g, dev)
+        out = _to_numpy_field(T, swap)                  # synchronises
+        _c.finish(ws, dev)
+        return out
+    cd = _c.to_device(c, dev, pinned=pinned)
     T, info, ws = _c.solve2d_until(cd, g, s, swap)
     out = _to_numpy_field(T, swap)                      # synchronises
     _c.finish(ws, dev)

@@ -2,6 +2,7 @@
 emulation of the reference's early-exit ("partial field") semantics."""
 from __future__ import annotations
 
+import os
 import weakref
 
 import numpy as np
@@ -29,17 +30,26 @@ def device() -> torch.device:
 # pinned tensor whose memory backs the returned NumPy array (owned by the caller through the array's base).  An array
 # that came from here is recognised as pinned on its way back in (getPathGDM on a field biComputeTmap returned) and
 # uploaded with one DMA.
+# fmb_solve2d_h2d_f64 (upload overlapped with the solve) can be switched off, e.g. under a profiler that replays kernels
+# and restores device memory in between (the solve waits on flags the copy stream sets): FMB_H2D_OVERLAP=0
+H2D_OVERLAP = os.environ.get("FMB_H2D_OVERLAP", "1") != "0"
 _STAGE = {}
 _STAGE_ELEMS = 2 << 20            # 16 MiB of float64 per staging buffer
 _STAGE_BUFS = 4
 
 
-def to_device(a: np.ndarray, dev: torch.device) -> torch.Tensor:
-    """C-contiguous float64 NumPy array -> device tensor of the same shape."""
+def is_page_locked(a: np.ndarray) -> bool:
+    """True for an array this module returned and for a caller's array it has page-locked (a second sighting does that)."""
+    return a.size >= (1 << 18) and (_is_ours(a) or _page_locked_on_reuse(a))
+
+
+def to_device(a: np.ndarray, dev: torch.device, pinned=None) -> torch.Tensor:
+    """C-contiguous float64 NumPy array -> device tensor of the same shape (pinned: is_page_locked(a), when the caller
+    already asked)."""
     t = torch.from_numpy(a)
     if a.size < (1 << 18):
         return t.to(dev)
-    if _is_ours(a) or _page_locked_on_reuse(a):         # a field this module returned / a caller's array seen before: one DMA
+    if is_page_locked(a) if pinned is None else pinned:         # one DMA
         return t.to(dev, non_blocking=True)
     out = torch.empty(a.shape, dtype=torch.float64, device=dev)
     flat_src, flat_dst = t.reshape(-1), out.reshape(-1)
@@ -364,6 +374,22 @@ def bisolve2d(cd: torch.Tensor, goal, start, transposed: bool):
                                         out[0].data_ptr(), out[1].data_ptr(), info.data_ptr(), ws.data_ptr(), ws.numel(),
                                         cur.cuda_stream, side.cuda_stream))
     return out[0], out[1], info, ws
+
+
+def solve2d_h2d(c: np.ndarray, goal, dev: torch.device):
+    """fmb_solve2d_h2d_f64: the full field of the page-locked host map `c`, its upload (bands of rows, nearest to the goal
+    first, on the side stream) overlapped with the solve.  Returns (T on the device, workspace)."""
+    rows, cols = c.shape
+    L = _capi.lib()
+    ws = _ws(L.fmb_workspace_bytes_2d_h2d(rows, cols), dev, "h2d")
+    cd = torch.empty((rows, cols), dtype=torch.float64, device=dev)
+    out = torch.empty((rows, cols), dtype=torch.float64, device=dev)
+    cur, side = torch.cuda.current_stream(dev), _side_stream(dev)
+    with torch.cuda.device(dev):
+        _capi.check(L.fmb_solve2d_h2d_f64(c.ctypes.data, cd.data_ptr(), rows, cols, _i32(goal), out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                          cur.cuda_stream, side.cuda_stream))
+    cd.record_stream(side)
+    return out, ws
 
 
 def solve2d_until(cd: torch.Tensor, goal, start, transposed: bool):

@@ -146,6 +146,17 @@ int fmb_solve2d_f32(const float *d_cost, int64_t cost_pitch, int64_t cost_qstrid
                     int rows, int cols, int nq, const int32_t *d_seeds,
                     void *d_ws, size_t ws_bytes, void *stream);
 
+/* One 2D solve whose cost map is still on the host: the upload runs on `copy_stream` in bands of rows ordered by their
+ * distance from the goal while the solve already runs on `stream` (its CTAs wait per band on device flags the copy stream
+ * sets; every copy is queued before the kernel, so nothing waits for work queued behind it).  h_cost: dense [rows][cols]
+ * PAGE-LOCKED host memory (FMB_E_INVALID otherwise); d_cost: device buffer of the same shape, complete when `stream`
+ * reaches the end of the call's work; goal_xy: HOST int32[2].  Replaces "upload, then FastMarching.computeTmap's full
+ * field" of the drop-in (FastMarching.py:92-112 as intended) when the caller's map is page-locked: 4096^2 on B200 hides
+ * the 2.5 ms upload behind the 7.3 ms solve.  d_ws: fmb_workspace_bytes_2d_h2d bytes; fmb_finish(d_ws, ...) as usual. */
+size_t fmb_workspace_bytes_2d_h2d(int rows, int cols);
+int fmb_solve2d_h2d_f64(const double *h_cost, double *d_cost, int rows, int cols, const int32_t *goal_xy, double *d_T,
+                        void *d_ws, size_t ws_bytes, void *stream, void *copy_stream);
+
 /* Resume a single 2D solve from the CURRENT contents of d_T (no re-initialisation): used by the
  * row-slab domain decomposition of very large maps, where halo rows received from the neighbour
  * slabs are written into d_T between calls (they carry cost = +inf locally, so they are inputs

@@ -49,6 +49,10 @@ struct Problem2D {
     double hop_frac;         // second-ring wait rule: slack[1] = hop_frac x the same scale (<= 0: rule off)
     int win_running;         // 1: a tile keeps its level count while it RUNS (released when it finishes), so the
                              //    window is measured from the lowest queued-or-running level
+    // sweep engine, one map, cost map still being uploaded while the solve runs (fmb_solve2d_h2d_f64): band b of
+    // 2^band_shift rows has arrived once band_ready[b] != 0 (written by the copy stream after the band's DMA)
+    const int *band_ready = nullptr;
+    int band_shift = 0;
 };
 constexpr int WIN_LEVELS = 8192;
 __device__ __forceinline__ int win_level(unsigned long long pbits, double inv_delta) {

@@ -144,6 +144,22 @@ __global__ void __launch_bounds__(128, FMB_SWEEP2D_MINB) solve2d_sweep_kernel(Pr
         const real *cq = P.cost + (long long)q * P.cost_qstride;
         real *Tq = P.T + (long long)q * P.T_qstride;
 
+        // ---- the cost map may still be arriving (fmb_solve2d_h2d_f64): wait for the band of rows this tile lies in ----
+        if (P.band_ready) {
+            if (tid == 0) {
+                int gone = 0;
+                const long long t0 = clock64();
+                while (ld_acquire_sys(&P.band_ready[y0 >> P.band_shift]) == 0) {
+                    if (ld_volatile(&P.q.ctl->abort)) { gone = 1; break; }
+                    if (clock64() - t0 > P.q.watchdog_cycles) { atomicCAS(&P.q.ctl->abort, 0, DEV_WATCHDOG); gone = 1; break; }
+                    __nanosleep(200);
+                }
+                sCtl[1] = gone;
+            }
+            __syncthreads();
+            if (sCtl[1]) break;                    // aborted while waiting
+        }
+
         // ---- stage tile + halo (cp.async.cg for interior aligned tiles, bounds-checked loads otherwise) ----
         {
             constexpr int EPC = 16 / (int)sizeof(real);

@@ -367,7 +367,7 @@ int launch_solve2d_wsweep(fmb::Problem2D<real> P, const WsLayout &L, cudaStream_
 template <typename real>
 int solve2d(const real *d_cost, int64_t cost_pitch, int64_t cost_qstride, real *d_T, int64_t T_pitch,
             int64_t T_qstride, int rows, int cols, int nq, const int32_t *d_seeds, void *d_ws, size_t ws_bytes,
-            void *stream, int resume_activate = -1, int arm_rows = 0) {
+            void *stream, int resume_activate = -1, int arm_rows = 0, const int *band_ready = nullptr, int band_shift = 0) {
     if (!d_cost || !d_T || !d_seeds || !d_ws) return fail(FMB_E_INVALID, "null pointer argument%s");
     if (rows < 1 || cols < 1 || nq < 1) return fail(FMB_E_INVALID, "rows, cols and nq must be positive%s");
     if (cost_pitch < cols || T_pitch < cols) return fail(FMB_E_INVALID, "pitch smaller than cols%s");
@@ -430,6 +430,9 @@ int solve2d(const real *d_cost, int64_t cost_pitch, int64_t cost_qstride, real *
     // 7.0 ms with the straight-line sweep step as well (510 -> 376 cycles per step) and two check passes instead of four
     P.hop_frac = O.ring2 > 0 ? 0.01 * O.ring2 : (O.ring2 < 0 ? 0.0 : 2.0);
     P.variant = O.variant > 0 ? O.variant : (O.variant < 0 ? 0 : 3);
+    P.band_ready = band_ready; P.band_shift = band_shift;
+    if (band_ready && !(engine == 3 && !P.best_first && nq == 1 && resume_activate < 0))
+        return fail(FMB_E_INVALID, "a solve on a cost map that is still arriving needs the sweep engine on one map%s");
     P.slack_frac = O.causal_slack > 0 ? 0.01 * O.causal_slack : 0.0;      // measured 4096^2: 10.4 / 10.6 / 11.9 / 15.9 ms at 0 / 25 / 50 / 100 %
     cudaStream_t st = (cudaStream_t)stream;
     if (engine >= 4 && resume_activate < 0) {
@@ -536,6 +539,74 @@ int fmb_solve2d_f32(const float *d_cost, int64_t cost_pitch, int64_t cost_qstrid
                     size_t ws_bytes, void *stream) {
     return solve2d<float>(d_cost, cost_pitch, cost_qstride, d_T, T_pitch, T_qstride, rows, cols, nq, d_seeds, d_ws,
                           ws_bytes, stream);
+}
+
+// ---- upload of the cost map overlapped with the solve --------------------------------------------------------------
+namespace {
+int band_shift_for(int rows) {              // ~16 bands, a power of two of at least 32 rows (tile rows never straddle a band)
+    int sh = 5;
+    while ((rows >> sh) > 16) ++sh;
+    return sh;
+}
+int *pinned_one() {
+    static int *one = nullptr;
+    if (!one) { if (cudaHostAlloc((void **)&one, sizeof(int), cudaHostAllocDefault) != cudaSuccess) { one = nullptr; cudaGetLastError(); } else *one = 1; }
+    return one;
+}
+}  // namespace
+size_t fmb_workspace_bytes_2d_h2d(int rows, int cols) {
+    if (rows < 1 || cols < 1) return 0;
+    return ((fmb_workspace_bytes_2d(rows, cols, 1) + 255) & ~(size_t)255) + 256 + 4 * (size_t)((rows >> 5) + 2) + 256;
+}
+int fmb_solve2d_h2d_f64(const double *h_cost, double *d_cost, int rows, int cols, const int32_t *goal_xy, double *d_T,
+                        void *d_ws, size_t ws_bytes, void *stream, void *copy_stream) {
+    if (!h_cost || !d_cost || !goal_xy || !d_T || !d_ws || !copy_stream) return fail(FMB_E_INVALID, "null pointer argument%s");
+    if (rows < 1 || cols < 1) return fail(FMB_E_INVALID, "bad shape%s");
+    if (goal_xy[0] < 0 || goal_xy[0] >= cols || goal_xy[1] < 0 || goal_xy[1] >= rows) return fail(FMB_E_INVALID, "goal outside the map%s");
+    if (ws_bytes < fmb_workspace_bytes_2d_h2d(rows, cols)) return fail(FMB_E_WORKSPACE, "workspace too small%s");
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, h_cost) != cudaSuccess || pa.type != cudaMemoryTypeHost) {
+        cudaGetLastError();
+        return fail(FMB_E_INVALID, "h_cost must be page-locked host memory (cudaHostAlloc / cudaHostRegister)%s");
+    }
+    int *one = pinned_one();
+    if (!one) return fail(FMB_E_CUDA, "cudaHostAlloc(flag source) failed%s");
+    cudaStream_t st = (cudaStream_t)stream, cs = (cudaStream_t)copy_stream;
+    char *ws = (char *)d_ws;
+    const size_t solve_bytes = fmb_workspace_bytes_2d(rows, cols, 1);
+    size_t o = (solve_bytes + 255) & ~(size_t)255;
+    int32_t *seeds = (int32_t *)(ws + o); o += 256;
+    int *flags = (int *)(ws + o);
+    const int sh = band_shift_for(rows), band_rows = 1 << sh, nb = (rows + band_rows - 1) >> sh;
+    const int gb = goal_xy[1] >> sh;
+    cudaEvent_t e0, e1, e2;
+    CK(cudaEventCreateWithFlags(&e0, cudaEventDisableTiming), "cudaEventCreate");
+    CK(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming), "cudaEventCreate");
+    CK(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming), "cudaEventCreate");
+    // Every copy and every flag write is queued BEFORE the solve is launched: where streams do not overlap (a serialising
+    // profiler, CUDA_LAUNCH_BLOCKING) the kernel then finds all flags set instead of waiting for work queued behind it.
+    CK(cudaMemsetAsync(flags, 0, sizeof(int) * (size_t)nb, st), "cudaMemsetAsync(band flags)");
+    CK(cudaMemcpyAsync(seeds, goal_xy, 2 * sizeof(int32_t), cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(seeds)");
+    CK(cudaEventRecord(e0, st), "cudaEventRecord");
+    CK(cudaStreamWaitEvent(cs, e0, 0), "cudaStreamWaitEvent");
+    for (int d = 0; d < nb; ++d) {               // bands by distance from the goal's band: gb, gb + 1, gb - 1, gb + 2, ...
+        for (int sgn = 0; sgn < (d ? 2 : 1); ++sgn) {
+            const int b = sgn ? gb - d : gb + d;
+            if (b < 0 || b >= nb) continue;
+            const int r0 = b << sh, nr = (r0 + band_rows <= rows) ? band_rows : rows - r0;
+            CK(cudaMemcpyAsync(d_cost + (size_t)r0 * cols, h_cost + (size_t)r0 * cols, sizeof(double) * (size_t)nr * cols,
+                               cudaMemcpyHostToDevice, cs), "cudaMemcpyAsync(cost band)");
+            CK(cudaMemcpyAsync(flags + b, one, sizeof(int), cudaMemcpyHostToDevice, cs), "cudaMemcpyAsync(band flag)");
+            if (d == 0) CK(cudaEventRecord(e1, cs), "cudaEventRecord");
+        }
+    }
+    CK(cudaEventRecord(e2, cs), "cudaEventRecord");
+    CK(cudaStreamWaitEvent(st, e1, 0), "cudaStreamWaitEvent");        // the seed kernel reads the cost at the goal
+    int rc = solve2d<double>(d_cost, cols, 0, d_T, cols, (int64_t)rows * cols, rows, cols, 1, seeds, d_ws, solve_bytes, stream, -1, 0,
+                             flags, sh);
+    CK(cudaStreamWaitEvent(st, e2, 0), "cudaStreamWaitEvent");        // d_cost is complete for whatever follows on `stream`
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    return rc;
 }
 
 int fmb_resolve2d_f64(const double *d_cost, int64_t cost_pitch, double *d_T, int64_t T_pitch, int rows, int cols,

@@ -1134,3 +1134,44 @@ def test_branch_free_division_is_correctly_rounded(eng):
         assert int(bad[0]) == 0
         accepted += int(bad[1])
     assert accepted > 25_000_000
+
+
+@pytest.mark.parametrize("shape,goal", [((2048, 2048), [300, 1900]), ((1000, 1100), [1050, 20]), ((97, 130), [5, 90])])
+def test_solve_overlapped_with_the_upload_of_its_cost_map(eng, shape, goal):
+    """fmb_solve2d_h2d_f64: the cost map is uploaded in bands of rows (nearest to the goal first) on a second stream
+    while the solve already runs and waits per band on device flags.  Same field as the solve of the resident map (to
+    rounding: the visit order differs) and as the oracle; the device copy of the map is complete afterwards; a pageable
+    host array is refused."""
+    import ctypes as C
+    import torch
+    from oracle import oracle as O
+    from planning_motion_planning_b200 import _capi, synth
+    L = _capi.lib()
+    rows, cols = shape
+    c = synth.mars_costmap(max(rows, cols), 12)[:rows, :cols].copy() if rows >= 512 else rand_map(shape, 5)
+    c[0, :] = c[-1, :] = c[:, 0] = c[:, -1] = np.inf
+    c[goal[1], goal[0]] = 1.0
+    h = torch.empty(shape, dtype=torch.float64).pin_memory()
+    h.copy_(torch.from_numpy(c))
+    cd = torch.full(shape, float("nan"), dtype=torch.float64, device="cuda")
+    T = torch.empty(shape, dtype=torch.float64, device="cuda")
+    ws = torch.empty(L.fmb_workspace_bytes_2d_h2d(rows, cols), dtype=torch.uint8, device="cuda")
+    side = torch.cuda.Stream()
+    st = torch.cuda.current_stream()
+    g32 = (C.c_int32 * 2)(*goal)
+    for rep in range(3):
+        cd.fill_(float("nan"))
+        _capi.check(L.fmb_solve2d_h2d_f64(h.data_ptr(), cd.data_ptr(), rows, cols, g32, T.data_ptr(), ws.data_ptr(), ws.numel(),
+                                          st.cuda_stream, side.cuda_stream))
+        _capi.check(L.fmb_finish(ws.data_ptr(), ws.numel(), st.cuda_stream, None))
+        assert torch.equal(cd.cpu(), h)                                   # every band arrived
+        got = T.cpu().numpy()
+        if rep == 0:
+            ref = O.computeTmap(c, goal)
+        assert rel_err(got, ref) < TOL64
+    res = eng.solve2d(cd, [goal])[0].cpu().numpy()
+    assert np.array_equal(np.isfinite(res), np.isfinite(got)) and rel_err(got, res) < 1e-12
+    pageable = np.ascontiguousarray(c)
+    rc = L.fmb_solve2d_h2d_f64(pageable.ctypes.data, cd.data_ptr(), rows, cols, g32, T.data_ptr(), ws.data_ptr(), ws.numel(),
+                               st.cuda_stream, side.cuda_stream)
+    assert rc != 0 and b"page-locked" in L.fmb_last_error()
