@@ -112,12 +112,7 @@ def getPathGDM(totalCostMap, initWaypoint, endWaypoint, tau):
     end = np.asarray(endWaypoint, dtype=np.float64).reshape(-1)[:2]
     dev = _c.device()
 
-    def run(Td):
-        # unlike the solver, the tracer is NOT symmetric in x and y (the reference normalises dx
-        # first and reuses it for dy, FastMarching.py:226-227), so an F-ordered field is put back
-        # into [y, x] order on the device instead of tracing in swapped coordinates
-        return engine.trace2d(Td.T.contiguous() if swap else Td, init[None, :], end[None, :], tau)
-    out, count, status = _c.trace_field(np.ascontiguousarray(c), dev, run)
+    out, count, status = _c.trace_field2d(np.ascontiguousarray(c), swap, dev, init, end, tau)
     n, st = int(count[0]), int(status[0])
     _c.raise_trace(st)
     return out[0, :n].cpu().numpy()

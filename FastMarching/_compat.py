@@ -187,6 +187,36 @@ def _device_copy_of(c: np.ndarray):
     return t
 
 
+_LOG_BLOCKS = 4096                 # block log of the 2D tracer (a block per ~30 steps)
+
+
+def trace_field2d(c: np.ndarray, swap: bool, dev: torch.device, init, end, tau):
+    """2D tracer on the C-contiguous host field `c` (swap: the caller's array is its transpose; the tracer is not
+    symmetric in x and y -- the reference normalises dx first and reuses it for dy, FastMarching.py:226-227 -- so an
+    F-ordered field is put back into [y, x] order on the device).  When the device copy `c` was downloaded from is still
+    kept, the path is traced on it at once and the cells it READ -- the windows of its gradient blocks, logged by the
+    tracer -- are compared bitwise with the caller's array, which the comparison kernel reads in place over the bus
+    (fmb_trace2d_logged_f64 + fmb_windows_differ_f64): nothing of the 128 MiB array moves.  A difference (the caller
+    edited the array where the path looked at it) or an overflowing log: upload and trace again."""
+    def run(Td, log=0):
+        Tt = Td.T.contiguous() if swap else Td
+        return Tt, engine.trace2d(Tt, init[None, :], end[None, :], tau, log_blocks=log)
+    cached = _device_copy_of(c)
+    if cached is None:
+        return run(to_device(c, dev))[1]
+    Tt, (out, count, status, blocks, nblocks) = run(cached, _LOG_BLOCKS)
+    rows, cols = Tt.shape
+    hs_y, hs_x = (1, c.shape[1]) if swap else (c.shape[1], 1)          # element (y, x) of the traced field inside `c`
+    flag = torch.empty(1, dtype=torch.int32, device=dev)
+    rc = _capi.lib().fmb_windows_differ_f64(Tt.data_ptr(), cols, rows, cols, c.ctypes.data, hs_y, hs_x, blocks.data_ptr(),
+                                            nblocks.data_ptr(), _LOG_BLOCKS, flag.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+    if rc != 0 or int(flag[0]):            # (rc: the array is not addressable by the device -- compare the slow way)
+        TRACE_STATS["retraced"] += 1
+        return run(to_device(c, dev))[1]
+    TRACE_STATS["reused"] += 1
+    return out, count, status
+
+
 def trace_field(c: np.ndarray, dev: torch.device, run):
     """run(Td) -> (paths, count, status) for the C-contiguous float64 host field `c`; returns what run returns."""
     cached = _device_copy_of(c)

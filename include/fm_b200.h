@@ -340,6 +340,19 @@ size_t fmb_workspace_bytes_pathpost(void);
  * of a field it returned; when the caller hands that array to getPathGDM (Coupled_motion_planner.py:1229-1230) the tracer
  * starts on the copy while the array is uploaded again, and this check decides whether the path may be used. */
 int fmb_fields_differ_f64(const double *d_a, const double *d_b, int64_t n, int32_t *d_flag, void *stream);
+/* The same question without moving the array: fmb_trace2d_logged_f64 = fmb_trace2d_f64 that also logs which cells of the
+ * field the path read (the origin node of every 16 x 16 gradient block it staged: d_blocks [npaths][cap_blocks][2] = bx, by;
+ * d_nblocks[p] = count, cap_blocks + 1 on overflow, -1 for fields too small for blocks), and fmb_windows_differ_f64
+ * compares exactly those 18 x 18 windows of the traced device field with the caller's array, which the kernel reads in
+ * place: h_field = page-locked host memory addressed by the device through the same pointer (cudaHostAlloc under
+ * unified addressing; FMB_E_INVALID otherwise), element (y, x) at h_field[y * hs_y + x * hs_x].  *d_flag = 1 on any
+ * difference, overflow or missing log.  One path (the log of path 0 is used). */
+int fmb_trace2d_logged_f64(const double *d_T, int64_t T_pitch, int64_t T_qstride, int rows, int cols, int npaths,
+                           const int32_t *d_field_of_path, const double *d_init, const double *d_end, double tau,
+                           int max_steps, double *d_out, int64_t cap, int32_t *d_count, int32_t *d_status,
+                           int32_t *d_blocks, int32_t *d_nblocks, int cap_blocks, void *stream);
+int fmb_windows_differ_f64(const double *d_field, int64_t pitch, int rows, int cols, const double *h_field, int64_t hs_y, int64_t hs_x,
+                           const int32_t *d_blocks, const int32_t *d_nblocks, int cap_blocks, int32_t *d_flag, void *stream);
 int fmb_path_stitch2d_f64(const double *d_pathS, const int32_t *d_countS, const double *d_pathG, const int32_t *d_countG,
                           int64_t cap, int npairs, double resolution, double *d_out, int32_t *d_count_out, void *stream);
 int fmb_path_post3d_f64(const double *d_paths, const int32_t *d_count, int64_t cap, int npaths, const double *scale3,

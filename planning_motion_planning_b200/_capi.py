@@ -103,6 +103,8 @@ SIGNATURES = {
                                         C.POINTER(C.POINTER(FmbPlan2DResult))]),
     "fmb_plan2d_free": (None, [C.POINTER(FmbPlan2DResult)]),
     "fmb_fields_differ_f64": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
+    "fmb_trace2d_logged_f64": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _dbl, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "fmb_windows_differ_f64": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _i64, _i64, _vp, _vp, _i32, _vp, _vp]),
     "fmb_workspace_bytes_2d_h2d": (_sz, [_i32, _i32]),
     "fmb_solve2d_h2d_f64": (C.c_int, [_vp, _vp, _i32, _i32, C.POINTER(C.c_int32), _vp, _vp, _sz, _vp, _vp]),
     "fmb_workspace_bytes_costvolume": (_sz, [_i32, _i32, _i32]),

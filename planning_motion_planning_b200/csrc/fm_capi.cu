@@ -652,9 +652,11 @@ int fmb_finish(void *d_ws, size_t ws_bytes, void *stream, fmb_stats *stats) {
     return FMB_OK;
 }
 
-int fmb_trace2d_f64(const double *d_T, int64_t T_pitch, int64_t T_qstride, int rows, int cols, int npaths,
-                    const int32_t *d_field_of_path, const double *d_init, const double *d_end, double tau,
-                    int max_steps, double *d_out, int64_t cap, int32_t *d_count, int32_t *d_status, void *stream) {
+namespace {
+int trace2d_impl(const double *d_T, int64_t T_pitch, int64_t T_qstride, int rows, int cols, int npaths,
+                 const int32_t *d_field_of_path, const double *d_init, const double *d_end, double tau,
+                 int max_steps, double *d_out, int64_t cap, int32_t *d_count, int32_t *d_status, int32_t *d_blocks,
+                 int32_t *d_nblocks, int cap_blocks, void *stream) {
     if (!d_T || !d_init || !d_end || !d_out || !d_count || !d_status) return fail(FMB_E_INVALID, "null pointer argument%s");
     if (rows < 2 || cols < 2 || npaths < 1 || max_steps < 0) return fail(FMB_E_INVALID, "bad shape%s");
     if (cap < (int64_t)max_steps + 2) return fail(FMB_E_INVALID, "cap must be >= max_steps + 2%s");
@@ -662,9 +664,41 @@ int fmb_trace2d_f64(const double *d_T, int64_t T_pitch, int64_t T_qstride, int r
     A.T = d_T; A.T_pitch = T_pitch; A.T_qstride = T_qstride; A.rows = rows; A.cols = cols; A.npaths = npaths;
     A.field_of_path = d_field_of_path; A.init = d_init; A.end = d_end; A.tau = tau; A.max_steps = max_steps;
     A.out = d_out; A.cap = cap; A.count = d_count; A.status = d_status;
+    A.blocks = d_blocks; A.nblocks = d_nblocks; A.cap_blocks = cap_blocks;
     constexpr int TW_ = 4;
     fmb::trace2d_kernel<double, TW_><<<(npaths + TW_ - 1) / TW_, TW_ * 32, TW_ * fmb::TRACE2D_SMEM_PER_WARP, (cudaStream_t)stream>>>(A);
     CK(cudaGetLastError(), "launch trace2d");
+    return FMB_OK;
+}
+}  // namespace
+
+int fmb_trace2d_f64(const double *d_T, int64_t T_pitch, int64_t T_qstride, int rows, int cols, int npaths,
+                    const int32_t *d_field_of_path, const double *d_init, const double *d_end, double tau,
+                    int max_steps, double *d_out, int64_t cap, int32_t *d_count, int32_t *d_status, void *stream) {
+    return trace2d_impl(d_T, T_pitch, T_qstride, rows, cols, npaths, d_field_of_path, d_init, d_end, tau, max_steps, d_out, cap,
+                        d_count, d_status, nullptr, nullptr, 0, stream);
+}
+int fmb_trace2d_logged_f64(const double *d_T, int64_t T_pitch, int64_t T_qstride, int rows, int cols, int npaths,
+                           const int32_t *d_field_of_path, const double *d_init, const double *d_end, double tau,
+                           int max_steps, double *d_out, int64_t cap, int32_t *d_count, int32_t *d_status,
+                           int32_t *d_blocks, int32_t *d_nblocks, int cap_blocks, void *stream) {
+    if (!d_blocks || !d_nblocks || cap_blocks < 1) return fail(FMB_E_INVALID, "bad block log%s");
+    return trace2d_impl(d_T, T_pitch, T_qstride, rows, cols, npaths, d_field_of_path, d_init, d_end, tau, max_steps, d_out, cap,
+                        d_count, d_status, d_blocks, d_nblocks, cap_blocks, stream);
+}
+int fmb_windows_differ_f64(const double *d_field, int64_t pitch, int rows, int cols, const double *h_field, int64_t hs_y, int64_t hs_x,
+                           const int32_t *d_blocks, const int32_t *d_nblocks, int cap_blocks, int32_t *d_flag, void *stream) {
+    if (!d_field || !h_field || !d_blocks || !d_nblocks || !d_flag || cap_blocks < 1) return fail(FMB_E_INVALID, "bad argument%s");
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, h_field) != cudaSuccess || pa.type != cudaMemoryTypeHost || pa.devicePointer != (void *)h_field) {
+        cudaGetLastError();
+        return fail(FMB_E_INVALID, "h_field must be page-locked host memory the device addresses by the same pointer%s");
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaMemsetAsync(d_flag, 0, sizeof(int32_t), st), "cudaMemsetAsync(flag)");
+    int blocks = cap_blocks < 2 * sm_count() ? cap_blocks : 2 * sm_count();
+    fmb::windows_differ_kernel<<<blocks, 128, 0, st>>>(d_field, pitch, rows, cols, h_field, hs_y, hs_x, d_blocks, d_nblocks, cap_blocks, d_flag);
+    CK(cudaGetLastError(), "launch windows_differ");
     return FMB_OK;
 }
 

@@ -36,6 +36,11 @@ struct TraceArgs2D {
     double *out;
     long long cap;
     int *count, *status;
+    // optional log of the field cells a path read (fmb_trace2d_logged_f64): origin node (bx, by) of every gradient block
+    // it staged -- all reads of a path lie in the (TB + 2)^2 windows of its blocks.  blocks [npaths][cap_blocks][2],
+    // nblocks [npaths] = number of blocks, cap_blocks + 1 when the log overflowed, -1 when the field is too small for blocks
+    int *blocks = nullptr, *nblocks = nullptr;
+    int cap_blocks = 0;
 };
 
 #ifndef FMB_HOST_EMU
@@ -184,6 +189,7 @@ __global__ void __launch_bounds__(WARPS * 32) trace2d_kernel(TraceArgs2D<real> A
     double cfi = -1.0, cfj = -1.0;                          // fast step: cell whose bilinear coefficients are cached
     double fx0 = 0, fx1 = 0, fx2 = 0, fx3 = 0, fy0 = 0, fy1 = 0, fy2 = 0, fy3 = 0;
     const double nd = (double)n, md = (double)m;
+    int n_logged = blocked ? 0 : -1;
 
     for (int step = 0; step < A.max_steps; ++step) {
         double nx = 0.0, ny = 0.0;
@@ -210,6 +216,12 @@ __global__ void __launch_bounds__(WARPS * 32) trace2d_kernel(TraceArgs2D<real> A
                     bx = min(max(i - (lnx > 0.0 ? TB - 3 : (lnx < 0.0 ? 1 : TB / 2 - 1)), 0), n - TB);
                     by = min(max(j - (lny > 0.0 ? TB - 3 : (lny < 0.0 ? 1 : TB / 2 - 1)), 0), m - TB);
                     load_gradient_block<real>(T, A.T_pitch, m, n, bx, by, sW, sG, lane);
+                    if (A.blocks) {
+                        if (n_logged < A.cap_blocks) {
+                            if (lane == 0) { int *e = A.blocks + ((long long)p * A.cap_blocks + n_logged) * 2; e[0] = bx; e[1] = by; }
+                            ++n_logged;
+                        } else n_logged = A.cap_blocks + 1;
+                    }
                     bxlo = (double)bx; bxhi = (double)(bx + TB - 2); bylo = (double)by; byhi = (double)(by + TB - 2);
                     inb = true;
                 }
@@ -309,7 +321,29 @@ __global__ void __launch_bounds__(WARPS * 32) trace2d_kernel(TraceArgs2D<real> A
         if (lane == 0) { out[2 * K] = ex; out[2 * K + 1] = ey; }
         ++K;
     }
-    if (lane == 0) { A.count[p] = (int)K; A.status[p] = status; }
+    if (lane == 0) { A.count[p] = (int)K; A.status[p] = status; if (A.nblocks) A.nblocks[p] = n_logged; }
+}
+
+// Bitwise comparison of a traced device field with a host array over the windows a path read (see TraceArgs2D::blocks):
+// one CTA per logged block.  h is DEVICE-ACCESSIBLE host memory (page-locked, unified addressing): the kernel reads the
+// ~(TB + 2)^2 values of a window over the bus, nothing else of the array moves.  Element (y, x) of the field sits at
+// h[y * hs_y + x * hs_x].  *flag |= 1 on any difference, on a log that overflowed or is missing.
+__global__ void windows_differ_kernel(const double *field, long long pitch, int rows, int cols, const double *h, long long hs_y,
+                                      long long hs_x, const int *blocks, const int *nblocks, int cap_blocks, int *flag) {
+    const int nb = nblocks[0];
+    if (nb < 0 || nb > cap_blocks) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicExch(flag, 1); return; }
+    int diff = 0;
+    for (int b = blockIdx.x; b < nb; b += gridDim.x) {
+        const int bx = blocks[2 * b], by = blocks[2 * b + 1];
+        for (int t = threadIdx.x; t < TWIN * TWIN; t += blockDim.x) {
+            const int wy = t / TWIN, wx = t - wy * TWIN;
+            const int y = min(max(by - 1 + wy, 0), rows - 1), x = min(max(bx - 1 + wx, 0), cols - 1);
+            const unsigned long long a = reinterpret_cast<const unsigned long long *>(field)[(long long)y * pitch + x];
+            const unsigned long long c = reinterpret_cast<const unsigned long long *>(h)[(long long)y * hs_y + (long long)x * hs_x];
+            diff |= a != c;
+        }
+    }
+    if (__syncthreads_or(diff) && threadIdx.x == 0) atomicExch(flag, 1);
 }
 
 }  // namespace fmb

@@ -122,11 +122,12 @@ def solve2d(cost: torch.Tensor, seeds, out: Optional[torch.Tensor] = None, nq: O
 
 
 def trace2d(T: torch.Tensor, init, end, tau: float = 0.5, field_of_path=None,
-            max_steps: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+            max_steps: Optional[int] = None, log_blocks: int = 0):
     """Gradient-descent paths over 2D field(s) (FastMarching.py:164-236).
 
     T (rows, cols) or (nf, rows, cols) float64; init/end (np, 2) [x, y] in cell units.
-    Returns (paths (np, cap, 2) float64, count (np,) int32, status (np,) int32).
+    Returns (paths (np, cap, 2) float64, count (np,) int32, status (np,) int32).  log_blocks > 0: also the log of the
+    field cells each path read (fmb_trace2d_logged_f64): (..., blocks (np, log_blocks, 2) int32, nblocks (np,) int32).
     """
     _require_cuda(T, "T")
     if T.dtype != torch.float64:
@@ -157,6 +158,15 @@ def trace2d(T: torch.Tensor, init, end, tau: float = 0.5, field_of_path=None,
     count = torch.empty(npaths, dtype=torch.int32, device=dev)
     status = torch.empty(npaths, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
+        if log_blocks > 0:
+            blocks = torch.empty((npaths, log_blocks, 2), dtype=torch.int32, device=dev)
+            nblocks = torch.empty(npaths, dtype=torch.int32, device=dev)
+            _capi.check(_capi.lib().fmb_trace2d_logged_f64(T.data_ptr(), cols, rows * cols, rows, cols, npaths,
+                                                           fop.data_ptr() if fop is not None else None,
+                                                           i.data_ptr(), e.data_ptr(), float(tau), max_steps,
+                                                           out.data_ptr(), cap, count.data_ptr(), status.data_ptr(),
+                                                           blocks.data_ptr(), nblocks.data_ptr(), int(log_blocks), _stream()))
+            return out, count, status, blocks, nblocks
         _capi.check(_capi.lib().fmb_trace2d_f64(T.data_ptr(), cols, rows * cols, rows, cols, npaths,
                                                 fop.data_ptr() if fop is not None else None,
                                                 i.data_ptr(), e.data_ptr(), float(tau), max_steps,

@@ -1051,6 +1051,17 @@ def test_dropin_tracer_reuses_the_device_field_only_if_unchanged(order):
     ref = O.getPathGDM(np.ascontiguousarray(T), s, np.array(goal, dtype=np.float64), 0.5)
     assert p.shape == ref.shape and np.abs(p - ref).max() < TOLP
     assert C.TRACE_STATS["reused"] == before["reused"] + 1 and C.TRACE_STATS["retraced"] == before["retraced"]
+    # an edit the path never looked at (far from every window of its gradient blocks) changes nothing the tracer reads:
+    # the kept device copy still serves, and the result is the oracle's path over the EDITED array
+    yy, xx = np.mgrid[20:n - 20:40, 20:n - 20:40]
+    far = np.array([np.min(np.hypot(p[:, 0] - x, p[:, 1] - y)) for y, x in zip(yy.ravel(), xx.ravel())])
+    fy, fx = int(yy.ravel()[far.argmax()]), int(xx.ravel()[far.argmax()])
+    assert far.max() > 60
+    T[fy - 3:fy + 3, fx - 3:fx + 3] += 1.0
+    p1 = FM.getPathGDM(T, s, goal, 0.5)
+    ref1 = O.getPathGDM(np.ascontiguousarray(T), s, np.array(goal, dtype=np.float64), 0.5)
+    assert p1.shape == ref1.shape and np.abs(p1 - ref1).max() < TOLP and np.array_equal(p1, p)
+    assert C.TRACE_STATS["reused"] == before["reused"] + 2 and C.TRACE_STATS["retraced"] == before["retraced"]
     # the caller edits the array in place: a wall with one gap far from the old path
     mid = int(p[len(p) // 2, 1])
     T[mid, :] = np.inf
