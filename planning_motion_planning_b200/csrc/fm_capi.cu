@@ -579,10 +579,12 @@ int fmb_solve2d_h2d_f64(const double *h_cost, double *d_cost, int rows, int cols
     int *flags = (int *)(ws + o);
     const int sh = band_shift_for(rows), band_rows = 1 << sh, nb = (rows + band_rows - 1) >> sh;
     const int gb = goal_xy[1] >> sh;
-    cudaEvent_t e0, e1, e2;
-    CK(cudaEventCreateWithFlags(&e0, cudaEventDisableTiming), "cudaEventCreate");
-    CK(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming), "cudaEventCreate");
-    CK(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming), "cudaEventCreate");
+    struct Events {                              // released on every return path (destroying a recorded event is deferred by the runtime)
+        cudaEvent_t e[3] = {nullptr, nullptr, nullptr};
+        ~Events() { for (cudaEvent_t x : e) if (x) cudaEventDestroy(x); }
+    } ev;
+    for (cudaEvent_t &x : ev.e) CK(cudaEventCreateWithFlags(&x, cudaEventDisableTiming), "cudaEventCreate");
+    cudaEvent_t e0 = ev.e[0], e1 = ev.e[1], e2 = ev.e[2];
     // Every copy and every flag write is queued BEFORE the solve is launched: where streams do not overlap (a serialising
     // profiler, CUDA_LAUNCH_BLOCKING) the kernel then finds all flags set instead of waiting for work queued behind it.
     CK(cudaMemsetAsync(flags, 0, sizeof(int) * (size_t)nb, st), "cudaMemsetAsync(band flags)");
@@ -605,7 +607,6 @@ int fmb_solve2d_h2d_f64(const double *h_cost, double *d_cost, int rows, int cols
     int rc = solve2d<double>(d_cost, cols, 0, d_T, cols, (int64_t)rows * cols, rows, cols, 1, seeds, d_ws, solve_bytes, stream, -1, 0,
                              flags, sh);
     CK(cudaStreamWaitEvent(st, e2, 0), "cudaStreamWaitEvent");        // d_cost is complete for whatever follows on `stream`
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
     return rc;
 }
 
