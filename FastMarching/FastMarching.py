@@ -34,20 +34,6 @@ def getEikonal(Thor, Tver, cost):
     return .5 * (Thor + Tver + math.sqrt(2 * np.square(cost) - np.square(Thor - Tver)))
 
 
-def _device_map(costMap, nodes):
-    """(device copy of the map in C order, swap, nodes in the device map's orientation)."""
-    c, swap = _c.as_c_field(costMap)
-    rows, cols = c.shape
-    out = []
-    for k, p in enumerate(nodes):
-        q = _c.node2(p, swap)
-        if k == 0:
-            _c.check_node2(q, rows, cols)
-        out.append(q)
-    dev = _c.device()
-    return _c.to_device(np.ascontiguousarray(c), dev), swap, out, dev
-
-
 def _to_numpy_field(Tt: torch.Tensor, swap: bool) -> np.ndarray:
     a = _c.to_host(Tt, keep_device=True)
     return a.T if swap else a          # .T of a C array is F-ordered, like zeros_like() of the planner's view
@@ -90,16 +76,24 @@ def biComputeTmap(costMap, goal, start):
     FastMarching.py:114-162.  Returns ``(TmapG, TmapS, nodeJoin)`` with ``nodeJoin`` a
     ``np.uint32[2]`` ``[x, y]``.  Raises ``NameError`` when the fronts never meet, like the
     reference (:161).  One library call (fmb_bisolve2d_f64); the S front's ranks and replay run on a second stream."""
-    cd, swap, (g, s), dev = _device_map(costMap, [goal, start])
-    _c.check_node2(s, *cd.shape)
-    TG, TS, info, ws = _c.bisolve2d(cd, g, s, swap)
+    c, swap = _c.as_c_field(costMap)
+    c = np.ascontiguousarray(c)
+    g, s = _c.node2(goal, swap), _c.node2(start, swap)
+    _c.check_node2(g, *c.shape)
+    _c.check_node2(s, *c.shape)
+    dev = _c.device()
+    pinned = _c.is_page_locked(c)
+    if pinned and _c.H2D_OVERLAP:
+        TG, TS, info, ws = _c.bisolve2d(c, g, s, swap, dev)          # the map's upload runs in bands behind the two solves
+    else:
+        TG, TS, info, ws = _c.bisolve2d(_c.to_device(c, dev, pinned=pinned), g, s, swap)
     _c.finish(ws, dev)                                  # synchronises; device-side failures of the solve surface here
     inf = info.tolist()
     k, j = inf[0], inf[1]
     if k == 0x7fffffff:
         raise NameError("name 'nodeJoin' is not defined")
     _c.check_info(inf, fronts=2)
-    jy, jx = divmod(j, cd.shape[1])
+    jy, jx = divmod(j, c.shape[1])
     node = (jy, jx) if swap else (jx, jy)
     return _to_numpy_field(TG, swap), _to_numpy_field(TS, swap), np.uint32(node)
 

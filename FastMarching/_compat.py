@@ -387,11 +387,14 @@ def bi_join(rankG: torch.Tensor, rankS: torch.Tensor):
     return (None, None) if k == big else (k, j)
 
 
-def bisolve2d(cd: torch.Tensor, goal, start, transposed: bool):
+def bisolve2d(cd, goal, start, transposed: bool, dev: torch.device = None):
     """fmb_bisolve2d_f64: (TG, TS, info) -- both partial fields of biComputeTmap on the device and the int32[16] info
-    tensor (k, join cell, statuses), still on the device: nothing here synchronises."""
+    tensor (k, join cell, statuses), still on the device: nothing here synchronises.  cd: the map on the device, or -- a
+    page-locked C-contiguous NumPy array -- still on the host: its upload then runs in bands on the side stream behind
+    the two solves that consume it (fmb_bisolve2d_h2d_f64)."""
+    on_host = isinstance(cd, np.ndarray)
     rows, cols = cd.shape
-    dev = cd.device
+    dev = cd.device if not on_host else dev
     L = _capi.lib()
     ws = _ws(L.fmb_workspace_bytes_bisolve2d(rows, cols), dev, "bisolve")
     out = torch.empty((2, rows, cols), dtype=torch.float64, device=dev)
@@ -400,9 +403,16 @@ def bisolve2d(cd: torch.Tensor, goal, start, transposed: bool):
     side = _side_stream(dev)
     side.wait_stream(cur)
     with torch.cuda.device(dev):
-        _capi.check(L.fmb_bisolve2d_f64(cd.data_ptr(), rows, cols, _i32(goal), _i32(start), int(bool(transposed)),
-                                        out[0].data_ptr(), out[1].data_ptr(), info.data_ptr(), ws.data_ptr(), ws.numel(),
-                                        cur.cuda_stream, side.cuda_stream))
+        if on_host:
+            cdev = torch.empty((rows, cols), dtype=torch.float64, device=dev)
+            _capi.check(L.fmb_bisolve2d_h2d_f64(cd.ctypes.data, cdev.data_ptr(), rows, cols, _i32(goal), _i32(start), int(bool(transposed)),
+                                                out[0].data_ptr(), out[1].data_ptr(), info.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                cur.cuda_stream, side.cuda_stream))
+            cdev.record_stream(side)
+        else:
+            _capi.check(L.fmb_bisolve2d_f64(cd.data_ptr(), rows, cols, _i32(goal), _i32(start), int(bool(transposed)),
+                                            out[0].data_ptr(), out[1].data_ptr(), info.data_ptr(), ws.data_ptr(), ws.numel(),
+                                            cur.cuda_stream, side.cuda_stream))
     return out[0], out[1], info, ws
 
 

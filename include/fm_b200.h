@@ -390,6 +390,11 @@ int fmb_pop_ranks_status(const void *d_ws, void *stream, int32_t *out4);
 size_t fmb_workspace_bytes_bisolve2d(int rows, int cols);
 int fmb_bisolve2d_f64(const double *d_cost, int rows, int cols, const int32_t *goal_xy, const int32_t *start_xy, int32_t transposed,
                       double *d_TG, double *d_TS, int32_t *d_join, void *d_ws, size_t ws_bytes, void *stream, void *stream2);
+/* The same with the cost map still on the host: h_cost = dense [rows][cols] PAGE-LOCKED host memory, uploaded into d_cost
+ * in bands of rows on stream2 (required, != stream) behind the two solves that consume it (see fmb_solve2d_h2d_f64). */
+int fmb_bisolve2d_h2d_f64(const double *h_cost, double *d_cost, int rows, int cols, const int32_t *goal_xy, const int32_t *start_xy,
+                          int32_t transposed, double *d_TG, double *d_TS, int32_t *d_join, void *d_ws, size_t ws_bytes, void *stream,
+                          void *stream2);
 /* Single front with the reference's early exit in ONE call: FastMarching.py:92-112 (as intended) / FastMarching3D.py:126-145.
  * The partial field after `start` is accepted; the full field when start is outside the array, unreached, or == goal
  * (closed before the loop, never popped).  3D: the fast solve decides where it can -- the field in the reference's own

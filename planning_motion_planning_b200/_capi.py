@@ -95,6 +95,7 @@ SIGNATURES = {
     "fmb_pop_ranks_status": (C.c_int, [_vp, _vp, C.POINTER(C.c_int32)]),
     "fmb_workspace_bytes_bisolve2d": (_sz, [_i32, _i32]),
     "fmb_bisolve2d_f64": (C.c_int, [_vp, _i32, _i32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _i32, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "fmb_bisolve2d_h2d_f64": (C.c_int, [_vp, _vp, _i32, _i32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _i32, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
     "fmb_workspace_bytes_until2d": (_sz, [_i32, _i32]),
     "fmb_workspace_bytes_until3d": (_sz, [_i32, _i32, _i32]),
     "fmb_solve2d_until_f64": (C.c_int, [_vp, _i32, _i32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _i32, _vp, _vp, _vp, _sz, _vp]),

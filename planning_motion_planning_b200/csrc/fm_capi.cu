@@ -431,8 +431,8 @@ int solve2d(const real *d_cost, int64_t cost_pitch, int64_t cost_qstride, real *
     P.hop_frac = O.ring2 > 0 ? 0.01 * O.ring2 : (O.ring2 < 0 ? 0.0 : 2.0);
     P.variant = O.variant > 0 ? O.variant : (O.variant < 0 ? 0 : 3);
     P.band_ready = band_ready; P.band_shift = band_shift;
-    if (band_ready && !(engine == 3 && !P.best_first && nq == 1 && resume_activate < 0))
-        return fail(FMB_E_INVALID, "a solve on a cost map that is still arriving needs the sweep engine on one map%s");
+    if (band_ready && !(engine == 3 && !P.best_first && (nq == 1 || cost_qstride == 0) && resume_activate < 0))
+        return fail(FMB_E_INVALID, "a solve on a cost map that is still arriving needs the sweep engine on one (shared) map%s");
     P.slack_frac = O.causal_slack > 0 ? 0.01 * O.causal_slack : 0.0;      // measured 4096^2: 10.4 / 10.6 / 11.9 / 15.9 ms at 0 / 25 / 50 / 100 %
     cudaStream_t st = (cudaStream_t)stream;
     if (engine >= 4 && resume_activate < 0) {
@@ -553,17 +553,18 @@ int *pinned_one() {
     if (!one) { if (cudaHostAlloc((void **)&one, sizeof(int), cudaHostAllocDefault) != cudaSuccess) { one = nullptr; cudaGetLastError(); } else *one = 1; }
     return one;
 }
-}  // namespace
-size_t fmb_workspace_bytes_2d_h2d(int rows, int cols) {
-    if (rows < 1 || cols < 1) return 0;
-    return ((fmb_workspace_bytes_2d(rows, cols, 1) + 255) & ~(size_t)255) + 256 + 4 * (size_t)((rows >> 5) + 2) + 256;
-}
-int fmb_solve2d_h2d_f64(const double *h_cost, double *d_cost, int rows, int cols, const int32_t *goal_xy, double *d_T,
-                        void *d_ws, size_t ws_bytes, void *stream, void *copy_stream) {
-    if (!h_cost || !d_cost || !goal_xy || !d_T || !d_ws || !copy_stream) return fail(FMB_E_INVALID, "null pointer argument%s");
-    if (rows < 1 || cols < 1) return fail(FMB_E_INVALID, "bad shape%s");
-    if (goal_xy[0] < 0 || goal_xy[0] >= cols || goal_xy[1] < 0 || goal_xy[1] >= rows) return fail(FMB_E_INVALID, "goal outside the map%s");
-    if (ws_bytes < fmb_workspace_bytes_2d_h2d(rows, cols)) return fail(FMB_E_WORKSPACE, "workspace too small%s");
+struct BandEvents {                              // released on every return path (destroying a recorded event is deferred by the runtime)
+    cudaEvent_t e[3] = {nullptr, nullptr, nullptr};
+    ~BandEvents() { for (cudaEvent_t x : e) if (x) cudaEventDestroy(x); }
+};
+size_t band_flag_bytes(int rows) { return 4 * (size_t)((rows >> 5) + 2) + 256; }
+// Queues the upload of a page-locked host map in bands of rows on the copy stream `cs`, each band followed by the write of
+// its device flag: first the bands that hold the seed rows (event e[1] marks their arrival: the seed kernel reads the cost
+// there), then the others by their distance from the nearest seed; e[2] marks the end.  The flags are cleared on `st` first
+// (e[0]).  Every copy is queued BEFORE the caller launches the solve: where streams do not overlap (a serialising
+// profiler, CUDA_LAUNCH_BLOCKING) the kernel then finds all flags set instead of waiting for work queued behind it.
+int enqueue_band_upload(const double *h_cost, double *d_cost, int rows, int cols, const int *seed_rows, int nseeds, int *flags,
+                        cudaStream_t st, cudaStream_t cs, BandEvents &ev, int *shift_out) {
     cudaPointerAttributes pa;
     if (cudaPointerGetAttributes(&pa, h_cost) != cudaSuccess || pa.type != cudaMemoryTypeHost) {
         cudaGetLastError();
@@ -571,42 +572,60 @@ int fmb_solve2d_h2d_f64(const double *h_cost, double *d_cost, int rows, int cols
     }
     int *one = pinned_one();
     if (!one) return fail(FMB_E_CUDA, "cudaHostAlloc(flag source) failed%s");
+    const int sh = band_shift_for(rows), band_rows = 1 << sh, nb = (rows + band_rows - 1) >> sh;
+    *shift_out = sh;
+    for (cudaEvent_t &x : ev.e) CK(cudaEventCreateWithFlags(&x, cudaEventDisableTiming), "cudaEventCreate");
+    CK(cudaMemsetAsync(flags, 0, sizeof(int) * (size_t)nb, st), "cudaMemsetAsync(band flags)");
+    CK(cudaEventRecord(ev.e[0], st), "cudaEventRecord");
+    CK(cudaStreamWaitEvent(cs, ev.e[0], 0), "cudaStreamWaitEvent");
+    std::vector<char> sent((size_t)nb, 0);
+    auto send = [&](int b) -> int {
+        if (b < 0 || b >= nb || sent[b]) return FMB_OK;
+        sent[b] = 1;
+        const int r0 = b << sh, nr = (r0 + band_rows <= rows) ? band_rows : rows - r0;
+        CK(cudaMemcpyAsync(d_cost + (size_t)r0 * cols, h_cost + (size_t)r0 * cols, sizeof(double) * (size_t)nr * cols,
+                           cudaMemcpyHostToDevice, cs), "cudaMemcpyAsync(cost band)");
+        CK(cudaMemcpyAsync(flags + b, one, sizeof(int), cudaMemcpyHostToDevice, cs), "cudaMemcpyAsync(band flag)");
+        return FMB_OK;
+    };
+    for (int k = 0; k < nseeds; ++k) { const int rc = send(seed_rows[k] >> sh); if (rc) return rc; }
+    CK(cudaEventRecord(ev.e[1], cs), "cudaEventRecord");
+    for (int d = 0; d < nb; ++d)                 // rings of bands around every seed: b + 1, b - 1, b + 2, ... (a front's next
+        for (int k = 0; k < nseeds; ++k) {       // rows arrive before it needs them, whichever seed it started from)
+            const int b = seed_rows[k] >> sh;
+            int rc = send(b + d); if (rc) return rc;
+            rc = send(b - d); if (rc) return rc;
+        }
+    CK(cudaEventRecord(ev.e[2], cs), "cudaEventRecord");
+    return FMB_OK;
+}
+}  // namespace
+size_t fmb_workspace_bytes_2d_h2d(int rows, int cols) {
+    if (rows < 1 || cols < 1) return 0;
+    return ((fmb_workspace_bytes_2d(rows, cols, 1) + 255) & ~(size_t)255) + 256 + band_flag_bytes(rows);
+}
+int fmb_solve2d_h2d_f64(const double *h_cost, double *d_cost, int rows, int cols, const int32_t *goal_xy, double *d_T,
+                        void *d_ws, size_t ws_bytes, void *stream, void *copy_stream) {
+    if (!h_cost || !d_cost || !goal_xy || !d_T || !d_ws || !copy_stream) return fail(FMB_E_INVALID, "null pointer argument%s");
+    if (rows < 1 || cols < 1) return fail(FMB_E_INVALID, "bad shape%s");
+    if (goal_xy[0] < 0 || goal_xy[0] >= cols || goal_xy[1] < 0 || goal_xy[1] >= rows) return fail(FMB_E_INVALID, "goal outside the map%s");
+    if (ws_bytes < fmb_workspace_bytes_2d_h2d(rows, cols)) return fail(FMB_E_WORKSPACE, "workspace too small%s");
     cudaStream_t st = (cudaStream_t)stream, cs = (cudaStream_t)copy_stream;
     char *ws = (char *)d_ws;
     const size_t solve_bytes = fmb_workspace_bytes_2d(rows, cols, 1);
     size_t o = (solve_bytes + 255) & ~(size_t)255;
     int32_t *seeds = (int32_t *)(ws + o); o += 256;
     int *flags = (int *)(ws + o);
-    const int sh = band_shift_for(rows), band_rows = 1 << sh, nb = (rows + band_rows - 1) >> sh;
-    const int gb = goal_xy[1] >> sh;
-    struct Events {                              // released on every return path (destroying a recorded event is deferred by the runtime)
-        cudaEvent_t e[3] = {nullptr, nullptr, nullptr};
-        ~Events() { for (cudaEvent_t x : e) if (x) cudaEventDestroy(x); }
-    } ev;
-    for (cudaEvent_t &x : ev.e) CK(cudaEventCreateWithFlags(&x, cudaEventDisableTiming), "cudaEventCreate");
-    cudaEvent_t e0 = ev.e[0], e1 = ev.e[1], e2 = ev.e[2];
-    // Every copy and every flag write is queued BEFORE the solve is launched: where streams do not overlap (a serialising
-    // profiler, CUDA_LAUNCH_BLOCKING) the kernel then finds all flags set instead of waiting for work queued behind it.
-    CK(cudaMemsetAsync(flags, 0, sizeof(int) * (size_t)nb, st), "cudaMemsetAsync(band flags)");
+    BandEvents ev;
+    int sh = 0;
+    const int seed_row = goal_xy[1];
+    int rc = enqueue_band_upload(h_cost, d_cost, rows, cols, &seed_row, 1, flags, st, cs, ev, &sh);
+    if (rc) return rc;
     CK(cudaMemcpyAsync(seeds, goal_xy, 2 * sizeof(int32_t), cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(seeds)");
-    CK(cudaEventRecord(e0, st), "cudaEventRecord");
-    CK(cudaStreamWaitEvent(cs, e0, 0), "cudaStreamWaitEvent");
-    for (int d = 0; d < nb; ++d) {               // bands by distance from the goal's band: gb, gb + 1, gb - 1, gb + 2, ...
-        for (int sgn = 0; sgn < (d ? 2 : 1); ++sgn) {
-            const int b = sgn ? gb - d : gb + d;
-            if (b < 0 || b >= nb) continue;
-            const int r0 = b << sh, nr = (r0 + band_rows <= rows) ? band_rows : rows - r0;
-            CK(cudaMemcpyAsync(d_cost + (size_t)r0 * cols, h_cost + (size_t)r0 * cols, sizeof(double) * (size_t)nr * cols,
-                               cudaMemcpyHostToDevice, cs), "cudaMemcpyAsync(cost band)");
-            CK(cudaMemcpyAsync(flags + b, one, sizeof(int), cudaMemcpyHostToDevice, cs), "cudaMemcpyAsync(band flag)");
-            if (d == 0) CK(cudaEventRecord(e1, cs), "cudaEventRecord");
-        }
-    }
-    CK(cudaEventRecord(e2, cs), "cudaEventRecord");
-    CK(cudaStreamWaitEvent(st, e1, 0), "cudaStreamWaitEvent");        // the seed kernel reads the cost at the goal
-    int rc = solve2d<double>(d_cost, cols, 0, d_T, cols, (int64_t)rows * cols, rows, cols, 1, seeds, d_ws, solve_bytes, stream, -1, 0,
-                             flags, sh);
-    CK(cudaStreamWaitEvent(st, e2, 0), "cudaStreamWaitEvent");        // d_cost is complete for whatever follows on `stream`
+    CK(cudaStreamWaitEvent(st, ev.e[1], 0), "cudaStreamWaitEvent");        // the seed kernel reads the cost at the goal
+    rc = solve2d<double>(d_cost, cols, 0, d_T, cols, (int64_t)rows * cols, rows, cols, 1, seeds, d_ws, solve_bytes, stream, -1, 0,
+                         flags, sh);
+    CK(cudaStreamWaitEvent(st, ev.e[2], 0), "cudaStreamWaitEvent");        // d_cost is complete for whatever follows on `stream`
     return rc;
 }
 

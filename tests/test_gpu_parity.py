@@ -1108,8 +1108,15 @@ def test_dropin_pagelocks_a_callers_array_on_reuse():
     c[300:340, 100:500] = np.inf                            # the caller edits its map in place
     T3 = FM.computeTmap(c, goal, [-1, -1])
     assert rel_err(T3, O.computeTmap(c, goal)) < TOL64 and not np.array_equal(np.isfinite(T3), np.isfinite(T2))
-    TG, TS, jn = FM.biComputeTmap(c, goal, list(synth.free_cell_near(c, 100, 560)))
-    assert np.isfinite(TG[jn[1], jn[0]]) and np.isfinite(TS[jn[1], jn[0]])
+    start = list(synth.free_cell_near(c, 100, 560))
+    TG, TS, jn = FM.biComputeTmap(c, goal, start)          # page-locked map: uploaded in bands behind the two solves
+    oTG, oTS, oj = O.biComputeTmap(c, goal, start)
+    assert list(jn) == list(oj) and rel_err(TG, oTG) < TOL64 and rel_err(TS, oTS) < TOL64
+    cf = np.asfortranarray(c)                               # the planner's F-ordered view, twice: the second call overlaps
+    for _ in range(2):
+        TGf, TSf, jf = FM.biComputeTmap(cf, goal, start)
+        assert list(jf) == list(oj) and rel_err(np.ascontiguousarray(TGf), oTG) < TOL64 and rel_err(np.ascontiguousarray(TSf), oTS) < TOL64
+    del cf
     del c
     gc.collect()
     assert len(C._REGISTERED) == n0
