@@ -72,7 +72,8 @@ def to_device(a: np.ndarray, dev: torch.device, pinned=None) -> torch.Tensor:
 
 
 # A caller's array that comes in a SECOND time (goal sweeps over one cost map, a planner that re-plans on the same map)
-# is page-locked in place with cudaHostRegister (one-off cost of a few tens of ms for 128 MiB) and from then on
+# is page-locked in place with cudaHostRegister (one-off cost: 10-16 ms for 128 MiB, tools/gpu_hostregister_cost.py -- more
+# than the 5.8 ms of one staged upload, which is why a first sighting is not registered) and from then on
 # uploaded with one DMA at PCIe speed instead of through the staging copy (4096^2: 5.8 -> 2.5 ms per call).  The
 # registration ends when the array is garbage-collected; at most _REG_MAX arrays / _REG_BYTES_MAX bytes are held.
 _SEEN = {}                         # id(root array) -> weakref to it
