@@ -28,8 +28,9 @@ def device() -> torch.device:
 # at 3-4 GB/s; through page-locked memory it moves at PCIe speed.  So: uploads are staged chunk-wise through four small
 # pinned buffers (the memcpy of chunk k+1 overlaps the DMA of chunk k), and results are downloaded straight into a
 # pinned tensor whose memory backs the returned NumPy array (owned by the caller through the array's base).  An array
-# that came from here is recognised as pinned on its way back in (getPathGDM on a field biComputeTmap returned) and
-# uploaded with one DMA.
+# that came from here is recognised on its way back in (getPathGDM on a field biComputeTmap returned): the tracer runs
+# on the device copy that was kept of it and only the windows the path read are checked against the array, in place
+# (trace_field2d below); where it has to be uploaded after all, one DMA does it.
 # fmb_solve2d_h2d_f64 (upload overlapped with the solve) can be switched off, e.g. under a profiler that replays kernels
 # and restores device memory in between (the solve waits on flags the copy stream sets): FMB_H2D_OVERLAP=0
 H2D_OVERLAP = os.environ.get("FMB_H2D_OVERLAP", "1") != "0"
