@@ -226,11 +226,40 @@ def reference_arm(args):
     crop[0, :] = crop[-1, :] = crop[:, 0] = crop[:, -1] = np.inf
     for _ in range(max(1, args.warmup)):
         O.computeTmap(crop, [small // 4, small // 4])
+    # K steps of `threads` full-size queries each -- unless that would take more than a few minutes (a driver that asks for
+    # many steps): then the steps after the first run on a centred crop of the same map (same algorithm, same threads;
+    # crops are cache-friendlier, which only flatters this arm), sized so that the whole run stays within the budget
+    budget_s, cells_done, crop_note = float(os.environ.get("FMB_REF_BUDGET_S", "150")), 0, ""
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step(nq, threads)
+    step(nq, threads)
+    t_first = time.perf_counter() - t0
+    cells_done += nq * n * n
+    m = n
+    if args.steps > 1 and t_first * args.steps > budget_s:
+        while m > 256 and t_first * (m / n) ** 2 * (args.steps - 1) > budget_s - t_first:
+            m //= 2
+    if m < n:
+        lo = (n - m) // 2
+        cc = np.ascontiguousarray(c[lo:lo + m, lo:lo + m]).copy()
+        cc[0, :] = cc[-1, :] = cc[:, 0] = cc[:, -1] = np.inf
+        from planning_motion_planning_b200 import synth as _synth
+        gq, sq = _synth.free_cell_near(cc, m // 4, m // 4), _synth.free_cell_near(cc, 3 * m // 4, 3 * m // 4)
+
+        def one_crop(i):
+            T = O.computeTmap(cc, gq)
+            O.getPathGDM(T, np.array(sq), gq, 0.5, return_status=True)
+
+        for _ in range(args.steps - 1):
+            with ThreadPoolExecutor(max_workers=threads) as ex:
+                list(ex.map(one_crop, range(nq)))
+            cells_done += nq * m * m
+        crop_note = f"; steps 2..{args.steps} on a centred {m}x{m} crop to stay within {int(budget_s)} s"
+    else:
+        for _ in range(args.steps - 1):
+            step(nq, threads)
+            cells_done += nq * n * n
     total = time.perf_counter() - t0
-    value = nq * n * n * args.steps / total
+    value = cells_done / total
     # context 1: one query on one thread (the latency a single caller of the reference path sees)
     t0 = time.perf_counter()
     step(1, 1)
@@ -245,7 +274,7 @@ def reference_arm(args):
     O.getPathGDM(TS, np.array(j, dtype=np.float64), s_bi, 0.5)
     bi_s = time.perf_counter() - t0
     sample = (f"{nq} full {n}x{n} solve(s) + path per step, one host thread per query, all at a time "
-              f"({threads} of {cores} cores; C port of FastMarching.py heap FMM + tracer)")
+              f"({threads} of {cores} cores; C port of FastMarching.py heap FMM + tracer){crop_note}")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
